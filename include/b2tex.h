@@ -1,0 +1,171 @@
+/*
+ * b2tex.h -- C ABI of the B200-native mvs-texturing hot path (libb2tex.so).
+ *
+ * Drop-in boundary: the reference exposes this path as four C++ free functions in
+ * libs/tex/texturing.h; each entry point below replaces one of them and is what a maintainer's
+ * binding (mvs-texturing_b200/tex/ for the C++ veneer that keeps the tex::
+ * signatures) calls:
+ *
+ *   tex::calculate_data_costs   libs/tex/texturing.h:66-69  -> b2tex_calculate_data_costs
+ *   tex::view_selection         libs/tex/texturing.h:79-80  -> b2tex_view_selection
+ *   tex::global_seam_leveling   libs/tex/texturing.h:97-101 -> b2tex_global_seam_leveling
+ *   (build_adjacency_graph      libs/tex/texturing.h:59-61  input of view_selection, passed as CSR)
+ *
+ * Plain pointers and sizes only; host buffers are owned by the caller, device memory by the
+ * library.  Every function returns 0 on success and a non-zero status otherwise;
+ * b2tex_last_error() returns a thread-local message (the C++ veneer turns it into the
+ * std::runtime_error the reference throws, calculate_data_costs.cpp:315-318,
+ * view_selection.cpp:126-128).  There is no CPU fallback: without a CUDA device every entry
+ * point fails with B2TEX_ERR_CUDA.
+ */
+#ifndef B2TEX_H
+#define B2TEX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2TEX_OK 0
+#define B2TEX_ERR_CUDA 1      /* CUDA runtime error / no device */
+#define B2TEX_ERR_LIMITS 2    /* "Exeeded maximal number of faces/views" (calculate_data_costs.cpp:315-318) */
+#define B2TEX_ERR_ARG 3       /* bad argument / stage prerequisites missing */
+#define B2TEX_ERR_LABELING 4  /* "Incorrect labeling" (view_selection.cpp:126-128) */
+#define B2TEX_ERR_UNSUPPORTED 5
+
+/* tex::TextureView camera + image (libs/tex/texture_view.h:39-52) as POD */
+typedef struct {
+    float pos[3];        /* camera centre, world */
+    float viewdir[3];    /* viewing direction, world */
+    float proj[9];       /* calibration, row major 3x3 (pixels) */
+    float w2c[16];       /* world_to_cam, row major 4x4 */
+    int32_t width, height;
+    const uint8_t *rgb;  /* H x W x 3 interleaved, host memory */
+} b2tex_view;
+
+/* the fields of tex::Settings the path reads (libs/tex/settings.h:82-94) */
+typedef struct {
+    int32_t data_term;                 /* 0 DATA_TERM_AREA, 1 DATA_TERM_GMI */
+    int32_t outlier_removal;           /* 0 NONE (others: B2TEX_ERR_UNSUPPORTED) */
+    int32_t geometric_visibility_test; /* bool */
+} b2tex_settings;
+
+typedef struct {
+    uint64_t nnz;          /* DataCosts entries */
+    uint64_t candidates;   /* (face,view) pairs that passed culling + projection */
+    uint64_t rays;         /* distinct (vertex,view) visibility rays traced */
+    float max_quality;     /* calculate_data_costs.cpp:304 */
+    float percentile;      /* calculate_data_costs.cpp:305 */
+} b2tex_dc_info;
+
+/* mapMAP control as configured at view_selection.cpp:84,103-115, mapped onto the forest-BCD solver */
+typedef struct {
+    uint32_t max_iterations;
+    uint32_t rounds;       /* forest growth rounds per iteration */
+    uint32_t root_div;     /* one root candidate per root_div nodes; 0 = single root */
+    uint32_t seed;         /* initial_seed */
+    uint32_t window;       /* StopWhenReturnsDiminish(window, ratio) */
+    float ratio;
+    uint32_t num_parts;    /* logical face partitions (>=1); >1 reproduces the multi-GPU schedule */
+} b2tex_mrf_params;
+
+typedef struct {
+    uint32_t iterations;
+    double energy_initial;
+    double energy_final;
+    uint64_t unseen;       /* "faces have not been seen" view_selection.cpp:132 */
+    uint64_t sweep_bytes;  /* algorithmic bytes of one sweep: 14 nnz + 20 F */
+} b2tex_mrf_info;
+
+typedef struct {
+    uint32_t num_rows;       /* Lhs dimensionality, global_seam_leveling.cpp:253 */
+    uint32_t num_a_rows;
+    uint32_t num_gamma_rows;
+    uint64_t nnz_full;       /* non-zeros of the full symmetric Lhs */
+    uint32_t iterations[3];  /* cg.iterations() per colour channel, :280 */
+    float residual[3];       /* cg.error() per colour channel, :281 */
+    uint32_t cg_launch_iterations; /* iterations executed by the batched kernel = max over channels */
+    float cg_ms;             /* device time of the PCG kernel (CUDA events) */
+} b2tex_seam_info;
+
+typedef struct b2tex_ctx b2tex_ctx;
+
+/* ---- lifetime ---- */
+int b2tex_create(int device, b2tex_ctx **out);
+void b2tex_destroy(b2tex_ctx *ctx);
+const char *b2tex_last_error(void);
+void b2tex_free(void *host_ptr);                 /* frees buffers returned by one-shot calls */
+int b2tex_device_synchronize(b2tex_ctx *ctx);
+void b2tex_default_mrf_params(b2tex_mrf_params *p);
+
+/* ---- resident API: upload once, run stages on the device, download results ---- */
+int b2tex_set_mesh(b2tex_ctx *ctx, const float *verts, uint32_t num_verts, const uint32_t *faces,
+                   const float *face_normals, uint32_t num_faces);
+int b2tex_set_views(b2tex_ctx *ctx, const b2tex_view *views, uint32_t num_views);
+int b2tex_set_adjacency(b2tex_ctx *ctx, const uint32_t *adj_ptr, const uint32_t *adj_idx);
+int b2tex_set_vertex_rings(b2tex_ctx *ctx, const uint32_t *vf_ptr, const uint32_t *vf_idx,
+                           const uint32_t *vv_ptr, const uint32_t *vv_idx);
+int b2tex_set_data_costs(b2tex_ctx *ctx, const uint64_t *face_ptr, const uint16_t *view,
+                         const float *cost);
+int b2tex_set_labels(b2tex_ctx *ctx, const uint32_t *labels);
+/* restrict this context to faces [face_begin, face_end) for the data-cost stage (multi-GPU shard);
+ * default is all faces */
+int b2tex_set_face_range(b2tex_ctx *ctx, uint32_t face_begin, uint32_t face_end);
+
+int b2tex_data_costs_run(b2tex_ctx *ctx, const b2tex_settings *settings, b2tex_dc_info *info);
+/* split form of the normalisation for sharded runs (calculate_data_costs.cpp:277-302):
+ * qualities -> [allreduce max] -> histogram -> [allreduce sum] -> normalise */
+int b2tex_data_costs_qualities(b2tex_ctx *ctx, const b2tex_settings *settings, b2tex_dc_info *info);
+int b2tex_data_costs_histogram(b2tex_ctx *ctx, float global_max, uint32_t *bins10000_device_or_host,
+                               int to_host);
+int b2tex_data_costs_normalize(b2tex_ctx *ctx, float global_max, const uint32_t *bins10000_host,
+                               b2tex_dc_info *info);
+int b2tex_data_costs_download(b2tex_ctx *ctx, uint64_t *face_ptr, uint16_t *view, float *cost,
+                              float *quality_or_null);
+
+int b2tex_view_selection_run(b2tex_ctx *ctx, const b2tex_mrf_params *params, b2tex_mrf_info *info,
+                             double *energy_trace_or_null);
+int b2tex_labels_download(b2tex_ctx *ctx, uint32_t *labels);
+/* building blocks of one solver iteration, exposed so that a sharded run can exchange boundary
+ * labels between iterations; view_selection_run = init + loop(iterate, energy) */
+int b2tex_mrf_init(b2tex_ctx *ctx, const b2tex_mrf_params *params, int64_t *energy_fixed);
+int b2tex_mrf_iterate(b2tex_ctx *ctx, uint32_t iteration, int64_t *energy_fixed);
+int b2tex_mrf_sample_forest(b2tex_ctx *ctx, const b2tex_mrf_params *params, uint32_t iteration,
+                            uint32_t *level_out_host);
+
+int b2tex_seam_run(b2tex_ctx *ctx, b2tex_seam_info *info);
+int b2tex_seam_download(b2tex_ctx *ctx, uint32_t *row_ptr, uint32_t *row_label, float *x,
+                        float *rhs_or_null);
+/* full symmetric CSR of Lhs (for tests / inspection); arrays sized from b2tex_seam_info */
+int b2tex_seam_matrix_download(b2tex_ctx *ctx, uint32_t *csr_ptr, uint32_t *csr_col, float *csr_val);
+/* raw device pointers of resident results (torch / NCCL plumbing); 0 if absent */
+uint64_t b2tex_device_ptr(b2tex_ctx *ctx, const char *name, uint64_t *num_elements);
+
+/* ---- one-shot host-buffer entry points (what the reference-side binding calls) ---- */
+/* tex::calculate_data_costs: out arrays are malloc'ed by the library (b2tex_free), CSR by face:
+ * face_ptr[F+1], view[nnz] ascending per face, cost[nnz]. */
+int b2tex_calculate_data_costs(const float *verts, uint32_t num_verts, const uint32_t *faces,
+                               const float *face_normals, uint32_t num_faces,
+                               const b2tex_view *views, uint32_t num_views,
+                               const b2tex_settings *settings, uint64_t **face_ptr_out,
+                               uint16_t **view_out, float **cost_out, b2tex_dc_info *info);
+/* tex::view_selection: labels_out[F] (0 = unseen, else view index + 1) */
+int b2tex_view_selection(uint32_t num_faces, const uint32_t *adj_ptr, const uint32_t *adj_idx,
+                         const uint64_t *face_ptr, const uint16_t *view, const float *cost,
+                         const b2tex_mrf_params *params_or_null, uint32_t *labels_out,
+                         b2tex_mrf_info *info);
+/* tex::global_seam_leveling up to the per-(vertex,label) adjust values (:283-289):
+ * row_ptr_out[Vn+1] caller allocated; row_label/x (R and R*3, centred) malloc'ed by the library. */
+int b2tex_global_seam_leveling(const float *verts, uint32_t num_verts, const uint32_t *faces,
+                               uint32_t num_faces, const uint32_t *vf_ptr, const uint32_t *vf_idx,
+                               const uint32_t *vv_ptr, const uint32_t *vv_idx,
+                               const uint32_t *labels, const b2tex_view *views, uint32_t num_views,
+                               uint32_t *row_ptr_out, uint32_t **row_label_out, float **x_out,
+                               b2tex_seam_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2TEX_H */

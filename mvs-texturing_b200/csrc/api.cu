@@ -1,0 +1,396 @@
+// api.cu -- extern "C" entry points declared in include/b2tex.h.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b2 {
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+const char *b2tex_last_error(void) { return g_err; }
+void b2tex_free(void *p) { free(p); }
+
+void b2tex_default_mrf_params(b2tex_mrf_params *p)
+{
+    p->max_iterations = 100;
+    p->rounds = 32;
+    p->root_div = 256;
+    p->seed = 548923723u;  // view_selection.cpp:115
+    p->window = 5;         // view_selection.cpp:84
+    p->ratio = 0.01f;
+    p->num_parts = 1;
+}
+
+int b2tex_create(int device, b2tex_ctx **out)
+{
+    if (!out) { set_error("b2tex_create: out is null"); return B2TEX_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return B2TEX_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d)", device, ndev); return B2TEX_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(device));
+    b2tex_ctx *c = new b2tex_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return B2TEX_OK;
+}
+
+void b2tex_destroy(b2tex_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->mrf_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)c->mrf_graph_exec);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int b2tex_device_synchronize(b2tex_ctx *c)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2TEX_OK;
+}
+
+int b2tex_set_mesh(b2tex_ctx *c, const float *verts, uint32_t nv, const uint32_t *faces, const float *normals,
+                   uint32_t nf)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    if (!verts || !faces || !normals) { set_error("set_mesh: null pointer"); return B2TEX_ERR_ARG; }
+    c->Vn = nv; c->F = nf; c->face_begin = 0; c->face_end = nf;
+    B2_TRY(c->verts.upload(verts, 3 * (size_t)nv, c->stream));
+    B2_TRY(c->faces.upload(faces, 3 * (size_t)nf, c->stream));
+    B2_TRY(c->normals.upload(normals, 3 * (size_t)nf, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->bvh_built = false; c->have_costs = false; c->have_labels = false; c->have_adj = false;
+    c->have_rings = false; c->mrf_ready = false; c->have_seam = false;
+    return B2TEX_OK;
+}
+
+int b2tex_set_face_range(b2tex_ctx *c, uint32_t fb, uint32_t fe)
+{
+    if (fb > fe || fe > c->F) { set_error("bad face range"); return B2TEX_ERR_ARG; }
+    c->face_begin = fb; c->face_end = fe;
+    c->have_costs = false; c->mrf_ready = false;
+    return B2TEX_OK;
+}
+
+int b2tex_set_views(b2tex_ctx *c, const b2tex_view *views, uint32_t K)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    if (K > 65535u) { set_error("Exeeded maximal number of views"); return B2TEX_ERR_LIMITS; }
+    c->K = K;
+    c->views_host.assign(views, views + K);
+    c->img_off.assign((size_t)K + 1, 0);
+    for (uint32_t v = 0; v < K; ++v) {
+        if (views[v].width < 2 || views[v].height < 2 || !views[v].rgb) { set_error("view %u: bad image", v); return B2TEX_ERR_ARG; }
+        c->img_off[v + 1] = c->img_off[v] + (size_t)views[v].width * views[v].height;
+    }
+    B2_TRY(c->rgb.alloc(3 * c->img_off[K]));
+    for (uint32_t v = 0; v < K; ++v) {
+        size_t px = (size_t)views[v].width * views[v].height;
+        B2_CUDA(cudaMemcpyAsync(c->rgb.p + 3 * c->img_off[v], views[v].rgb, 3 * px, cudaMemcpyHostToDevice, c->stream));
+        c->views_host[v].rgb = nullptr;
+    }
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->images_prepared = false; c->prepared_data_term = -1; c->have_costs = false; c->have_seam = false;
+    return B2TEX_OK;
+}
+
+int b2tex_set_adjacency(b2tex_ctx *c, const uint32_t *adj_ptr, const uint32_t *adj_idx)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    if (!c->F) { set_error("set_adjacency: set the mesh (or data costs) first"); return B2TEX_ERR_ARG; }
+    B2_TRY(c->adj_ptr.upload(adj_ptr, (size_t)c->F + 1, c->stream));
+    B2_TRY(c->adj_idx.upload(adj_idx, adj_ptr[c->F], c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_adj = true; c->mrf_ready = false;
+    return B2TEX_OK;
+}
+
+int b2tex_set_vertex_rings(b2tex_ctx *c, const uint32_t *vf_ptr, const uint32_t *vf_idx, const uint32_t *vv_ptr,
+                           const uint32_t *vv_idx)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    if (!c->Vn) { set_error("set_vertex_rings: set the mesh first"); return B2TEX_ERR_ARG; }
+    B2_TRY(c->vf_ptr.upload(vf_ptr, (size_t)c->Vn + 1, c->stream));
+    B2_TRY(c->vf_idx.upload(vf_idx, vf_ptr[c->Vn], c->stream));
+    B2_TRY(c->vv_ptr.upload(vv_ptr, (size_t)c->Vn + 1, c->stream));
+    B2_TRY(c->vv_idx.upload(vv_idx, vv_ptr[c->Vn], c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_rings = true;
+    return B2TEX_OK;
+}
+
+int b2tex_set_data_costs(b2tex_ctx *c, const uint64_t *face_ptr, const uint16_t *view, const float *cost)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    if (!c->F) { set_error("set_data_costs: number of faces unknown (set mesh first)"); return B2TEX_ERR_ARG; }
+    uint64_t nnz = face_ptr[c->F];
+    B2_TRY(c->dc_ptr.upload(face_ptr, (size_t)c->F + 1, c->stream));
+    B2_TRY(c->dc_view.upload(view, nnz, c->stream));
+    B2_TRY(c->dc_cost.upload(cost, nnz, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->nnz = nnz; c->have_costs = true; c->mrf_ready = false;
+    return B2TEX_OK;
+}
+
+int b2tex_set_labels(b2tex_ctx *c, const uint32_t *labels)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_TRY(c->labels.upload(labels, c->F, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_labels = true;
+    return B2TEX_OK;
+}
+
+int b2tex_data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *info)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return data_costs_qualities(c, st, info);
+}
+
+int b2tex_data_costs_histogram(b2tex_ctx *c, float gmax, uint32_t *bins, int to_host)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_TRY(data_costs_histogram(c, gmax));
+    if (bins && to_host) {
+        B2_TRY(c->hist.download(bins, 10000, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return B2TEX_OK;
+}
+
+int b2tex_data_costs_normalize(b2tex_ctx *c, float gmax, const uint32_t *bins, b2tex_dc_info *info)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return data_costs_normalize(c, gmax, bins, info);
+}
+
+int b2tex_data_costs_run(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *info)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_TRY(data_costs_qualities(c, st, info));
+    float gmax = info->max_quality;
+    uint32_t *bins = (uint32_t *)malloc(10000 * sizeof(uint32_t));
+    int rc = b2tex_data_costs_histogram(c, gmax, bins, 1);
+    if (rc == B2TEX_OK) {
+        uint64_t cand = info->candidates, rays = info->rays;
+        rc = data_costs_normalize(c, gmax, bins, info);
+        info->candidates = cand; info->rays = rays;
+    }
+    free(bins);
+    return rc;
+}
+
+int b2tex_data_costs_download(b2tex_ctx *c, uint64_t *face_ptr, uint16_t *view, float *cost, float *quality)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    if (face_ptr) B2_TRY(c->dc_ptr.download(face_ptr, (size_t)c->F + 1, c->stream));
+    if (view) B2_TRY(c->dc_view.download(view, c->nnz, c->stream));
+    if (cost) B2_TRY(c->dc_cost.download(cost, c->nnz, c->stream));
+    if (quality) B2_TRY(c->dc_quality.download(quality, c->nnz, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2TEX_OK;
+}
+
+int b2tex_mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *efix)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return mrf_init(c, p, efix);
+}
+int b2tex_mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *efix)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return mrf_iterate(c, t, efix);
+}
+int b2tex_mrf_sample_forest(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t, uint32_t *level)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return mrf_sample_only(c, p, t, level);
+}
+
+int b2tex_view_selection_run(b2tex_ctx *c, const b2tex_mrf_params *params, b2tex_mrf_info *info, double *trace)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    b2tex_mrf_params p;
+    if (params) p = *params; else b2tex_default_mrf_params(&p);
+    if (p.window == 0) p.window = 1;
+    std::vector<int64_t> efix((size_t)p.max_iterations + 1, 0);
+    B2_TRY(mrf_init(c, &p, &efix[0]));
+    if (trace) trace[0] = (double)efix[0] / 4294967296.0;
+    uint32_t t = 1;
+    for (; t <= p.max_iterations; ++t) {
+        B2_TRY(mrf_iterate(c, t, &efix[t]));
+        if (trace) trace[t] = (double)efix[t] / 4294967296.0;
+        if (t >= p.window) {  // StopWhenReturnsDiminish (view_selection.cpp:84)
+            double e0 = (double)efix[t - p.window], e1 = (double)efix[t];
+            if (e0 <= 0.0 || (e0 - e1) / e0 < (double)p.ratio) break;
+        }
+    }
+    if (t > p.max_iterations) t = p.max_iterations;
+    info->iterations = t;
+    info->energy_initial = (double)efix[0] / 4294967296.0;
+    info->energy_final = (double)efix[t] / 4294967296.0;
+    info->sweep_bytes = 14ull * c->nnz + 20ull * c->F;
+    // label range check + unseen count (view_selection.cpp:121-132)
+    std::vector<uint32_t> lab(c->F);
+    B2_TRY(c->labels.download(lab.data(), c->F, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    uint64_t unseen = 0;
+    for (uint32_t i = c->face_begin; i < c->face_end; ++i) {
+        if (c->K && lab[i] > c->K) { set_error("Incorrect labeling"); return B2TEX_ERR_LABELING; }
+        if (lab[i] == 0) ++unseen;
+    }
+    info->unseen = unseen;
+    return B2TEX_OK;
+}
+
+int b2tex_labels_download(b2tex_ctx *c, uint32_t *labels)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_TRY(c->labels.download(labels, c->F, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2TEX_OK;
+}
+
+int b2tex_seam_run(b2tex_ctx *c, b2tex_seam_info *info)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return seam_run(c, info);
+}
+
+int b2tex_seam_download(b2tex_ctx *c, uint32_t *row_ptr, uint32_t *row_label, float *x, float *rhs)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    if (!c->have_seam) { set_error("seam_download before seam_run"); return B2TEX_ERR_ARG; }
+    const size_t R = c->R;
+    if (row_ptr) B2_TRY(c->row_ptr.download(row_ptr, (size_t)c->Vn + 1, c->stream));
+    if (row_label) B2_TRY(c->row_label.download(row_label, R, c->stream));
+    std::vector<float> tmp(3 * R);
+    for (int pass = 0; pass < 2; ++pass) {
+        float *dst = pass == 0 ? x : rhs;
+        if (!dst) continue;
+        B2_TRY((pass == 0 ? c->seam_x : c->seam_rhs).download(tmp.data(), 3 * R, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        for (size_t r = 0; r < R; ++r)
+            for (int ch = 0; ch < 3; ++ch) dst[3 * r + ch] = tmp[(size_t)ch * R + r];
+    }
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2TEX_OK;
+}
+
+int b2tex_seam_matrix_download(b2tex_ctx *c, uint32_t *csr_ptr, uint32_t *csr_col, float *csr_val)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    if (!c->have_seam) { set_error("seam_matrix_download before seam_run"); return B2TEX_ERR_ARG; }
+    B2_TRY(c->csr_ptr.download(csr_ptr, (size_t)c->R + 1, c->stream));
+    B2_TRY(c->csr_col.download(csr_col, c->nnz_L, c->stream));
+    B2_TRY(c->csr_val.download(csr_val, c->nnz_L, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2TEX_OK;
+}
+
+uint64_t b2tex_device_ptr(b2tex_ctx *c, const char *name, uint64_t *n)
+{
+    uint64_t p = 0, cnt = 0;
+#define B2_NAME(nm, buf) if (!strcmp(name, nm)) { p = (uint64_t)(uintptr_t)(buf).p; cnt = (buf).n; }
+    B2_NAME("labels", c->labels)
+    B2_NAME("dc_ptr", c->dc_ptr)
+    B2_NAME("dc_view", c->dc_view)
+    B2_NAME("dc_cost", c->dc_cost)
+    B2_NAME("dc_quality", c->dc_quality)
+    B2_NAME("hist", c->hist)
+    B2_NAME("seam_x", c->seam_x)
+    B2_NAME("rgb", c->rgb)
+    B2_NAME("grad", c->grad)
+#undef B2_NAME
+    if (n) *n = cnt;
+    return p;
+}
+
+// ---- one-shot host-buffer entry points ---------------------------------------------------------
+
+int b2tex_calculate_data_costs(const float *verts, uint32_t nv, const uint32_t *faces, const float *normals,
+                               uint32_t nf, const b2tex_view *views, uint32_t K, const b2tex_settings *st,
+                               uint64_t **face_ptr_out, uint16_t **view_out, float **cost_out, b2tex_dc_info *info)
+{
+    if (K > 65535u) { set_error("Exeeded maximal number of views"); return B2TEX_ERR_LIMITS; }
+    b2tex_ctx *c = nullptr;
+    B2_TRY(b2tex_create(0, &c));
+    int rc = b2tex_set_mesh(c, verts, nv, faces, normals, nf);
+    if (rc == B2TEX_OK) rc = b2tex_set_views(c, views, K);
+    if (rc == B2TEX_OK) rc = b2tex_data_costs_run(c, st, info);
+    if (rc == B2TEX_OK) {
+        *face_ptr_out = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)nf + 1));
+        *view_out = (uint16_t *)malloc(sizeof(uint16_t) * (info->nnz ? info->nnz : 1));
+        *cost_out = (float *)malloc(sizeof(float) * (info->nnz ? info->nnz : 1));
+        rc = b2tex_data_costs_download(c, *face_ptr_out, *view_out, *cost_out, nullptr);
+    }
+    b2tex_destroy(c);
+    return rc;
+}
+
+int b2tex_view_selection(uint32_t nf, const uint32_t *adj_ptr, const uint32_t *adj_idx, const uint64_t *face_ptr,
+                         const uint16_t *view, const float *cost, const b2tex_mrf_params *params,
+                         uint32_t *labels_out, b2tex_mrf_info *info)
+{
+    b2tex_ctx *c = nullptr;
+    B2_TRY(b2tex_create(0, &c));
+    c->F = nf; c->face_begin = 0; c->face_end = nf;
+    uint32_t maxview = 0;
+    for (uint64_t i = 0; i < face_ptr[nf]; ++i) maxview = view[i] > maxview ? view[i] : maxview;
+    c->K = face_ptr[nf] ? maxview + 1 : 0;  // DataCosts::rows() is not part of the CSR; bound from content
+    int rc = b2tex_set_data_costs(c, face_ptr, view, cost);
+    if (rc == B2TEX_OK) rc = b2tex_set_adjacency(c, adj_ptr, adj_idx);
+    if (rc == B2TEX_OK) rc = b2tex_view_selection_run(c, params, info, nullptr);
+    if (rc == B2TEX_OK) rc = b2tex_labels_download(c, labels_out);
+    b2tex_destroy(c);
+    return rc;
+}
+
+int b2tex_global_seam_leveling(const float *verts, uint32_t nv, const uint32_t *faces, uint32_t nf,
+                               const uint32_t *vf_ptr, const uint32_t *vf_idx, const uint32_t *vv_ptr,
+                               const uint32_t *vv_idx, const uint32_t *labels, const b2tex_view *views, uint32_t K,
+                               uint32_t *row_ptr_out, uint32_t **row_label_out, float **x_out, b2tex_seam_info *info)
+{
+    b2tex_ctx *c = nullptr;
+    B2_TRY(b2tex_create(0, &c));
+    std::vector<float> dummy_normals(3 * (size_t)nf, 0.0f);
+    int rc = b2tex_set_mesh(c, verts, nv, faces, dummy_normals.data(), nf);
+    if (rc == B2TEX_OK) rc = b2tex_set_views(c, views, K);
+    if (rc == B2TEX_OK) rc = b2tex_set_vertex_rings(c, vf_ptr, vf_idx, vv_ptr, vv_idx);
+    if (rc == B2TEX_OK) rc = b2tex_set_labels(c, labels);
+    if (rc == B2TEX_OK) rc = b2tex_seam_run(c, info);
+    if (rc == B2TEX_OK) {
+        *row_label_out = (uint32_t *)malloc(sizeof(uint32_t) * (info->num_rows ? info->num_rows : 1));
+        *x_out = (float *)malloc(sizeof(float) * 3 * (info->num_rows ? info->num_rows : 1));
+        rc = b2tex_seam_download(c, row_ptr_out, *row_label_out, *x_out, nullptr);
+    }
+    b2tex_destroy(c);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+// common.cuh -- context, device buffers and error plumbing shared by the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/b2tex.h"
+
+namespace b2 {
+
+void set_error(const char *fmt, ...);
+
+#define B2_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            b2::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return B2TEX_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+#define B2_TRY(expr)                    \
+    do {                                \
+        int _rc = (expr);               \
+        if (_rc != B2TEX_OK) return _rc; \
+    } while (0)
+
+#define B2_KERNEL_CHECK() B2_CUDA(cudaGetLastError())
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;    // elements in use
+    size_t cap = 0;  // elements allocated
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = cap = 0;
+    }
+    // grow-only allocation; contents are NOT preserved
+    int alloc(size_t count)
+    {
+        if (count > cap) {
+            if (p) cudaFree(p);
+            p = nullptr;
+            cap = 0;
+            size_t want = count ? count : 1;
+            cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+            if (e != cudaSuccess) {
+                set_error("cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+                n = 0;
+                return B2TEX_ERR_CUDA;
+            }
+            cap = want;
+        }
+        n = count;
+        return B2TEX_OK;
+    }
+    int upload(const T *host, size_t count, cudaStream_t s)
+    {
+        B2_TRY(alloc(count));
+        if (count) B2_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        return B2TEX_OK;
+    }
+    int download(T *host, size_t count, cudaStream_t s) const
+    {
+        if (count) B2_CUDA(cudaMemcpyAsync(host, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+        return B2TEX_OK;
+    }
+    int zero(cudaStream_t s)
+    {
+        if (n) B2_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+        return B2TEX_OK;
+    }
+};
+
+// device-side copy of one view (camera + prepared images)
+struct ViewDev {
+    float pos[3];
+    float dir[3];
+    float proj[9];
+    float w2c[12];
+    int32_t w, h;
+    const uint8_t *rgb;    // H*W*3
+    const uint8_t *grad;   // H*W (null for DATA_TERM_AREA)
+    const uint8_t *valid4; // H*W, 1 = all four bilinear taps valid; null = everything valid
+};
+
+// two-child BVH node: both child boxes in one 64-byte record
+struct __align__(16) BvhNode {
+    float lo0[3], hi0[3];  // left child box
+    float lo1[3], hi1[3];  // right child box
+    int32_t left, right;   // >=0 internal node index, <0: ~(sorted triangle slot)
+    int32_t pad0, pad1;
+};
+
+struct Bvh {
+    DevBuf<BvhNode> nodes;      // N-1 internal nodes (N>=2)
+    DevBuf<float> tri;          // 9 floats per triangle in Morton order
+    uint32_t num_tris = 0;
+};
+
+}  // namespace b2
+
+// The opaque C-ABI context.
+struct b2tex_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+
+    // mesh
+    uint32_t Vn = 0, F = 0;
+    uint32_t face_begin = 0, face_end = 0;
+    b2::DevBuf<float> verts, normals;
+    b2::DevBuf<uint32_t> faces;
+
+    // views
+    uint32_t K = 0;
+    std::vector<b2tex_view> views_host;   // camera params (rgb pointer = caller memory, not kept)
+    b2::DevBuf<uint8_t> rgb, grad, valid4;
+    std::vector<size_t> img_off;          // pixel offset of each view in grad/valid4 (rgb: *3)
+    b2::DevBuf<b2::ViewDev> views_dev;
+    bool images_prepared = false;
+    int prepared_data_term = -1;
+
+    // bvh
+    b2::Bvh bvh;
+    bool bvh_built = false;
+
+    // data costs (CSR by face over [face_begin, face_end) -> global face ids keep absolute ptr layout)
+    b2::DevBuf<uint64_t> dc_ptr;       // F+1
+    b2::DevBuf<uint16_t> dc_view;      // nnz
+    b2::DevBuf<float> dc_cost;         // nnz
+    b2::DevBuf<float> dc_quality;      // nnz
+    uint64_t nnz = 0;
+    bool have_costs = false;
+    // scratch of the data-cost stage
+    b2::DevBuf<uint64_t> cand_ptr;     // F+1
+    b2::DevBuf<uint16_t> cand_view;
+    b2::DevBuf<uint32_t> cand_face;
+    b2::DevBuf<float> cand_q;
+    b2::DevBuf<uint32_t> need_bits, occ_bits;
+    b2::DevBuf<uint32_t> hist;         // 10000 bins
+    b2::DevBuf<uint32_t> scalars;      // misc device scalars
+    b2::DevBuf<uint8_t> cub_tmp;
+    uint64_t num_cand = 0;
+
+    // graph + labels
+    b2::DevBuf<uint32_t> adj_ptr, adj_idx;
+    b2::DevBuf<uint32_t> labels;
+    bool have_adj = false, have_labels = false;
+
+    // mrf scratch
+    b2::DevBuf<float> mrf_H, mrf_hminp1;
+    b2::DevBuf<uint32_t> mrf_amin, mrf_level, mrf_order, mrf_lvlptr, mrf_cursor;
+    b2::DevBuf<unsigned long long> mrf_energy;
+    b2tex_mrf_params mrf_params{};
+    bool mrf_ready = false;
+    void *mrf_graph_exec = nullptr;    // cudaGraphExec_t of one iteration
+    uint32_t mrf_graph_rounds = 0;
+    int mrf_group = 32;
+
+    // seam
+    b2::DevBuf<uint32_t> vf_ptr, vf_idx, vv_ptr, vv_idx;
+    bool have_rings = false;
+    b2::DevBuf<uint32_t> row_ptr, row_label, arow_ptr, arow_rows;
+    b2::DevBuf<float> arow_b;
+    b2::DevBuf<uint32_t> csr_ptr, csr_col;
+    b2::DevBuf<float> csr_val, seam_diag, seam_rhs, seam_x, seam_r, seam_t;
+    b2::DevBuf<float4> seam_p;
+    b2::DevBuf<double> seam_partials;
+    b2::DevBuf<uint32_t> seam_status;
+    uint32_t R = 0, A_rows = 0;
+    uint64_t nnz_L = 0;
+    bool have_seam = false;
+};
+
+namespace b2 {
+// stage entry points implemented in the individual .cu files
+int prepare_images(b2tex_ctx *c, int data_term);
+int build_bvh(b2tex_ctx *c);
+int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *info);
+int data_costs_histogram(b2tex_ctx *c, float gmax);
+int data_costs_normalize(b2tex_ctx *c, float gmax, const uint32_t *bins_host, b2tex_dc_info *info);
+int mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *energy_fixed);
+int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *energy_fixed);
+int mrf_sample_only(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t, uint32_t *level_host);
+int mrf_energy_double(b2tex_ctx *c, double *e, uint64_t *unseen);
+int seam_run(b2tex_ctx *c, b2tex_seam_info *info);
+int cub_exclusive_sum_u64(b2tex_ctx *c, const uint64_t *in, uint64_t *out, size_t n);
+int cub_exclusive_sum_u32(b2tex_ctx *c, const uint32_t *in, uint32_t *out, size_t n);
+}  // namespace b2

@@ -1,0 +1,237 @@
+// imgprep.cu -- K1: per-view image preparation on the device.
+//   gradient magnitude = Sobel(luminance(rgb)) as u8       (reference: texture_view.cpp:102-107)
+//   validity mask      = corner flood fill of zero pixels   (texture_view.cpp:42-94)
+//   erosion            = 3x3 dilation of interior invalids   (texture_view.cpp:109-132, incl. the
+//                        border quirk: image-border pixels are not invalidated)
+//   valid4             = AND of the 4 bilinear taps          (texture_view.cpp:264-277)
+// Integer/u8 outputs are bit-exact restatements; compiled with -fmad=false.
+#include "common.cuh"
+
+namespace b2 {
+
+namespace {
+
+constexpr int TW = 64, TH = 16;
+
+__device__ __forceinline__ uint8_t luminance_u8(const uint8_t *px)
+{
+    // MVE desaturate_luminance -> math::interpolate<uchar>: (u8)(r*.21f + g*.72f + b*.07f + .5f)
+    float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn((float)px[0], 0.21f), __fmul_rn((float)px[1], 0.72f)),
+                                  __fmul_rn((float)px[2], 0.07f)), 0.5f);
+    return (uint8_t)v;
+}
+
+// One block = TW x TH output pixels; luminance tile with a 1-pixel halo staged in shared memory so
+// every rgb byte is read once from global (HBM-bound: 3 B read + 1 B written per pixel).
+__global__ void __launch_bounds__(256) k_lum_sobel(const uint8_t *__restrict__ rgb,
+                                                   uint8_t *__restrict__ grad, int w, int h)
+{
+    __shared__ uint8_t lum[TH + 2][TW + 2 + 2];
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    for (int i = threadIdx.x; i < (TW + 2) * (TH + 2); i += blockDim.x) {
+        int ly = i / (TW + 2), lx = i - ly * (TW + 2);
+        int gx = x0 + lx - 1, gy = y0 + ly - 1;
+        uint8_t v = 0;
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h) v = luminance_u8(rgb + 3 * ((size_t)gx + (size_t)gy * w));
+        lum[ly][lx] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TW * TH; i += blockDim.x) {
+        int ly = i / TW, lx = i - ly * TW;
+        int gx = x0 + lx, gy = y0 + ly;
+        if (gx >= w || gy >= h) continue;
+        uint8_t out = 0;
+        if (!(gy == 0 || gy == h - 1 || gx == 0 || gx == w - 1)) {
+            int a = lum[ly][lx], b = lum[ly][lx + 1], c = lum[ly][lx + 2];
+            int d = lum[ly + 1][lx], f = lum[ly + 1][lx + 2];
+            int g = lum[ly + 2][lx], hh = lum[ly + 2][lx + 1], k = lum[ly + 2][lx + 2];
+            int sx = (c - a) + 2 * (f - d) + (k - g);
+            int sy = (g - a) + 2 * (hh - b) + (k - c);
+            int s = sx * sx + sy * sy;  // exact; (u8)min(255, sqrt(double(s))) == min(255, isqrt(s))
+            int r = (int)sqrtf((float)s);
+            while (r * r > s) --r;
+            while ((r + 1) * (r + 1) <= s) ++r;
+            out = (uint8_t)(r < 255 ? r : 255);
+        }
+        grad[(size_t)gx + (size_t)gy * w] = out;
+    }
+}
+
+__global__ void k_corner_check(const ViewDev *views, int K, uint32_t *flags)
+{
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= K) return;
+    const ViewDev &V = views[v];
+    int cx[4] = {0, 0, V.w - 1, V.w - 1}, cy[4] = {0, V.h - 1, 0, V.h - 1};
+    uint32_t any = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint8_t *p = V.rgb + 3 * ((size_t)cx[i] + (size_t)cy[i] * V.w);
+        if ((int)p[0] + p[1] + p[2] == 0) any = 1;
+    }
+    flags[v] = any;
+}
+
+__global__ void k_flood_seed(const uint8_t *rgb, uint8_t *inv, int w, int h)
+{
+    int i = threadIdx.x;
+    if (i >= 4) return;
+    int cx = (i & 2) ? w - 1 : 0, cy = (i & 1) ? h - 1 : 0;
+    const uint8_t *p = rgb + 3 * ((size_t)cx + (size_t)cy * w);
+    if ((int)p[0] + p[1] + p[2] == 0) inv[(size_t)cx + (size_t)cy * w] = 1;
+}
+
+// tile-local flood iteration: invalid spreads through 4-connected zero-sum pixels
+__global__ void __launch_bounds__(256) k_flood(const uint8_t *__restrict__ rgb, uint8_t *inv, int w,
+                                               int h, uint32_t *changed)
+{
+    __shared__ uint8_t z[34][36], s[34][36];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    for (int i = threadIdx.x; i < 34 * 34; i += blockDim.x) {
+        int ly = i / 34, lx = i - ly * 34;
+        int gx = x0 + lx - 1, gy = y0 + ly - 1;
+        uint8_t zz = 0, ss = 0;
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+            const uint8_t *p = rgb + 3 * ((size_t)gx + (size_t)gy * w);
+            zz = ((int)p[0] + p[1] + p[2] == 0);
+            ss = inv[(size_t)gx + (size_t)gy * w];
+        }
+        z[ly][lx] = zz;
+        s[ly][lx] = ss;
+    }
+    __syncthreads();
+    bool any_new = false;
+    for (;;) {
+        int ch = 0;
+        for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+            int ly = i / 32 + 1, lx = (i & 31) + 1;
+            if (z[ly][lx] && !s[ly][lx] && (s[ly - 1][lx] | s[ly + 1][lx] | s[ly][lx - 1] | s[ly][lx + 1])) {
+                s[ly][lx] = 1;
+                ch = 1;
+            }
+        }
+        if (!__syncthreads_or(ch)) break;
+        any_new = true;
+    }
+    if (any_new) {
+        for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+            int ly = i / 32 + 1, lx = (i & 31) + 1;
+            int gx = x0 + lx - 1, gy = y0 + ly - 1;
+            if (gx < w && gy < h && s[ly][lx]) inv[(size_t)gx + (size_t)gy * w] = 1;
+        }
+        if (threadIdx.x == 0) *changed = 1;
+    }
+}
+
+// erosion (optional) + 4-tap AND.  inv: 1 = invalid after flood fill.
+__global__ void k_erode(const uint8_t *__restrict__ inv, uint8_t *__restrict__ er, int w, int h)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    uint8_t bad = inv[(size_t)x + (size_t)y * w];
+    for (int j = -1; j <= 1 && !bad; ++j)
+        for (int i = -1; i <= 1; ++i) {
+            int nx = x + i, ny = y + j;
+            // only INTERIOR invalid pixels dilate (texture_view.cpp:115-127)
+            if (nx < 1 || nx > w - 2 || ny < 1 || ny > h - 2) continue;
+            if (inv[(size_t)nx + (size_t)ny * w]) { bad = 1; break; }
+        }
+    er[(size_t)x + (size_t)y * w] = bad;
+}
+
+__global__ void k_valid4(const uint8_t *__restrict__ inv, uint8_t *__restrict__ v4, int w, int h)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    int x1 = min(x + 1, w - 1), y1 = min(y + 1, h - 1);
+    uint8_t bad = inv[(size_t)x + (size_t)y * w] | inv[(size_t)x1 + (size_t)y * w]
+        | inv[(size_t)x + (size_t)y1 * w] | inv[(size_t)x1 + (size_t)y1 * w];
+    v4[(size_t)x + (size_t)y * w] = bad ? 0 : 1;
+}
+
+}  // namespace
+
+int prepare_images(b2tex_ctx *c, int data_term)
+{
+    if (c->images_prepared && c->prepared_data_term == data_term) return B2TEX_OK;
+    if (!c->K) { set_error("prepare_images: no views set"); return B2TEX_ERR_ARG; }
+    cudaStream_t s = c->stream;
+    const uint32_t K = c->K;
+    size_t total_px = c->img_off[K];
+
+    if (data_term == 1) {
+        B2_TRY(c->grad.alloc(total_px));
+        for (uint32_t v = 0; v < K; ++v) {
+            int w = c->views_host[v].width, h = c->views_host[v].height;
+            dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH);
+            k_lum_sobel<<<grid, 256, 0, s>>>(c->rgb.p + 3 * c->img_off[v], c->grad.p + c->img_off[v], w, h);
+        }
+        B2_KERNEL_CHECK();
+    }
+
+    // validity: only views with a zero-sum corner can have invalid pixels at all
+    std::vector<ViewDev> vd(K);
+    for (uint32_t v = 0; v < K; ++v) {
+        const b2tex_view &hv = c->views_host[v];
+        ViewDev &d = vd[v];
+        for (int i = 0; i < 3; ++i) { d.pos[i] = hv.pos[i]; d.dir[i] = hv.viewdir[i]; }
+        for (int i = 0; i < 9; ++i) d.proj[i] = hv.proj[i];
+        for (int i = 0; i < 12; ++i) d.w2c[i] = hv.w2c[i];
+        d.w = hv.width; d.h = hv.height;
+        d.rgb = c->rgb.p + 3 * c->img_off[v];
+        d.grad = data_term == 1 ? c->grad.p + c->img_off[v] : nullptr;
+        d.valid4 = nullptr;
+    }
+    B2_TRY(c->views_dev.upload(vd.data(), K, s));
+    B2_TRY(c->scalars.alloc(std::max<size_t>(K + 64, 256)));
+    k_corner_check<<<(K + 127) / 128, 128, 0, s>>>(c->views_dev.p, (int)K, c->scalars.p + 64);
+    B2_KERNEL_CHECK();
+    std::vector<uint32_t> flags(K);
+    B2_CUDA(cudaMemcpyAsync(flags.data(), c->scalars.p + 64, K * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    bool any = false;
+    for (uint32_t v = 0; v < K; ++v) any |= flags[v] != 0;
+    if (any) {
+        B2_TRY(c->valid4.alloc(total_px));
+        DevBuf<uint8_t> inv, er;
+        size_t maxpx = 0;
+        for (uint32_t v = 0; v < K; ++v)
+            maxpx = std::max(maxpx, (size_t)c->views_host[v].width * c->views_host[v].height);
+        B2_TRY(inv.alloc(maxpx));
+        B2_TRY(er.alloc(maxpx));
+        for (uint32_t v = 0; v < K; ++v) {
+            if (!flags[v]) continue;
+            int w = c->views_host[v].width, h = c->views_host[v].height;
+            const uint8_t *rgb = c->rgb.p + 3 * c->img_off[v];
+            B2_CUDA(cudaMemsetAsync(inv.p, 0, (size_t)w * h, s));
+            k_flood_seed<<<1, 32, 0, s>>>(rgb, inv.p, w, h);
+            dim3 fgrid((w + 31) / 32, (h + 31) / 32);
+            for (int it = 0; it < 100000; ++it) {
+                B2_CUDA(cudaMemsetAsync(c->scalars.p, 0, sizeof(uint32_t), s));
+                k_flood<<<fgrid, 256, 0, s>>>(rgb, inv.p, w, h, c->scalars.p);
+                uint32_t changed = 0;
+                B2_CUDA(cudaMemcpyAsync(&changed, c->scalars.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                B2_CUDA(cudaStreamSynchronize(s));
+                if (!changed) break;
+            }
+            dim3 b(32, 8), g((w + 31) / 32, (h + 7) / 8);
+            const uint8_t *src = inv.p;
+            if (data_term == 1) {
+                k_erode<<<g, b, 0, s>>>(inv.p, er.p, w, h);
+                src = er.p;
+            }
+            k_valid4<<<g, b, 0, s>>>(src, c->valid4.p + c->img_off[v], w, h);
+            B2_KERNEL_CHECK();
+            vd[v].valid4 = c->valid4.p + c->img_off[v];
+        }
+        B2_CUDA(cudaStreamSynchronize(s));
+        B2_TRY(c->views_dev.upload(vd.data(), K, s));
+        B2_CUDA(cudaStreamSynchronize(s));  // vd is a local
+    } else {
+        B2_CUDA(cudaStreamSynchronize(s));
+    }
+    c->images_prepared = true;
+    c->prepared_data_term = data_term;
+    return B2TEX_OK;
+}
+
+}  // namespace b2
