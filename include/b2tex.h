@@ -98,6 +98,10 @@ void b2tex_destroy(b2tex_ctx *ctx);
 const char *b2tex_last_error(void);
 void b2tex_free(void *host_ptr);                 /* frees buffers returned by one-shot calls */
 int b2tex_device_synchronize(b2tex_ctx *ctx);
+uint64_t b2tex_stream(b2tex_ctx *ctx);            /* the cudaStream_t every kernel is launched on */
+/* per-kernel CUDA-event timing: enable, run stages, read "name ms algorithmic_bytes" lines */
+int b2tex_profile(b2tex_ctx *ctx, int enable);
+int b2tex_profile_report(b2tex_ctx *ctx, char *buf, uint64_t cap);
 void b2tex_default_mrf_params(b2tex_mrf_params *p);
 
 /* ---- resident API: upload once, run stages on the device, download results ---- */

@@ -22,6 +22,7 @@ LIB_PATH = os.path.join(_HERE, "libb2tex.so")
 
 EXPORTS = [
     "b2tex_create", "b2tex_destroy", "b2tex_last_error", "b2tex_free", "b2tex_device_synchronize",
+    "b2tex_stream", "b2tex_profile", "b2tex_profile_report",
     "b2tex_default_mrf_params", "b2tex_set_mesh", "b2tex_set_views", "b2tex_set_adjacency",
     "b2tex_set_vertex_rings", "b2tex_set_data_costs", "b2tex_set_labels", "b2tex_set_face_range",
     "b2tex_data_costs_run", "b2tex_data_costs_qualities", "b2tex_data_costs_histogram",
@@ -84,6 +85,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.b2tex_last_error.restype = C.c_char_p
         L.b2tex_device_ptr.restype = C.c_uint64
+        L.b2tex_stream.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -184,6 +186,22 @@ class Context:
     def synchronize(self):
         _check(lib().b2tex_device_synchronize(self._h))
 
+    def stream(self) -> int:
+        return int(lib().b2tex_stream(self._h))
+
+    def profile(self, enable=True):
+        _check(lib().b2tex_profile(self._h, C.c_int(1 if enable else 0)))
+
+    def profile_report(self):
+        """list of (name, ms, algorithmic_bytes) per recorded launch group since profile(True)"""
+        buf = C.create_string_buffer(1 << 20)
+        lib().b2tex_profile_report(self._h, buf, C.c_uint64(len(buf)))
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, ms, by = line.rsplit(" ", 2)
+            out.append((name, float(ms), float(by)))
+        return out
+
     # ---- stages ----
     def data_costs_run(self, data_term=1, visibility=True):
         st = B2Settings(data_term, 0, 1 if visibility else 0)
@@ -201,6 +219,10 @@ class Context:
         bins = np.zeros(10000, np.uint32)
         _check(lib().b2tex_data_costs_histogram(self._h, C.c_float(gmax), _p(bins), C.c_int(1)))
         return bins
+
+    def data_costs_histogram_device(self, gmax):
+        """histogram stays on the device (buffer "hist") so that NCCL can all-reduce it in place"""
+        _check(lib().b2tex_data_costs_histogram(self._h, C.c_float(gmax), None, C.c_int(0)))
 
     def data_costs_normalize(self, gmax, bins):
         info = B2DcInfo()

@@ -67,6 +67,37 @@ void b2tex_destroy(b2tex_ctx *c)
     delete c;
 }
 
+uint64_t b2tex_stream(b2tex_ctx *c) { return (uint64_t)(uintptr_t)c->stream; }
+
+int b2tex_profile(b2tex_ctx *c, int enable)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto &t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    c->timers.clear();
+    c->profile = enable != 0;
+    return B2TEX_OK;
+}
+
+// "name ms bytes" per recorded launch group, newline separated; returns the number of records
+int b2tex_profile_report(b2tex_ctx *c, char *buf, uint64_t cap)
+{
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    size_t off = 0;
+    int n = 0;
+    if (cap) buf[0] = 0;
+    for (auto &t : c->timers) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) != cudaSuccess) continue;
+        int w = snprintf(buf + off, off < cap ? cap - off : 0, "%s %.6f %.0f\n", t.name, ms, t.bytes);
+        if (w < 0 || off + (size_t)w >= cap) break;
+        off += (size_t)w;
+        ++n;
+    }
+    return n;
+}
+
 int b2tex_device_synchronize(b2tex_ctx *c)
 {
     B2_CUDA(cudaSetDevice(c->device));

@@ -183,9 +183,10 @@ __global__ void k_refit(BvhNode *nodes, const int *__restrict__ parent_internal,
 
 }  // namespace
 
-int build_bvh(b2tex_ctx *c)
+int build_bvh(b2tex_ctx *c, bool force)
 {
-    if (c->bvh_built) return B2TEX_OK;
+    if (c->bvh_built && !force) return B2TEX_OK;
+    ScopedTimer tm(c, "bvh_build");
     cudaStream_t s = c->stream;
     const uint32_t n = c->F;
     c->bvh.num_tris = n;

@@ -110,8 +110,19 @@ struct Bvh {
 
 }  // namespace b2
 
+namespace b2 {
+struct KTimer {
+    const char *name;
+    cudaEvent_t a, b;
+    double bytes;  // algorithmic bytes of this launch (0 = not accounted)
+};
+}  // namespace b2
+
 // The opaque C-ABI context.
 struct b2tex_ctx {
+    bool profile = false;
+    std::vector<b2::KTimer> timers;
+
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
@@ -184,9 +195,27 @@ struct b2tex_ctx {
 };
 
 namespace b2 {
+// Records a pair of events around a launch sequence on the context's stream when profiling is on.
+struct ScopedTimer {
+    b2tex_ctx *c;
+    size_t idx = (size_t)-1;
+    ScopedTimer(b2tex_ctx *ctx, const char *name, double bytes = 0.0) : c(ctx)
+    {
+        if (!c->profile) return;
+        KTimer t{name, nullptr, nullptr, bytes};
+        if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
+        cudaEventRecord(t.a, c->stream);
+        idx = c->timers.size();
+        c->timers.push_back(t);
+    }
+    ~ScopedTimer()
+    {
+        if (idx != (size_t)-1) cudaEventRecord(c->timers[idx].b, c->stream);
+    }
+};
 // stage entry points implemented in the individual .cu files
-int prepare_images(b2tex_ctx *c, int data_term);
-int build_bvh(b2tex_ctx *c);
+int prepare_images(b2tex_ctx *c, int data_term, bool force = false);
+int build_bvh(b2tex_ctx *c, bool force = false);
 int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *info);
 int data_costs_histogram(b2tex_ctx *c, float gmax);
 int data_costs_normalize(b2tex_ctx *c, float gmax, const uint32_t *bins_host, b2tex_dc_info *info);

@@ -401,9 +401,11 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     if (st->outlier_removal != 0) { set_error("outlier removal is not implemented"); return B2TEX_ERR_UNSUPPORTED; }
     if (c->K > 65535u) { set_error("Exeeded maximal number of views"); return B2TEX_ERR_LIMITS; }
     cudaStream_t s = c->stream;
-    B2_TRY(prepare_images(c, st->data_term));
+    // image preparation and the BVH are part of the stage in the reference
+    // (calculate_data_costs.cpp:144,157-163), so they are redone on every call
+    B2_TRY(prepare_images(c, st->data_term, true));
     const bool vis = st->geometric_visibility_test != 0;
-    if (vis) B2_TRY(build_bvh(c));
+    if (vis) B2_TRY(build_bvh(c, true));
 
     const uint32_t F = c->F, K = c->K, fb = c->face_begin, fe = c->face_end;
     const uint32_t nf = fe - fb;
@@ -418,9 +420,12 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     B2_TRY(c->scalars.alloc(std::max<size_t>(c->scalars.n, 256)));
     B2_CUDA(cudaMemsetAsync(c->scalars.p, 0, 64 * sizeof(uint32_t), s));
     const uint32_t blocks = (nf + 255) / 256;
-    if (nf)
+    const double mesh_bytes = 24.0 * nf + 12.0 * c->Vn;
+    if (nf) {
+        ScopedTimer tm(c, "k_cull<count>", mesh_bytes + 8.0 * nf);
         k_cull<false><<<blocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->normals.p, c->views_dev.p, K, fb, fe,
                                              cos_thr, cnt.p, nullptr, nullptr, nullptr, nullptr, vwords);
+    }
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u64(c, cnt.p, c->cand_ptr.p, (size_t)F + 1));
     uint64_t num_cand = 0;
@@ -435,27 +440,34 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
         B2_TRY(c->occ_bits.alloc((size_t)K * vwords));
         B2_TRY(c->need_bits.zero(s));
     }
-    if (nf)
+    if (nf) {
+        ScopedTimer tm(c, "k_cull<fill>", mesh_bytes + 6.0 * (double)num_cand);
         k_cull<true><<<blocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->normals.p, c->views_dev.p, K, fb, fe,
                                             cos_thr, nullptr, c->cand_ptr.p, c->cand_view.p, c->cand_face.p,
                                             vis ? c->need_bits.p : nullptr, vwords);
+    }
     B2_KERNEL_CHECK();
     unsigned long long *ray_count = reinterpret_cast<unsigned long long *>(c->scalars.p + 2);
     if (vis) {
         size_t warps = (size_t)K * vwords;
         size_t rblocks = (warps * 32 + 255) / 256;
+        ScopedTimer tm(c, "k_rays", 8.0 * (double)warps + 12.0 * c->Vn);
         k_rays<<<(unsigned)rblocks, 256, 0, s>>>(c->verts.p, c->Vn, c->views_dev.p, K, c->need_bits.p, c->occ_bits.p,
                                                  vwords, c->bvh.nodes.p, c->bvh.tri.p, c->bvh.num_tris, ray_count);
         B2_KERNEL_CHECK();
     }
     if (num_cand) {
         size_t qblocks = (num_cand + 255) / 256;
+        ScopedTimer tm(c, "k_quality", 10.0 * (double)num_cand + mesh_bytes);
         k_quality<<<(unsigned)qblocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->views_dev.p, c->cand_view.p,
                                                     c->cand_face.p, num_cand, vis ? c->occ_bits.p : nullptr, vwords,
                                                     st->data_term, c->cand_q.p, c->scalars.p);
         B2_KERNEL_CHECK();
     }
-    k_count_survivors<<<(F + 1 + 255) / 256, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, fb, fe, F, cnt.p);
+    {
+        ScopedTimer tm(c, "k_count_survivors", 4.0 * (double)num_cand + 16.0 * F);
+        k_count_survivors<<<(F + 1 + 255) / 256, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, fb, fe, F, cnt.p);
+    }
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u64(c, cnt.p, c->dc_ptr.p, (size_t)F + 1));
     uint64_t nnz = 0;
@@ -469,9 +481,11 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     B2_TRY(c->dc_view.alloc(nnz));
     B2_TRY(c->dc_quality.alloc(nnz));
     B2_TRY(c->dc_cost.alloc(nnz));
-    if (nf)
+    if (nf) {
+        ScopedTimer tm(c, "k_compact", 6.0 * (double)num_cand + 6.0 * (double)nnz + 16.0 * nf);
         k_compact<<<blocks, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, c->cand_view.p, c->dc_ptr.p, fb, fe,
                                          c->dc_view.p, c->dc_quality.p);
+    }
     B2_KERNEL_CHECK();
     float maxq;
     memcpy(&maxq, &maxbits, 4);
@@ -491,6 +505,7 @@ int data_costs_histogram(b2tex_ctx *c, float gmax)
     B2_TRY(c->hist.zero(s));
     if (c->nnz) {
         int blocks = std::max(1, c->num_sms * 2);
+        ScopedTimer tm(c, "k_histogram", 4.0 * (double)c->nnz);
         k_histogram<<<blocks, 512, 0, s>>>(c->dc_quality.p, c->nnz, gmax, c->hist.p);
         B2_KERNEL_CHECK();
     }
@@ -510,6 +525,7 @@ int data_costs_normalize(b2tex_ctx *c, float gmax, const uint32_t *bins, b2tex_d
         upper_bound = ((float)i / (float)(HIST_BINS - 1)) * (gmax - 0.0f) + 0.0f;
     }
     if (c->nnz) {
+        ScopedTimer tm(c, "k_normalize", 8.0 * (double)c->nnz);
         k_normalize<<<(unsigned)((c->nnz + 255) / 256), 256, 0, c->stream>>>(c->dc_quality.p, c->nnz, percentile,
                                                                             c->dc_cost.p);
         B2_KERNEL_CHECK();

@@ -150,9 +150,9 @@ __global__ void k_valid4(const uint8_t *__restrict__ inv, uint8_t *__restrict__ 
 
 }  // namespace
 
-int prepare_images(b2tex_ctx *c, int data_term)
+int prepare_images(b2tex_ctx *c, int data_term, bool force)
 {
-    if (c->images_prepared && c->prepared_data_term == data_term) return B2TEX_OK;
+    if (!force && c->images_prepared && c->prepared_data_term == data_term) return B2TEX_OK;
     if (!c->K) { set_error("prepare_images: no views set"); return B2TEX_ERR_ARG; }
     cudaStream_t s = c->stream;
     const uint32_t K = c->K;
@@ -160,6 +160,7 @@ int prepare_images(b2tex_ctx *c, int data_term)
 
     if (data_term == 1) {
         B2_TRY(c->grad.alloc(total_px));
+        ScopedTimer tm(c, "k_lum_sobel", 4.0 * (double)total_px);  // 3 B rgb read + 1 B gradient written
         for (uint32_t v = 0; v < K; ++v) {
             int w = c->views_host[v].width, h = c->views_host[v].height;
             dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH);

@@ -439,6 +439,7 @@ int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *efix)
     Mrf m = make_mrf(c);
     cudaStream_t s = c->stream;
     B2_TRY(set_iter(c, m, t));
+    ScopedTimer tm(c, "mrf_iteration", 14.0 * (double)c->nnz + 20.0 * (double)(c->face_end - c->face_begin));
     static const bool no_graph = getenv("B2TEX_NO_GRAPH") != nullptr;
     if (no_graph) {
         B2_TRY(enqueue_iteration(c, m));

@@ -409,6 +409,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
     cudaStream_t s = c->stream;
     B2_TRY(prepare_images(c, c->prepared_data_term >= 0 ? c->prepared_data_term : 1));
     const uint32_t Vn = c->Vn;
+    ScopedTimer *tm_asm = new ScopedTimer(c, "seam_assembly");
     DevBuf<uint32_t> cnt, row_vertex;
     B2_TRY(cnt.alloc((size_t)Vn + 1));
     B2_TRY(cnt.zero(s));
@@ -479,6 +480,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
     info->cg_launch_iterations = 0;
     info->cg_ms = 0.0f;
 
+    delete tm_asm;
     B2_TRY(c->seam_status.alloc(16));
     B2_TRY(c->seam_status.zero(s));
     if (R) {

@@ -1,0 +1,232 @@
+"""Host-side driver of the resident pipeline, one process per GPU.
+
+world == 1 : data costs -> view selection -> seam leveling on one context.
+world  > 1 : faces are split into `world` contiguous ranges (rank r owns [r*psz, (r+1)*psz)):
+    data costs : each rank evaluates its own faces; the normalisation is global, so
+                 qualities -> all_reduce(MAX) -> histogram -> all_reduce(SUM, 10 000 bins) -> normalise
+                 (calculate_data_costs.cpp:277-302)
+    MRF        : each rank runs the forest-BCD iteration on its own nodes with cut edges conditioned
+                 (the schedule of oracle/mrf.c with num_parts = world); after every iteration the
+                 label ranges are all-gathered and the 32.32 fixed-point energy is all-reduced for the
+                 StopWhenReturnsDiminish test (view_selection.cpp:84)
+    seam       : replicated on every rank (row-partitioned PCG with a halo exchange is not built yet)
+torch.distributed (NCCL) is plumbing only; every kernel is in libb2tex.so.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+
+def returns_diminish(efix, t, window, ratio):
+    """StopWhenReturnsDiminish(window, ratio) (view_selection.cpp:84) on 32.32 fixed-point energies;
+    same double arithmetic as b2tex_view_selection_run and oracle/mrf.c."""
+    if t < window:
+        return False
+    e0, e1 = float(efix[t - window]), float(efix[t])
+    return e0 <= 0.0 or (e0 - e1) / e0 < ratio
+
+
+def gather_label_ranges(dist, labels, mine, gathered, fb, fe, F):
+    """All-gather the owned label range of every rank into the full label array (in place).
+    `mine` (psz) and `gathered` (world*psz) are scratch tensors on the same device as `labels`."""
+    mine[: fe - fb].copy_(labels[fb:fe])
+    dist.all_gather_into_tensor(gathered, mine)
+    labels.copy_(gathered[:F])
+    return labels
+
+
+class _DevArray:
+    """Expose a raw device pointer of the library to torch (zero copy)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class ShardedPipeline:
+    def __init__(self, b2, scene, adj, rings, rank=0, world=1, local_rank=0, upload=True):
+        self.b2, self.scene, self.adj, self.rings = b2, scene, adj, rings
+        self.rank, self.world = rank, world
+        self.F = scene.num_faces
+        self.psz = (self.F + world - 1) // world
+        self.fb = min(self.F, rank * self.psz)
+        self.fe = min(self.F, (rank + 1) * self.psz)
+        self.ctx = b2.Context(local_rank)
+        if upload:
+            self.upload()
+
+    def upload(self):
+        c = self.ctx
+        c.set_scene(self.scene)
+        c.set_adjacency(*self.adj)
+        c.set_vertex_rings(*self.rings)
+        if self.world > 1:
+            c.set_face_range(self.fb, self.fe)
+
+    def describe(self):
+        if self.world == 1:
+            return "1 GPU, whole scene resident"
+        return (f"{self.world} GPUs: faces split in {self.world} contiguous ranges for data costs (NCCL max + "
+                f"histogram all-reduce) and MRF (label all-gather + energy all-reduce per iteration); seam "
+                f"leveling replicated")
+
+    # ---- one pass of the hot path ---------------------------------------------------------------
+    def step(self):
+        if self.world == 1:
+            return self._step_single()
+        return self._step_sharded()
+
+    def _step_single(self):
+        c = self.ctx
+        t0 = time.perf_counter()
+        dc = c.data_costs_run()
+        t1 = time.perf_counter()
+        mrf, trace = c.view_selection_run()
+        t2 = time.perf_counter()
+        seam = c.seam_run()
+        t3 = time.perf_counter()
+        return dict(dc=dc, mrf=mrf, seam=seam, trace=trace,
+                    stage_s=dict(data_costs=t1 - t0, view_selection=t2 - t1, seam_leveling=t3 - t2))
+
+    def _step_sharded(self):
+        import torch
+        import torch.distributed as dist
+        c, b2 = self.ctx, self.b2
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t0 = time.perf_counter()
+        info = c.data_costs_qualities()
+        gmax = torch.tensor([info.max_quality], dtype=torch.float32, device=dev)
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
+        gmax_f = float(gmax.item())
+        c.data_costs_histogram_device(gmax_f)
+        c.synchronize()
+        hp, hn = c.device_ptr("hist")
+        hist = torch.as_tensor(_DevArray(hp, hn, "<i4"), device=dev)
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        bins = hist.cpu().numpy().astype(np.uint32)
+        cand, rays = info.candidates, info.rays
+        info = c.data_costs_normalize(gmax_f, bins)
+        info.candidates, info.rays = cand, rays
+        counts = torch.tensor([info.nnz], dtype=torch.int64, device=dev)
+        dist.all_reduce(counts)
+        total_nnz = int(counts.item())
+        t1 = time.perf_counter()
+
+        # ---- MRF with boundary-label exchange ----
+        P, psz, F = self.world, self.psz, self.F
+        p = b2.mrf_params(num_parts=P)
+        ratio = float(np.float32(p.ratio))
+        efix = [self._allreduce_energy(c.mrf_init(num_parts=P))]
+        lp, ln = c.device_ptr("labels")
+        labels = torch.as_tensor(_DevArray(lp, ln, "<i4"), device=dev)
+        gathered = torch.zeros(P * psz, dtype=torch.int32, device=dev)
+        mine = torch.zeros(psz, dtype=torch.int32, device=dev)
+
+        def exchange():
+            gather_label_ranges(dist, labels, mine, gathered, self.fb, self.fe, F)
+            torch.cuda.current_stream().synchronize()
+
+        exchange()
+        t = 1
+        while t <= p.max_iterations:
+            e = c.mrf_iterate(t)
+            exchange()
+            efix.append(self._allreduce_energy(e))
+            if returns_diminish(efix, t, p.window, ratio):
+                break
+            t += 1
+        t = min(t, p.max_iterations)
+        mrf = b2.B2MrfInfo()
+        mrf.iterations = t
+        mrf.energy_initial = efix[0] / 4294967296.0
+        mrf.energy_final = efix[t] / 4294967296.0
+        mrf.sweep_bytes = 14 * total_nnz + 20 * F
+        t2 = time.perf_counter()
+        seam = c.seam_run()
+        t3 = time.perf_counter()
+        info.nnz = total_nnz
+        return dict(dc=info, mrf=mrf, seam=seam, trace=np.array(efix) / 4294967296.0,
+                    stage_s=dict(data_costs=t1 - t0, view_selection=t2 - t1, seam_leveling=t3 - t2))
+
+    def _allreduce_energy(self, e):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([e], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        return int(t.item())
+
+    # ---- e2e for the sharded configuration: upload from host every step ----------------------------
+    def e2e(self, torch, steps=1, warmup=1):
+        import torch.distributed as dist
+        s = self.scene
+        h2d = (s.verts.nbytes + s.faces.nbytes + s.face_normals.nbytes + s.images.nbytes + self.adj[0].nbytes
+               + self.adj[1].nbytes + sum(r.nbytes for r in self.rings))
+        times = []
+        d2h = 0
+        for i in range(warmup + steps):
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            self.upload()
+            res = self.step()
+            labels = self.ctx.labels_download()
+            x = self.ctx.seam_download(res["seam"])["x"]
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if self.world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if i >= warmup:
+                times.append(float(dt.item()))
+            d2h = labels.nbytes + x.nbytes
+        t = sum(times) / len(times)
+        return {"value": self.F / t, "unit": "faces/s", "h2d_bytes_per_step": int(h2d) * self.world,
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t,
+                "path": "resident API, scene re-uploaded from host memory every step on every rank"}
+
+
+def e2e_host_path(b2, torch, s, adj, rings, steps=1, warmup=1):
+    """The reference-shaped call sequence with pinned HOST buffers (what a texrecon drop-in does):
+    b2tex_calculate_data_costs -> b2tex_view_selection -> b2tex_global_seam_leveling."""
+    import copy
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        try:
+            t = t.pin_memory()
+        except Exception:
+            pass
+        return t.numpy(), t
+
+    keep = []
+    sp = copy.copy(s)
+    for name in ("verts", "faces", "face_normals", "images"):
+        arr, t = pin(getattr(s, name))
+        setattr(sp, name, arr)
+        keep.append(t)
+    ap, t = pin(adj[0]); keep.append(t)
+    ai, t = pin(adj[1]); keep.append(t)
+    pr = []
+    for r in rings:
+        a, t = pin(r); keep.append(t); pr.append(a)
+    times, h2d, d2h = [], 0, 0
+    for i in range(warmup + steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dc = b2.calculate_data_costs(sp)
+        labels, minfo = b2.view_selection(dc, ap, ai)
+        g = b2.global_seam_leveling(sp, pr, labels)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        mesh_b = sp.verts.nbytes + sp.faces.nbytes + sp.face_normals.nbytes
+        dc_b = dc.face_ptr.nbytes + dc.view.nbytes + dc.cost.nbytes
+        h2d = (mesh_b + sp.images.nbytes) + (dc_b + ap.nbytes + ai.nbytes) + \
+              (mesh_b + sp.images.nbytes + sum(r.nbytes for r in pr) + labels.nbytes)
+        d2h = dc_b + 2 * labels.nbytes + g["row_ptr"].nbytes + g["row_label"].nbytes + g["x"].nbytes
+    t = sum(times) / len(times)
+    return {"value": s.num_faces / t, "unit": "faces/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t,
+            "path": "b2tex_calculate_data_costs -> b2tex_view_selection -> b2tex_global_seam_leveling, pinned host buffers"}

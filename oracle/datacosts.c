@@ -266,7 +266,9 @@ int orc_data_costs(const float *verts, uint32_t num_verts, const uint32_t *faces
         const float *view_pos = tv->pos;
         const float *viewing_direction = tv->viewdir;
 
-        for (uint32_t face_id = 0; face_id < num_faces; ++face_id) { /* :168 */
+        uint32_t f_lo = 0, f_hi = num_faces;
+        if (settings->face_end > settings->face_begin) { f_lo = settings->face_begin; f_hi = settings->face_end < num_faces ? settings->face_end : num_faces; }
+        for (uint32_t face_id = f_lo; face_id < f_hi; ++face_id) { /* :168 */
             const float *v1 = verts + 3 * (size_t)faces[3 * (size_t)face_id];
             const float *v2 = verts + 3 * (size_t)faces[3 * (size_t)face_id + 1];
             const float *v3 = verts + 3 * (size_t)faces[3 * (size_t)face_id + 2];
