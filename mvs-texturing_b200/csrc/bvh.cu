@@ -86,6 +86,29 @@ __global__ void k_morton(const float *__restrict__ verts, const uint32_t *__rest
     ids[f] = f;
 }
 
+// Morton keys of the vertices (for coherent visibility rays)
+__global__ void k_morton_verts(const float *__restrict__ verts, uint32_t nv, const uint32_t *__restrict__ bnd,
+                               uint64_t *keys, uint32_t *ids)
+{
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    uint64_t code = 0;
+    for (int k = 0; k < 3; ++k) {
+        float lo = ord2f(bnd[k]), ext = ord2f(bnd[3 + k]) - lo;
+        if (!(ext > 0.0f)) ext = 1.0f;
+        float t = fminf(fmaxf((verts[3 * (size_t)v + k] - lo) / ext, 0.0f), 1.0f);
+        code |= expand21((uint64_t)(t * 2097151.0f)) << (2 - k);
+    }
+    keys[v] = code;
+    ids[v] = v;
+}
+
+__global__ void k_invert_perm(const uint32_t *__restrict__ order, uint32_t n, uint32_t *rank)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rank[order[i]] = i;
+}
+
 __global__ void k_gather_tris(const float *__restrict__ verts, const uint32_t *__restrict__ faces,
                               const uint32_t *__restrict__ ids, uint32_t nf, float *tri)
 {
@@ -192,9 +215,9 @@ int build_bvh(b2tex_ctx *c, bool force)
     c->bvh.num_tris = n;
     if (n == 0) { c->bvh_built = true; return B2TEX_OK; }
 
-    DevBuf<uint32_t> bnd, ids_in, ids_out, counters;
-    DevBuf<uint64_t> keys_in, keys_out;
-    DevBuf<int> parent_internal, parent_leaf;
+    DevBuf<uint32_t> &bnd = c->s_bnd, &ids_in = c->s_ids_in, &ids_out = c->s_ids_out, &counters = c->s_counters;
+    DevBuf<uint64_t> &keys_in = c->s_keys_in, &keys_out = c->s_keys_out;
+    DevBuf<int> &parent_internal = c->s_parent_internal, &parent_leaf = c->s_parent_leaf;
     B2_TRY(bnd.alloc(8));
     k_bounds_init<<<1, 32, 0, s>>>(bnd.p);
     k_bounds<<<std::max(1, c->num_sms * 4), 256, 0, s>>>(c->verts.p, c->Vn, bnd.p);
@@ -207,6 +230,21 @@ int build_bvh(b2tex_ctx *c, bool force)
     float diag = sqrtf(ext[0] * ext[0] + ext[1] * ext[1] + ext[2] * ext[2]);
     float pad = 1e-5f * diag;  // same conservative padding as oracle/bvh.c
 
+    // vertex order for the ray bitmaps
+    {
+        const uint32_t nv = c->Vn;
+        DevBuf<uint64_t> &vk_in = c->s_vk_in, &vk_out = c->s_vk_out;
+        DevBuf<uint32_t> &vi_in = c->s_vi_in;
+        B2_TRY(vk_in.alloc(nv)); B2_TRY(vk_out.alloc(nv)); B2_TRY(vi_in.alloc(nv));
+        B2_TRY(c->vorder.alloc(nv)); B2_TRY(c->vrank.alloc(nv));
+        k_morton_verts<<<(nv + 255) / 256, 256, 0, s>>>(c->verts.p, nv, bnd.p, vk_in.p, vi_in.p);
+        size_t vb = 0;
+        B2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, vb, vk_in.p, vk_out.p, vi_in.p, c->vorder.p, (int)nv, 0, 63, s));
+        B2_TRY(c->cub_tmp.alloc(vb));
+        B2_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, vb, vk_in.p, vk_out.p, vi_in.p, c->vorder.p, (int)nv, 0, 63, s));
+        k_invert_perm<<<(nv + 255) / 256, 256, 0, s>>>(c->vorder.p, nv, c->vrank.p);
+        B2_KERNEL_CHECK();
+    }
     B2_TRY(keys_in.alloc(n)); B2_TRY(keys_out.alloc(n));
     B2_TRY(ids_in.alloc(n)); B2_TRY(ids_out.alloc(n));
     k_morton<<<(n + 255) / 256, 256, 0, s>>>(c->verts.p, c->faces.p, n, bnd.p, keys_in.p, ids_in.p);

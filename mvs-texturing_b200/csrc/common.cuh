@@ -145,6 +145,11 @@ struct b2tex_ctx {
     // bvh
     b2::Bvh bvh;
     bool bvh_built = false;
+    b2::DevBuf<uint32_t> vrank, vorder;  // Morton rank of every vertex and its inverse
+    // persistent scratch (grow only): cudaMalloc/cudaFree inside a stage would serialise the device
+    b2::DevBuf<uint32_t> s_bnd, s_ids_in, s_ids_out, s_counters, s_vi_in, s_cnt32, s_row_vertex, s_rcnt;
+    b2::DevBuf<uint64_t> s_keys_in, s_keys_out, s_vk_in, s_vk_out, s_cnt64;
+    b2::DevBuf<int> s_parent_internal, s_parent_leaf;
 
     // data costs (CSR by face over [face_begin, face_end) -> global face ids keep absolute ptr layout)
     b2::DevBuf<uint64_t> dc_ptr;       // F+1
@@ -173,6 +178,12 @@ struct b2tex_ctx {
     b2::DevBuf<float> mrf_H, mrf_hminp1;
     b2::DevBuf<uint32_t> mrf_amin, mrf_level, mrf_order, mrf_lvlptr, mrf_cursor;
     b2::DevBuf<unsigned long long> mrf_energy;
+    b2::DevBuf<uint32_t> mrf_mask;     // per-node label bitmasks
+    b2::DevBuf<uint16_t> mrf_mpre;     // labels in lower mask words
+    uint32_t mrf_mask_words = 0;
+    b2::DevBuf<uint4> mrf_adj4;        // compact degree<=3 adjacency
+    b2::DevBuf<uint32_t> mrf_queue;    // forest frontier lists + stamps
+    b2::DevBuf<uint32_t> mrf_sort;     // radix sort keys/values of the level bucketing
     b2tex_mrf_params mrf_params{};
     bool mrf_ready = false;
     void *mrf_graph_exec = nullptr;    // cudaGraphExec_t of one iteration

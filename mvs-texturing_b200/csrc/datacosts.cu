@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) k_cull(const float *__restrict__ verts, c
                                               uint32_t K, uint32_t face_begin, uint32_t face_end, float cos_thr,
                                               uint64_t *cand_cnt, const uint64_t *__restrict__ cand_ptr,
                                               uint16_t *cand_view, uint32_t *cand_face, uint32_t *need_bits,
-                                              uint32_t vwords)
+                                              uint32_t vwords, const uint32_t *__restrict__ vrank)
 {
     uint32_t f = face_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= face_end) return;
@@ -131,6 +131,10 @@ __global__ void __launch_bounds__(256) k_cull(const float *__restrict__ verts, c
     load_face(verts, faces, normals, f, g, vid);
     uint64_t base = FILL ? cand_ptr[f] : 0;
     uint32_t count = 0;
+    // ray bitmaps are indexed by the Morton rank of the vertex so that a warp of k_rays traces 32
+    // spatially adjacent origins towards the same camera
+    uint32_t vr[3] = {0, 0, 0};
+    if (FILL && need_bits) { vr[0] = vrank[vid[0]]; vr[1] = vrank[vid[1]]; vr[2] = vrank[vid[2]]; }
     for (uint32_t j = 0; j < K; ++j) {
         if (!cull_pair(views[j], g, cos_thr)) continue;
         if (FILL) {
@@ -139,8 +143,8 @@ __global__ void __launch_bounds__(256) k_cull(const float *__restrict__ verts, c
             if (need_bits) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    size_t word = (size_t)j * vwords + (vid[k] >> 5);
-                    uint32_t bit = 1u << (vid[k] & 31);
+                    size_t word = (size_t)j * vwords + (vr[k] >> 5);
+                    uint32_t bit = 1u << (vr[k] & 31);
                     if (!(need_bits[word] & bit)) atomicOr(&need_bits[word], bit);
                 }
             }
@@ -154,7 +158,8 @@ __global__ void __launch_bounds__(256) k_cull(const float *__restrict__ verts, c
 __global__ void __launch_bounds__(256) k_rays(const float *__restrict__ verts, uint32_t Vn,
                                               const ViewDev *__restrict__ views, uint32_t K,
                                               const uint32_t *__restrict__ need_bits, uint32_t *occ_bits,
-                                              uint32_t vwords, const BvhNode *__restrict__ nodes,
+                                              uint32_t vwords, const uint32_t *__restrict__ vorder,
+                                              const BvhNode *__restrict__ nodes,
                                               const float *__restrict__ tri, uint32_t num_tris,
                                               unsigned long long *ray_count)
 {
@@ -165,9 +170,10 @@ __global__ void __launch_bounds__(256) k_rays(const float *__restrict__ verts, u
     uint32_t word = need_bits[warp];
     if (word == 0) { if (lane == 0) occ_bits[warp] = 0; return; }
     uint32_t view = (uint32_t)(warp / vwords);
-    uint32_t v = (uint32_t)(warp % vwords) * 32 + lane;
+    uint32_t rank = (uint32_t)(warp % vwords) * 32 + lane;
     bool occ = false;
     if ((word >> lane) & 1u) {
+        const uint32_t v = vorder[rank];
         const ViewDev &V = views[view];
         float ox = verts[3 * (size_t)v], oy = verts[3 * (size_t)v + 1], oz = verts[3 * (size_t)v + 2];
         float dx = V.pos[0] - ox, dy = V.pos[1] - oy, dz = V.pos[2] - oz;   // :203
@@ -292,6 +298,7 @@ __global__ void __launch_bounds__(256) k_quality(const float *__restrict__ verts
                                                  const uint16_t *__restrict__ cand_view,
                                                  const uint32_t *__restrict__ cand_face, uint64_t num_cand,
                                                  const uint32_t *__restrict__ occ_bits, uint32_t vwords,
+                                                 const uint32_t *__restrict__ vrank,
                                                  int data_term, float *cand_q, uint32_t *max_q_bits)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,8 +312,10 @@ __global__ void __launch_bounds__(256) k_quality(const float *__restrict__ verts
         bool visible = true;
         if (occ_bits) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if ((occ_bits[(size_t)j * vwords + (vid[k] >> 5)] >> (vid[k] & 31)) & 1u) visible = false;
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t r = vrank[vid[k]];
+                if ((occ_bits[(size_t)j * vwords + (r >> 5)] >> (r & 31)) & 1u) visible = false;
+            }
         }
         if (visible) {
             const ViewDev &V = views[j];
@@ -414,7 +423,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
 
     B2_TRY(c->cand_ptr.alloc((size_t)F + 1));
     B2_TRY(c->dc_ptr.alloc((size_t)F + 1));
-    DevBuf<uint64_t> cnt;
+    DevBuf<uint64_t> &cnt = c->s_cnt64;
     B2_TRY(cnt.alloc((size_t)F + 1));
     B2_TRY(cnt.zero(s));
     B2_TRY(c->scalars.alloc(std::max<size_t>(c->scalars.n, 256)));
@@ -424,7 +433,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     if (nf) {
         ScopedTimer tm(c, "k_cull<count>", mesh_bytes + 8.0 * nf);
         k_cull<false><<<blocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->normals.p, c->views_dev.p, K, fb, fe,
-                                             cos_thr, cnt.p, nullptr, nullptr, nullptr, nullptr, vwords);
+                                             cos_thr, cnt.p, nullptr, nullptr, nullptr, nullptr, vwords, nullptr);
     }
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u64(c, cnt.p, c->cand_ptr.p, (size_t)F + 1));
@@ -444,7 +453,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
         ScopedTimer tm(c, "k_cull<fill>", mesh_bytes + 6.0 * (double)num_cand);
         k_cull<true><<<blocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->normals.p, c->views_dev.p, K, fb, fe,
                                             cos_thr, nullptr, c->cand_ptr.p, c->cand_view.p, c->cand_face.p,
-                                            vis ? c->need_bits.p : nullptr, vwords);
+                                            vis ? c->need_bits.p : nullptr, vwords, c->vrank.p);
     }
     B2_KERNEL_CHECK();
     unsigned long long *ray_count = reinterpret_cast<unsigned long long *>(c->scalars.p + 2);
@@ -453,7 +462,8 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
         size_t rblocks = (warps * 32 + 255) / 256;
         ScopedTimer tm(c, "k_rays", 8.0 * (double)warps + 12.0 * c->Vn);
         k_rays<<<(unsigned)rblocks, 256, 0, s>>>(c->verts.p, c->Vn, c->views_dev.p, K, c->need_bits.p, c->occ_bits.p,
-                                                 vwords, c->bvh.nodes.p, c->bvh.tri.p, c->bvh.num_tris, ray_count);
+                                                 vwords, c->vorder.p, c->bvh.nodes.p, c->bvh.tri.p, c->bvh.num_tris,
+                                                 ray_count);
         B2_KERNEL_CHECK();
     }
     if (num_cand) {
@@ -461,6 +471,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
         ScopedTimer tm(c, "k_quality", 10.0 * (double)num_cand + mesh_bytes);
         k_quality<<<(unsigned)qblocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->views_dev.p, c->cand_view.p,
                                                     c->cand_face.p, num_cand, vis ? c->occ_bits.p : nullptr, vwords,
+                                                    c->vrank.p,
                                                     st->data_term, c->cand_q.p, c->scalars.p);
         B2_KERNEL_CHECK();
     }

@@ -7,10 +7,26 @@
 //   * forest sampling is order independent (hash priorities, level-synchronous rounds)
 //   * messages are summed in adjacency order in fp32 (no FMA: additions and minima only)
 //   * the energy used for termination is 32.32 fixed point, summed with integer atomics.
-// Work mapping: a group of G lanes (G = 4..32, chosen from the mean label count) owns one node and
-// strides over its sorted label list; min/argmin by warp shuffles; one launch per forest level,
-// the whole iteration captured in a CUDA graph.
+//
+// Execution (one iteration = 4 launches, no host round trips except the energy read-back):
+//   k_forest   persistent cooperative kernel: root selection, `rounds` growth rounds separated by
+//              grid.sync(), then bucketing of the forest nodes by level (deepest level first,
+//              every level padded to a multiple of 32 entries) -- all in one launch
+//   k_up<G>    persistent DATAFLOW kernel: warps claim 32/G nodes at a time in bucket order; a node
+//              waits on per-node flags of its children instead of a grid-wide level barrier, so the
+//              sweep is bounded by tree depth x node latency, not by 33 launches/barriers.  G lanes
+//              (4..32, from the mean label count) stride over the node's sorted label list; child
+//              messages are looked up through per-node label bitmasks + prefix popcounts (O(1)
+//              merge-join) or by binary search when K is large; min/argmin by warp shuffles
+//   k_down     persistent dataflow kernel, one thread per node waiting on its parent's flag
+//   k_energy   fixed-point energy
+#include <cooperative_groups.h>
+#include <cub/cub.cuh>
+#include <stdlib.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b2 {
 
@@ -18,6 +34,9 @@ namespace {
 
 constexpr uint32_t LVL_NONE = 0xFFFFFFFFu;
 constexpr uint32_t LVL_DEAD = 0xFFFFFFFEu;
+constexpr uint32_t NO_NODE = 0xFFFFFFFFu;
+constexpr int MAX_LEVELS = 1024;  // rounds + 1 must fit (shared-memory bucketing)
+constexpr int MAX_MASK_WORDS = 64;  // label bitmasks up to K = 2047 views, else binary search
 
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x)
 {
@@ -37,22 +56,96 @@ __device__ __forceinline__ bool root_cand(uint32_t v, uint32_t seed_t, uint32_t 
 struct Mrf {
     uint32_t F, nb, ne;          // nodes, owned node range
     const uint32_t *adj_ptr, *adj_idx;
+    const uint4 *adj4;           // compact adjacency: x,y,z = neighbours, w = degree (CSR if > 3)
     const uint64_t *ptr;
     const uint16_t *view;
     const float *cost;
     float *H, *hminp1;
-    uint32_t *amin, *level, *labels, *order, *lvl_ptr, *cursor;
-    const uint32_t *iter;        // device scalar: current iteration
-    uint32_t *max_prio;          // device scalar for single-root mode
+    uint32_t *amin, *level, *labels, *order;
+    uint32_t *ctl;               // control block, see CTL_* offsets
+    uint32_t *flag_up, *flag_dn;
+    uint32_t *queue, *qstamp;    // frontier lists [2][F] and push de-duplication stamps [F]
+    uint32_t *sort_key_in, *sort_key_out, *sort_val_in, *sort_val_out;
+    const uint32_t *mask;        // [F][mask_words] label bitmask (bit = label), or null
+    const uint16_t *mpre;        // [F][mask_words] labels in lower words
     unsigned long long *energy;
-    uint32_t part_size, rounds, rdiv, seed;
+    uint32_t mask_words;
+    uint32_t part_size, rounds, rdiv, seed, iter;
 };
+// control block layout (uint32 words)
+constexpr int CTL_CNT = 0;                      // [MAX_LEVELS] per-level counts
+constexpr int CTL_CUR = MAX_LEVELS;             // [MAX_LEVELS] per-level fill cursors
+constexpr int CTL_OFF = 2 * MAX_LEVELS;         // [MAX_LEVELS+1] padded bucket offsets (deepest first)
+constexpr int CTL_TOTAL = 3 * MAX_LEVELS + 8;   // padded number of order entries
+constexpr int CTL_UTOTAL = 3 * MAX_LEVELS + 9;  // forest nodes (unpadded)
+constexpr int CTL_MAXPRIO = 3 * MAX_LEVELS + 12;  // 64-bit, 8-byte aligned
+constexpr int CTL_QN = 3 * MAX_LEVELS + 16;      // [MAX_LEVELS+1] frontier sizes per round
+constexpr int CTL_WORDS = 4 * MAX_LEVELS + 32;
 
 __device__ __forceinline__ bool same_part(const Mrf &m, uint32_t a, uint32_t b)
 {
+    if (m.part_size >= m.F) return true;  // single partition: no integer divisions on the hot path
     return a / m.part_size == b / m.part_size;
 }
 __device__ __forceinline__ bool owned(const Mrf &m, uint32_t v) { return v >= m.nb && v < m.ne; }
+__device__ __forceinline__ bool local_pair(const Mrf &m, uint32_t v, uint32_t w)
+{
+    return owned(m, w) && same_part(m, v, w);
+}
+
+// Neighbour list of one node.  Face graphs of manifold meshes have degree <= 3: one 16-byte load
+// replaces the adj_ptr -> adj_idx dependent chain; larger degrees fall back to the CSR arrays.
+struct Nb { uint32_t deg, x, y, z, base; };
+__device__ __forceinline__ Nb load_nb(const Mrf &m, uint32_t v)
+{
+    const uint4 a = __ldg(m.adj4 + v);
+    Nb n; n.deg = a.w; n.x = a.x; n.y = a.y; n.z = a.z;
+    n.base = a.w > 3 ? m.adj_ptr[v] : 0;
+    return n;
+}
+__device__ __forceinline__ uint32_t nb_at(const Mrf &m, const Nb &n, uint32_t i)
+{
+    if (n.deg <= 3) return i == 0 ? n.x : (i == 1 ? n.y : n.z);
+    return m.adj_idx[n.base + i];
+}
+
+__global__ void __launch_bounds__(256) k_build_adj4(uint32_t F, const uint32_t *__restrict__ adj_ptr,
+                                                    const uint32_t *__restrict__ adj_idx, uint4 *adj4)
+{
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= F) return;
+    uint32_t a0 = adj_ptr[v], d = adj_ptr[v + 1] - a0;
+    uint4 r = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, d);
+    if (d <= 3) {
+        if (d > 0) r.x = adj_idx[a0];
+        if (d > 1) r.y = adj_idx[a0 + 1];
+        if (d > 2) r.z = adj_idx[a0 + 2];
+    }
+    adj4[v] = r;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// polling load without acquire semantics (no L1 invalidation per poll); pair with ONE acquire fence
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 template <int G>
 __global__ void __launch_bounds__(256) k_init_labels(Mrf m)
@@ -79,131 +172,41 @@ __global__ void __launch_bounds__(256) k_init_labels(Mrf m)
     }
 }
 
-__global__ void k_max_prio(Mrf m)
-{
-    uint32_t v = m.nb + blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t p = 0;
-    bool have = false;
-    if (v < m.ne && m.labels[v] != 0) { p = prio(v, iter_seed(m.seed, *m.iter)); have = true; }
-    // encode "have" so that prio 0 still wins over "none": store prio as 33-bit? use p|1 trick
-    // (prio is a bijection; collisions of p|1 only pair two nodes -> both may become roots only if
-    // non adjacent; the oracle uses the exact maximum, so keep exactness with a 64-bit key)
-    unsigned long long key = have ? (((unsigned long long)p << 1) | 1ull) : 0ull;
-    for (int s = 16; s; s >>= 1) {
-        unsigned long long o = __shfl_xor_sync(0xffffffffu, key, s);
-        key = o > key ? o : key;
-    }
-    if ((threadIdx.x & 31) == 0 && key) atomicMax(reinterpret_cast<unsigned long long *>(m.max_prio), key);
-}
-
-__global__ void __launch_bounds__(256) k_forest_init(Mrf m)
+// per-node label bitmask + number of labels in lower words (one thread per node)
+__global__ void __launch_bounds__(256) k_build_masks(Mrf m, uint32_t *mask, uint16_t *mpre)
 {
     uint32_t v = m.nb + blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= m.ne) return;
-    const uint32_t seed_t = iter_seed(m.seed, *m.iter);
-    if (m.labels[v] == 0) { m.level[v] = LVL_DEAD; return; }
-    const uint32_t pv = prio(v, seed_t);
-    bool eligible = true, is_root;
-    if (m.rdiv) is_root = root_cand(v, seed_t, m.rdiv);
-    else {
-        unsigned long long key = *reinterpret_cast<unsigned long long *>(m.max_prio);
-        is_root = key == ((((unsigned long long)pv) << 1) | 1ull);
-    }
-    for (uint32_t a = m.adj_ptr[v]; a < m.adj_ptr[v + 1]; ++a) {
-        uint32_t w = m.adj_idx[a];
-        if (m.labels[w] == 0) continue;
-        if (!(owned(m, w) && same_part(m, v, w))) { if (prio(w, seed_t) > pv) eligible = false; continue; }
-        if (m.rdiv && is_root && root_cand(w, seed_t, m.rdiv) && prio(w, seed_t) > pv) is_root = false;
-    }
-    m.level[v] = !eligible ? LVL_DEAD : (is_root ? 0u : LVL_NONE);
-}
-
-__device__ __forceinline__ uint32_t count_in_forest(const Mrf &m, uint32_t v, uint32_t r)
-{
-    uint32_t c = 0;
-    for (uint32_t a = m.adj_ptr[v]; a < m.adj_ptr[v + 1]; ++a) {
-        uint32_t w = m.adj_idx[a];
-        if (owned(m, w) && same_part(m, v, w) && ((volatile uint32_t *)m.level)[w] < r) ++c;
-    }
-    return c;
-}
-
-__global__ void __launch_bounds__(256) k_forest_round(Mrf m, uint32_t r)
-{
-    uint32_t v = m.nb + blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= m.ne) return;
-    if (m.level[v] != LVL_NONE) return;
-    uint32_t c = count_in_forest(m, v, r);
-    if (c >= 2) { m.level[v] = LVL_DEAD; return; }
-    if (c != 1) return;
-    const uint32_t seed_t = iter_seed(m.seed, *m.iter);
-    const uint32_t pv = prio(v, seed_t);
-    for (uint32_t a = m.adj_ptr[v]; a < m.adj_ptr[v + 1]; ++a) {
-        uint32_t w = m.adj_idx[a];
-        if (!(owned(m, w) && same_part(m, v, w))) continue;
-        uint32_t lw = ((volatile uint32_t *)m.level)[w];
-        if (!(lw == LVL_NONE || lw == r)) continue;
-        if (prio(w, seed_t) < pv) continue;
-        if (count_in_forest(m, w, r) == 1) return;  // a stronger adjacent candidate: wait
-    }
-    m.level[v] = r;
-}
-
-// ---- bucket nodes by level -------------------------------------------------------------------
-constexpr int MAX_LEVELS = 1024;  // rounds + 1 must fit for the shared-memory bucketing
-
-__global__ void __launch_bounds__(256) k_bucket_count(Mrf m)
-{
-    extern __shared__ uint32_t sc[];
-    for (uint32_t i = threadIdx.x; i <= m.rounds; i += blockDim.x) sc[i] = 0;
-    __syncthreads();
-    for (uint32_t v = m.nb + blockIdx.x * blockDim.x + threadIdx.x; v < m.ne; v += gridDim.x * blockDim.x) {
-        uint32_t l = m.level[v];
-        if (l <= m.rounds) atomicAdd(&sc[l], 1u);
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i <= m.rounds; i += blockDim.x)
-        if (sc[i]) atomicAdd(&m.cursor[i], sc[i]);
-}
-
-__global__ void k_bucket_scan(Mrf m)
-{
-    // single thread: rounds+1 entries
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        uint32_t acc = 0;
-        for (uint32_t i = 0; i <= m.rounds; ++i) {
-            uint32_t c = m.cursor[i];
-            m.lvl_ptr[i] = acc;
-            m.cursor[i] = acc;
-            acc += c;
+    const uint32_t W = m.mask_words;
+    uint32_t *mw = mask + (size_t)v * W;
+    uint16_t *mp = mpre + (size_t)v * W;
+    uint64_t k = m.ptr[v], end = m.ptr[v + 1];
+    uint32_t seen = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+        uint32_t bits = 0;
+        while (k < end) {
+            uint32_t lab = (uint32_t)m.view[k] + 1u;
+            if ((lab >> 5) != w) break;
+            bits |= 1u << (lab & 31);
+            ++k;
         }
-        m.lvl_ptr[m.rounds + 1] = acc;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_bucket_fill(Mrf m)
-{
-    extern __shared__ uint32_t sc[];  // [rounds+1] counts, then [rounds+1] bases
-    uint32_t *cnt = sc, *base = sc + (m.rounds + 1);
-    for (uint32_t start = m.nb + blockIdx.x * blockDim.x; start < m.ne; start += gridDim.x * blockDim.x) {
-        for (uint32_t i = threadIdx.x; i <= m.rounds; i += blockDim.x) cnt[i] = 0;
-        __syncthreads();
-        uint32_t v = start + threadIdx.x;
-        uint32_t l = v < m.ne ? m.level[v] : LVL_DEAD;
-        uint32_t rank = 0;
-        if (l <= m.rounds) rank = atomicAdd(&cnt[l], 1u);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i <= m.rounds; i += blockDim.x)
-            if (cnt[i]) base[i] = atomicAdd(&m.cursor[i], cnt[i]);
-        __syncthreads();
-        if (l <= m.rounds) m.order[base[l] + rank] = v;
-        __syncthreads();
+        mw[w] = bits;
+        mp[w] = (uint16_t)seen;
+        seen += __popc(bits);
     }
 }
 
 // position of label `lab` (= view+1) in node w's sorted list, or -1
 __device__ __forceinline__ long long find_label(const Mrf &m, uint32_t w, uint32_t lab)
 {
+    if (m.mask) {
+        const uint32_t word = lab >> 5, bit = lab & 31;
+        if (word >= m.mask_words) return -1;
+        const uint32_t mw = __ldg(m.mask + (size_t)w * m.mask_words + word);
+        if (!((mw >> bit) & 1u)) return -1;
+        const uint32_t pre = __ldg(m.mpre + (size_t)w * m.mask_words + word);
+        return (long long)(m.ptr[w] + pre + __popc(mw & ((1u << bit) - 1u)));
+    }
     uint64_t lo = m.ptr[w], end = m.ptr[w + 1], hi = end;
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
@@ -214,65 +217,318 @@ __device__ __forceinline__ long long find_label(const Mrf &m, uint32_t w, uint32
     return -1;
 }
 
-// bottom-up min-sum messages for forest level r
-template <int G>
-__global__ void __launch_bounds__(256) k_up(Mrf m, uint32_t r)
+// ---- forest sampling + bucketing, one persistent cooperative launch ------------------------------
+__device__ __forceinline__ uint32_t count_in_forest(const Mrf &m, uint32_t v, uint32_t r)
 {
-    const uint32_t beg = m.lvl_ptr[r], end = m.lvl_ptr[r + 1];
+    uint32_t c = 0;
+    const Nb nb = load_nb(m, v);
+    for (uint32_t i = 0; i < nb.deg; ++i) {
+        uint32_t w = nb_at(m, nb, i);
+        if (local_pair(m, v, w) && __ldcg(m.level + w) < r) ++c;
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(1024, 2) k_forest(Mrf m, int do_bucket)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ uint32_t sm[];  // [rounds+1] counts, [rounds+1] bases
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const uint32_t seed_t = iter_seed(m.seed, m.iter);
+    unsigned long long *maxprio = reinterpret_cast<unsigned long long *>(m.ctl + CTL_MAXPRIO);
+
+    if (m.rdiv == 0) {  // single-root mode: the seen node with the largest priority
+        unsigned long long key = 0;
+        for (uint32_t v = m.nb + tid; v < m.ne; v += nth)
+            if (m.labels[v] != 0) {
+                unsigned long long k = (((unsigned long long)prio(v, seed_t)) << 1) | 1ull;
+                key = k > key ? k : key;
+            }
+        for (int s = 16; s; s >>= 1) {
+            unsigned long long o = __shfl_xor_sync(0xffffffffu, key, s);
+            key = o > key ? o : key;
+        }
+        if ((threadIdx.x & 31) == 0 && key) atomicMax(maxprio, key);
+        grid.sync();
+    }
+    // round 0: eligibility and roots (full scan, once)
+    for (uint32_t v = m.nb + tid; v < m.ne; v += nth) {
+        if (m.labels[v] == 0) { m.level[v] = LVL_DEAD; continue; }
+        const uint32_t pv = prio(v, seed_t);
+        bool eligible = true, is_root;
+        if (m.rdiv) is_root = root_cand(v, seed_t, m.rdiv);
+        else is_root = *maxprio == ((((unsigned long long)pv) << 1) | 1ull);
+        const Nb nb = load_nb(m, v);
+        for (uint32_t i = 0; i < nb.deg; ++i) {
+            uint32_t w = nb_at(m, nb, i);
+            if (m.labels[w] == 0) continue;
+            if (!local_pair(m, v, w)) { if (prio(w, seed_t) > pv) eligible = false; continue; }
+            if (m.rdiv && is_root && root_cand(w, seed_t, m.rdiv) && prio(w, seed_t) > pv) is_root = false;
+        }
+        m.level[v] = !eligible ? LVL_DEAD : (is_root ? 0u : LVL_NONE);
+    }
+    grid.sync();
+    // Growth rounds on a FRONTIER instead of full scans.  Only an undecided node with >= 1 forest
+    // neighbour can change state in a round, and such a node is either newly adjacent to a node that
+    // joined in the previous round (pushed by that node) or a candidate that lost and re-queues
+    // itself.  The evaluated set equals the set a full scan would act on, so levels are identical to
+    // oracle/mrf.c; list order is irrelevant.  qstamp de-duplicates pushes (unique per iteration+round).
+    const uint32_t stamp_base = m.iter * 2048u;
+    auto push = [&](uint32_t w, uint32_t round) {
+        if (atomicExch(m.qstamp + w, stamp_base + round) == stamp_base + round) return;
+        cg::coalesced_group g = cg::coalesced_threads();
+        uint32_t base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(&m.ctl[CTL_QN + round], g.size());
+        base = g.shfl(base, 0);
+        m.queue[(size_t)(round & 1u) * m.F + base + g.thread_rank()] = w;
+    };
+    for (uint32_t v = m.nb + tid; v < m.ne; v += nth) {  // seed: undecided neighbours of the roots
+        if (__ldcg(m.level + v) != 0u) continue;
+        const Nb nb = load_nb(m, v);
+        for (uint32_t i = 0; i < nb.deg; ++i) {
+            uint32_t w = nb_at(m, nb, i);
+            if (local_pair(m, v, w) && __ldcg(m.level + w) == LVL_NONE) push(w, 1u);
+        }
+    }
+    grid.sync();
+    for (uint32_t r = 1; r <= m.rounds; ++r) {
+        const uint32_t n = __ldcg(m.ctl + CTL_QN + r);
+        const uint32_t *q = m.queue + (size_t)(r & 1u) * m.F;
+        for (uint32_t qi = tid; qi < n; qi += nth) {
+            const uint32_t v = __ldcg(q + qi);
+            if (__ldcg(m.level + v) != LVL_NONE) continue;
+            const Nb nb = load_nb(m, v);
+            uint32_t c = 0;
+            for (uint32_t i = 0; i < nb.deg; ++i) {
+                uint32_t w = nb_at(m, nb, i);
+                if (local_pair(m, v, w) && __ldcg(m.level + w) < r) ++c;
+            }
+            if (c >= 2) { m.level[v] = LVL_DEAD; continue; }
+            if (c != 1) continue;
+            const uint32_t pv = prio(v, seed_t);
+            bool win = true;
+            for (uint32_t i = 0; i < nb.deg && win; ++i) {
+                uint32_t w = nb_at(m, nb, i);
+                if (!local_pair(m, v, w)) continue;
+                uint32_t lw = __ldcg(m.level + w);
+                if (!(lw == LVL_NONE || lw == r)) continue;
+                if (prio(w, seed_t) < pv) continue;
+                if (count_in_forest(m, w, r) == 1) win = false;  // a stronger adjacent candidate: wait
+            }
+            if (win) {
+                m.level[v] = r;
+                if (r < m.rounds)
+                    for (uint32_t i = 0; i < nb.deg; ++i) {
+                        uint32_t w = nb_at(m, nb, i);
+                        if (local_pair(m, v, w) && __ldcg(m.level + w) == LVL_NONE) push(w, r + 1u);
+                    }
+            } else if (r < m.rounds) {
+                push(v, r + 1u);
+            }
+        }
+        grid.sync();
+    }
+    if (!do_bucket) return;
+
+    // ---- bucket the forest nodes by level: deepest level first, levels padded to 32 entries ----
+    uint32_t *cnt = sm, *base = sm + (m.rounds + 1);
+    for (uint32_t i = threadIdx.x; i <= m.rounds; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    for (uint32_t v = m.nb + tid; v < m.ne; v += nth) {
+        uint32_t l = m.level[v];
+        if (l <= m.rounds) atomicAdd(&cnt[l], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i <= m.rounds; i += blockDim.x)
+        if (cnt[i]) atomicAdd(&m.ctl[CTL_CNT + i], cnt[i]);
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t acc = 0, uacc = 0;
+        for (int l = (int)m.rounds; l >= 0; --l) {
+            m.ctl[CTL_OFF + l] = acc;     // padded start of level l (deepest level first)
+            m.ctl[CTL_CUR + l] = uacc;    // unpadded start of level l in the sorted list
+            acc += (m.ctl[CTL_CNT + l] + 31u) & ~31u;
+            uacc += m.ctl[CTL_CNT + l];
+        }
+        m.ctl[CTL_TOTAL] = acc;
+        m.ctl[CTL_UTOTAL] = uacc;
+    }
+    // sort keys: a stable radix sort by (rounds - level) keeps node ids ascending inside a level, so
+    // that consecutive order entries touch neighbouring rows of every per-node array (the sweeps are
+    // bound by scattered DRAM sectors, not by arithmetic)
+    (void)base;
+    for (uint32_t v = m.nb + tid; v < m.ne; v += nth) {
+        uint32_t l = m.level[v];
+        m.sort_key_in[v - m.nb] = l <= m.rounds ? m.rounds - l : m.rounds + 1u;
+        m.sort_val_in[v - m.nb] = v;
+    }
+}
+
+// sorted (level-major, node-ascending) list -> order array with every level padded to 32 entries
+__global__ void __launch_bounds__(256) k_scatter_order(Mrf m)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.ctl[CTL_UTOTAL]) return;
+    const uint32_t l = m.rounds - m.sort_key_out[i];
+    m.order[m.ctl[CTL_OFF + l] + (i - m.ctl[CTL_CUR + l])] = m.sort_val_out[i];
+}
+
+// ---- bottom-up min-sum messages, dataflow over the forest -------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256) k_up(Mrf m)
+{
+    constexpr uint32_t GPW = 32 / G;  // nodes per warp
     const uint32_t lane = threadIdx.x & (G - 1);
-    const uint32_t gpb = blockDim.x / G;
-    for (uint32_t base = beg + blockIdx.x * gpb; base < end; base += gridDim.x * gpb) {
-        uint32_t oi = base + threadIdx.x / G;
-        bool act = oi < end;
-        uint32_t v = act ? m.order[oi] : 0;
-        uint64_t p0 = act ? m.ptr[v] : 0, p1 = act ? m.ptr[v + 1] : 0;
-        uint32_t a0 = act ? m.adj_ptr[v] : 0, a1 = act ? m.adj_ptr[v + 1] : 0;
+    const uint32_t sub = (threadIdx.x & 31) / G;
+    const uint32_t total = m.ctl[CTL_TOTAL];
+    const uint32_t stamp = m.iter;
+    // Static round-robin over warps, chunks in bucket order (deepest level first).  A chunk only
+    // depends on EARLIER chunks and every warp walks its chunks in increasing order, so the earliest
+    // unfinished chunk can always run: no deadlock as long as all warps are resident (cooperative
+    // launch), and no claim atomics on the critical path.
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);; chunk += nwarps) {
+        const uint32_t oi = chunk * GPW + sub;
+        if ((uint64_t)chunk * GPW >= total) return;
+        const uint32_t v = oi < total ? m.order[oi] : NO_NODE;
+        const bool act = v != NO_NODE;
+        uint64_t p0 = 0, p1 = 0;
+        uint32_t lv = 0;
+        Nb nb; nb.deg = 0; nb.x = nb.y = nb.z = nb.base = 0;
+        if (act) { p0 = m.ptr[v]; p1 = m.ptr[v + 1]; lv = m.level[v]; nb = load_nb(m, v); }
         float bh = INFINITY;
         uint32_t bk = 0xFFFFFFFFu;
-        for (uint64_t k = p0 + lane; k < p1; k += G) {
-            const uint32_t lab = (uint32_t)m.view[k] + 1u;
-            float h = m.cost[k];
-            for (uint32_t a = a0; a < a1; ++a) {
-                const uint32_t w = m.adj_idx[a];
-                const uint32_t xw = m.labels[w];
-                if (xw == 0) continue;  // unseen faces carry no edges (view_selection.cpp:30,35)
-                const uint32_t lw = (owned(m, w) && same_part(m, v, w)) ? m.level[w] : LVL_DEAD;
-                if (lw <= m.rounds) {
-                    if (lw > r) {  // child: Potts message min(h_w(lab), hmin_w + 1)
-                        float msg = m.hminp1[w];
-                        long long j = find_label(m, w, lab);
-                        if (j >= 0) { float hw = m.H[j]; if (hw < msg) msg = hw; }
+        if (nb.deg <= 3) {
+            // issue the loads of the first two label chunks now: they overlap the neighbour
+            // classification and the flag waits below
+            const uint64_t k0 = p0 + lane, k1 = k0 + G;
+            uint32_t lab0 = 0, lab1 = 0;
+            float c0 = 0.0f, c1 = 0.0f;
+            if (k0 < p1) { lab0 = (uint32_t)m.view[k0] + 1u; c0 = m.cost[k0]; }
+            if (k1 < p1) { lab1 = (uint32_t)m.view[k1] + 1u; c1 = m.cost[k1]; }
+            // classify the (at most three) neighbours once: 0 = skip (unseen / parent), 1 = child, 2 = fixed
+            uint32_t kind[3] = {0, 0, 0}, xw[3] = {0, 0, 0}, wv[3] = {0, 0, 0};
+            float hm[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if ((uint32_t)i >= nb.deg) continue;
+                const uint32_t w = i == 0 ? nb.x : (i == 1 ? nb.y : nb.z);
+                const uint32_t x = m.labels[w];
+                wv[i] = w; xw[i] = x;
+                if (x == 0) continue;  // unseen faces carry no edges (view_selection.cpp:30,35)
+                const uint32_t lw = local_pair(m, v, w) ? m.level[w] : LVL_DEAD;
+                if (lw <= m.rounds) { if (lw > lv) kind[i] = 1; }
+                else kind[i] = 2;
+            }
+            bool any_child = false;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (kind[i] == 1) {  // wait for the child's messages
+                    while (ld_relaxed(m.flag_up + wv[i]) != stamp) __nanosleep(20);
+                    any_child = true;
+                }
+            if (any_child) fence_acq_rel();  // one acquire fence for all children of this node
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (kind[i] == 1) hm[i] = __ldcg(m.hminp1 + wv[i]);
+            auto eval = [&](uint32_t lab, float h) -> float {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    if (kind[i] == 1) {  // Potts message min(h_w(lab), hmin_w + 1)
+                        float msg = hm[i];
+                        long long j = find_label(m, wv[i], lab);
+                        if (j >= 0) { float hw = __ldcg(m.H + j); if (hw < msg) msg = hw; }
                         h = h + msg;
-                    }              // parent: skipped
-                } else {
-                    h = h + (lab != xw ? 1.0f : 0.0f);
+                    } else if (kind[i] == 2) {
+                        h = h + (lab != xw[i] ? 1.0f : 0.0f);
+                    }
+                }
+                return h;
+            };
+            if (k0 < p1) {
+                const float h0 = eval(lab0, c0);
+                float h1 = 0.0f;
+                if (k1 < p1) h1 = eval(lab1, c1);
+                m.H[k0] = h0;
+                if (h0 < bh) { bh = h0; bk = (uint32_t)(k0 - p0); }
+                if (k1 < p1) {
+                    m.H[k1] = h1;
+                    if (h1 < bh) { bh = h1; bk = (uint32_t)(k1 - p0); }
                 }
             }
-            m.H[k] = h;
-            if (h < bh) { bh = h; bk = (uint32_t)(k - p0); }
+            for (uint64_t k = k1 + G; k < p1; k += G) {
+                const float h = eval((uint32_t)m.view[k] + 1u, m.cost[k]);
+                m.H[k] = h;
+                if (h < bh) { bh = h; bk = (uint32_t)(k - p0); }
+            }
+        } else {
+            // generic degree (non-manifold edges): neighbour loop inside the label loop
+            for (uint32_t i = 0; i < nb.deg; ++i) {
+                const uint32_t w = nb_at(m, nb, i);
+                if (m.labels[w] == 0 || !local_pair(m, v, w)) continue;
+                const uint32_t lw = m.level[w];
+                if (lw <= m.rounds && lw > lv)
+                    while (ld_acquire(m.flag_up + w) != stamp) __nanosleep(32);
+            }
+            for (uint64_t k = p0 + lane; k < p1; k += G) {
+                const uint32_t lab = (uint32_t)m.view[k] + 1u;
+                float h = m.cost[k];
+                for (uint32_t i = 0; i < nb.deg; ++i) {
+                    const uint32_t w = nb_at(m, nb, i);
+                    const uint32_t x = m.labels[w];
+                    if (x == 0) continue;
+                    const uint32_t lw = local_pair(m, v, w) ? m.level[w] : LVL_DEAD;
+                    if (lw <= m.rounds) {
+                        if (lw > lv) {
+                            float msg = __ldcg(m.hminp1 + w);
+                            long long j = find_label(m, w, lab);
+                            if (j >= 0) { float hw = __ldcg(m.H + j); if (hw < msg) msg = hw; }
+                            h = h + msg;
+                        }
+                    } else {
+                        h = h + (lab != x ? 1.0f : 0.0f);
+                    }
+                }
+                m.H[k] = h;
+                if (h < bh) { bh = h; bk = (uint32_t)(k - p0); }
+            }
         }
-        __syncwarp();
+        __syncwarp();  // orders the H stores of all lanes before lane 0's fence + release below
         for (int s = G / 2; s; s >>= 1) {
             float oh = __shfl_xor_sync(0xffffffffu, bh, s);
             uint32_t ok = __shfl_xor_sync(0xffffffffu, bk, s);
             if (oh < bh || (oh == bh && ok < bk)) { bh = oh; bk = ok; }
         }
-        if (act && lane == 0) { m.hminp1[v] = bh + 1.0f; m.amin[v] = bk; }
+        if (act && lane == 0) {
+            m.hminp1[v] = bh + 1.0f;
+            m.amin[v] = bk;
+            fence_acq_rel();  // cumulative: covers the H stores of the other lanes (ordered by __syncwarp)
+            st_relaxed(m.flag_up + v, stamp);
+        }
     }
 }
 
-// top-down assignment for forest level r
-__global__ void __launch_bounds__(256) k_down(Mrf m, uint32_t r)
+// ---- top-down assignment, dataflow: one thread per node waits for its parent ---------------------------
+__global__ void __launch_bounds__(256) k_down(Mrf m)
 {
-    const uint32_t beg = m.lvl_ptr[r], end = m.lvl_ptr[r + 1];
-    for (uint32_t oi = beg + blockIdx.x * blockDim.x + threadIdx.x; oi < end; oi += gridDim.x * blockDim.x) {
-        uint32_t v = m.order[oi];
+    const uint32_t total = m.ctl[CTL_TOTAL];
+    const uint32_t stamp = m.iter;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);; chunk += nwarps) {
+        if ((uint64_t)chunk * 32u >= total) return;
+        // shallowest level first: walk the order array backwards (a warp never straddles two levels)
+        const uint32_t oi = total - 1u - (chunk * 32u + (threadIdx.x & 31));
+        const uint32_t v = m.order[oi];
+        if (v == NO_NODE) continue;
+        const uint32_t lv = m.level[v];
         uint32_t best = (uint32_t)m.view[m.ptr[v] + m.amin[v]] + 1u;
-        if (r > 0) {
-            for (uint32_t a = m.adj_ptr[v]; a < m.adj_ptr[v + 1]; ++a) {
-                uint32_t w = m.adj_idx[a];
-                if (owned(m, w) && same_part(m, v, w) && m.level[w] < r) {
-                    uint32_t xp = m.labels[w];
+        if (lv > 0) {
+            const Nb nb = load_nb(m, v);
+            for (uint32_t i = 0; i < nb.deg; ++i) {
+                const uint32_t w = nb_at(m, nb, i);
+                if (local_pair(m, v, w) && m.level[w] < lv) {
+                    while (ld_acquire(m.flag_dn + w) != stamp) __nanosleep(32);
+                    const uint32_t xp = __ldcg(m.labels + w);
                     long long j = find_label(m, v, xp);
                     if (j >= 0 && m.H[j] <= m.hminp1[v]) best = xp;
                     break;
@@ -280,11 +536,11 @@ __global__ void __launch_bounds__(256) k_down(Mrf m, uint32_t r)
             }
         }
         m.labels[v] = best;
+        st_release(m.flag_dn + v, stamp);
     }
 }
 
-// 32.32 fixed-point energy of the owned nodes: unaries + edges (i<j, counted by the lower id if both
-// owned, else by the owner of the lower... every edge is counted by its lower endpoint's owner)
+// 32.32 fixed-point energy of the owned nodes: unaries + edges counted by their lower endpoint
 __global__ void __launch_bounds__(256) k_energy(Mrf m)
 {
     unsigned long long e = 0;
@@ -293,8 +549,9 @@ __global__ void __launch_bounds__(256) k_energy(Mrf m)
         if (x == 0) { e += 1ull << 32; continue; }
         long long j = find_label(m, v, x);
         if (j >= 0) e += (unsigned long long)(long long)((double)m.cost[j] * 4294967296.0);
-        for (uint32_t a = m.adj_ptr[v]; a < m.adj_ptr[v + 1]; ++a) {
-            uint32_t w = m.adj_idx[a];
+        const Nb nb = load_nb(m, v);
+        for (uint32_t i = 0; i < nb.deg; ++i) {
+            uint32_t w = nb_at(m, nb, i);
             uint32_t xw = m.labels[w];
             if (w > v && xw != 0 && xw != x) e += 1ull << 32;
         }
@@ -303,16 +560,22 @@ __global__ void __launch_bounds__(256) k_energy(Mrf m)
     if ((threadIdx.x & 31) == 0 && e) atomicAdd(m.energy, e);
 }
 
-Mrf make_mrf(b2tex_ctx *c)
+Mrf make_mrf(b2tex_ctx *c, uint32_t iter)
 {
     Mrf m;
     m.F = c->F; m.nb = c->face_begin; m.ne = c->face_end;
     m.adj_ptr = c->adj_ptr.p; m.adj_idx = c->adj_idx.p;
+    m.adj4 = c->mrf_adj4.p;
     m.ptr = c->dc_ptr.p; m.view = c->dc_view.p; m.cost = c->dc_cost.p;
     m.H = c->mrf_H.p; m.hminp1 = c->mrf_hminp1.p; m.amin = c->mrf_amin.p; m.level = c->mrf_level.p;
-    m.labels = c->labels.p; m.order = c->mrf_order.p; m.lvl_ptr = c->mrf_lvlptr.p; m.cursor = c->mrf_cursor.p;
-    m.iter = c->mrf_cursor.p + MAX_LEVELS + 8;
-    m.max_prio = c->mrf_cursor.p + MAX_LEVELS + 16;
+    m.labels = c->labels.p; m.order = c->mrf_order.p; m.ctl = c->mrf_cursor.p;
+    m.flag_up = c->mrf_lvlptr.p; m.flag_dn = c->mrf_lvlptr.p + c->F;
+    m.queue = c->mrf_queue.p; m.qstamp = c->mrf_queue.p + 2 * (size_t)c->F;
+    m.sort_key_in = c->mrf_sort.p; m.sort_key_out = c->mrf_sort.p + c->F;
+    m.sort_val_in = c->mrf_sort.p + 2 * (size_t)c->F; m.sort_val_out = c->mrf_sort.p + 3 * (size_t)c->F;
+    m.mask = c->mrf_mask_words ? c->mrf_mask.p : nullptr;
+    m.mpre = c->mrf_mask_words ? c->mrf_mpre.p : nullptr;
+    m.mask_words = c->mrf_mask_words;
     m.energy = c->mrf_energy.p;
     const b2tex_mrf_params &p = c->mrf_params;
     uint32_t P = p.num_parts ? p.num_parts : 1;
@@ -321,58 +584,97 @@ Mrf make_mrf(b2tex_ctx *c)
     if (p.root_div == 0) m.rdiv = 0;
     else { uint32_t cap = c->F / 8u; if (cap < 1u) cap = 1u; m.rdiv = p.root_div < cap ? p.root_div : cap; }
     m.seed = p.seed;
+    m.iter = iter;
     return m;
 }
 
-template <int G>
-void launch_up(const Mrf &m, uint32_t r, int grid, cudaStream_t s) { k_up<G><<<grid, 256, 0, s>>>(m, r); }
-
-int enqueue_forest(b2tex_ctx *c, const Mrf &m)
+template <typename K>
+int coop_grid(b2tex_ctx *c, K kernel, size_t smem, int *grid, int threads = 256)
 {
-    cudaStream_t s = c->stream;
-    const uint32_t n = m.ne - m.nb;
-    const uint32_t nblocks = (n + 255) / 256;
-    if (!n) return B2TEX_OK;
-    if (m.rdiv == 0) {
-        B2_CUDA(cudaMemsetAsync(m.max_prio, 0, 8, s));
-        k_max_prio<<<nblocks, 256, 0, s>>>(m);
-    }
-    k_forest_init<<<nblocks, 256, 0, s>>>(m);
-    for (uint32_t r = 1; r <= m.rounds; ++r) k_forest_round<<<nblocks, 256, 0, s>>>(m, r);
-    B2_KERNEL_CHECK();
+    int per_sm = 0;
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) { set_error("mrf kernel cannot be resident"); return B2TEX_ERR_CUDA; }
+    *grid = c->num_sms * per_sm;
     return B2TEX_OK;
 }
 
-int enqueue_iteration(b2tex_ctx *c, const Mrf &m)
+int launch_forest(b2tex_ctx *c, Mrf &m, int do_bucket)
 {
     cudaStream_t s = c->stream;
-    const uint32_t n = m.ne - m.nb;
-    if (!n) return B2TEX_OK;
-    B2_TRY(enqueue_forest(c, m));
-    const int grid = std::max(1, c->num_sms * 8);
-    B2_CUDA(cudaMemsetAsync(m.cursor, 0, (m.rounds + 2) * sizeof(uint32_t), s));
-    size_t sh = (m.rounds + 1) * sizeof(uint32_t);
-    k_bucket_count<<<grid, 256, sh, s>>>(m);
-    k_bucket_scan<<<1, 32, 0, s>>>(m);
-    k_bucket_fill<<<grid, 256, 2 * sh, s>>>(m);
-    for (int r = (int)m.rounds; r >= 0; --r) {
+    size_t sh = 2 * (size_t)(m.rounds + 1) * sizeof(uint32_t);
+    int grid = 0;
+    // few fat blocks: the cost of grid.sync() grows with the number of blocks
+    B2_TRY(coop_grid(c, k_forest, sh, &grid, 1024));
+    uint32_t n = m.ne - m.nb;
+    int need = (int)((n + 1023) / 1024);
+    if (grid > need) grid = need > 0 ? need : 1;
+    B2_CUDA(cudaMemsetAsync(m.ctl, 0, CTL_WORDS * sizeof(uint32_t), s));
+    if (do_bucket) B2_CUDA(cudaMemsetAsync(m.order, 0xFF, c->mrf_order.n * sizeof(uint32_t), s));
+    void *args[] = {&m, &do_bucket};
+    B2_CUDA(cudaLaunchCooperativeKernel((void *)k_forest, dim3(grid), dim3(1024), args, sh, s));
+    if (do_bucket) {
+        int bits = 1;
+        while ((1u << bits) < m.rounds + 2u) ++bits;
+        size_t bytes = 0;
+        B2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, m.sort_key_in, m.sort_key_out, m.sort_val_in,
+                                                m.sort_val_out, (int)n, 0, bits, s));
+        B2_TRY(c->cub_tmp.alloc(bytes));
+        B2_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, m.sort_key_in, m.sort_key_out, m.sort_val_in,
+                                                m.sort_val_out, (int)n, 0, bits, s));
+        k_scatter_order<<<(n + 255) / 256, 256, 0, s>>>(m);
+        B2_KERNEL_CHECK();
+    }
+    return B2TEX_OK;
+}
+
+template <int G>
+int launch_up(b2tex_ctx *c, Mrf &m)
+{
+    int grid = 0;
+    B2_TRY(coop_grid(c, k_up<G>, 0, &grid));
+    void *args[] = {&m};
+    // cooperative launch only to guarantee co-residency of the spinning warps (no grid.sync inside)
+    B2_CUDA(cudaLaunchCooperativeKernel((void *)k_up<G>, dim3(grid), dim3(256), args, 0, c->stream));
+    return B2TEX_OK;
+}
+
+int enqueue_iteration(b2tex_ctx *c, Mrf &m)
+{
+    cudaStream_t s = c->stream;
+    if (m.ne <= m.nb) return B2TEX_OK;
+    {
+        ScopedTimer tf(c, "  mrf.k_forest");
+        B2_TRY(launch_forest(c, m, 1));
+    }
+    ScopedTimer *tu = new ScopedTimer(c, "  mrf.k_up");
+    switch (c->mrf_group) {
+        case 4: B2_TRY(launch_up<4>(c, m)); break;
+        case 8: B2_TRY(launch_up<8>(c, m)); break;
+        case 16: B2_TRY(launch_up<16>(c, m)); break;
+        default: B2_TRY(launch_up<32>(c, m)); break;
+    }
+    delete tu;
+    static const bool repeat_up = getenv("B2TEX_MRF_REPEAT_UP") != nullptr;
+    if (repeat_up) {  // experiment: second sweep finds every flag already set (no dataflow waits)
+        ScopedTimer tu2(c, "  mrf.k_up(again)");
         switch (c->mrf_group) {
-            case 4: launch_up<4>(m, r, grid, s); break;
-            case 8: launch_up<8>(m, r, grid, s); break;
-            case 16: launch_up<16>(m, r, grid, s); break;
-            default: launch_up<32>(m, r, grid, s); break;
+            case 4: B2_TRY(launch_up<4>(c, m)); break;
+            case 8: B2_TRY(launch_up<8>(c, m)); break;
+            case 16: B2_TRY(launch_up<16>(c, m)); break;
+            default: B2_TRY(launch_up<32>(c, m)); break;
         }
     }
-    for (uint32_t r = 0; r <= m.rounds; ++r) k_down<<<grid, 256, 0, s>>>(m, r);
+    {
+        ScopedTimer td(c, "  mrf.k_down");
+        int grid = 0;
+        B2_TRY(coop_grid(c, k_down, 0, &grid));
+        void *args[] = {&m};
+        B2_CUDA(cudaLaunchCooperativeKernel((void *)k_down, dim3(grid), dim3(256), args, 0, s));
+    }
+    ScopedTimer te(c, "  mrf.k_energy");
     B2_CUDA(cudaMemsetAsync(m.energy, 0, sizeof(unsigned long long), s));
-    k_energy<<<grid, 256, 0, s>>>(m);
+    k_energy<<<std::max(1, c->num_sms * 8), 256, 0, s>>>(m);
     B2_KERNEL_CHECK();
-    return B2TEX_OK;
-}
-
-int set_iter(b2tex_ctx *c, const Mrf &m, uint32_t t)
-{
-    B2_CUDA(cudaMemcpyAsync((void *)m.iter, &t, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     return B2TEX_OK;
 }
 
@@ -387,15 +689,33 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
     B2_TRY(c->mrf_hminp1.alloc(F));
     B2_TRY(c->mrf_amin.alloc(F));
     B2_TRY(c->mrf_level.alloc(F));
-    B2_TRY(c->mrf_order.alloc(F));
-    B2_TRY(c->mrf_lvlptr.alloc(MAX_LEVELS + 8));
-    B2_TRY(c->mrf_cursor.alloc(MAX_LEVELS + 32));
+    B2_TRY(c->mrf_order.alloc(F + 32 * ((size_t)p->rounds + 2)));
+    B2_TRY(c->mrf_sort.alloc(4 * F));    // sort keys/values in/out
+    B2_TRY(c->mrf_queue.alloc(3 * F));   // frontier lists [2][F] | qstamp [F]
+    B2_TRY(c->mrf_queue.zero(c->stream));
+    B2_TRY(c->mrf_lvlptr.alloc(2 * F));  // flag_up | flag_dn
+    B2_TRY(c->mrf_lvlptr.zero(c->stream));
+    B2_TRY(c->mrf_cursor.alloc(CTL_WORDS));
     B2_TRY(c->mrf_energy.alloc(4));
+    B2_TRY(c->mrf_adj4.alloc(F));
+    if (F) k_build_adj4<<<(unsigned)((F + 255) / 256), 256, 0, c->stream>>>((uint32_t)F, c->adj_ptr.p, c->adj_idx.p, c->mrf_adj4.p);
     if (!c->have_labels || c->labels.n != F) { B2_TRY(c->labels.alloc(F)); B2_TRY(c->labels.zero(c->stream)); }
     uint32_t nodes = c->face_end - c->face_begin;
     double rho = nodes ? (double)c->nnz / nodes : 0.0;
-    c->mrf_group = rho >= 24 ? 32 : rho >= 12 ? 16 : rho >= 6 ? 8 : 4;
-    if (c->mrf_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)c->mrf_graph_exec); c->mrf_graph_exec = nullptr; }
+    // lanes per node: fewer lanes = more nodes in flight per SM (the sweep is latency bound)
+    c->mrf_group = rho >= 56 ? 32 : rho >= 12 ? 16 : rho >= 6 ? 8 : 4;
+    if (const char *g = getenv("B2TEX_MRF_GROUP")) {
+        int v = atoi(g);
+        if (v == 4 || v == 8 || v == 16 || v == 32) c->mrf_group = v;
+    }
+    // label bitmasks: labels are view+1 <= K
+    uint32_t words = (c->K + 1 + 31) / 32;
+    static const bool no_masks = getenv("B2TEX_NO_MASKS") != nullptr;
+    c->mrf_mask_words = (c->K == 0 || words > (uint32_t)MAX_MASK_WORDS || no_masks) ? 0 : words;
+    if (c->mrf_mask_words) {
+        B2_TRY(c->mrf_mask.alloc(F * c->mrf_mask_words));
+        B2_TRY(c->mrf_mpre.alloc(F * c->mrf_mask_words));
+    }
     return B2TEX_OK;
 }
 
@@ -413,16 +733,19 @@ int read_energy(b2tex_ctx *c, const Mrf &m, int64_t *efix)
 int mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *efix)
 {
     B2_TRY(alloc_mrf(c, p));
-    Mrf m = make_mrf(c);
+    Mrf m = make_mrf(c, 0);
     cudaStream_t s = c->stream;
     const int grid = std::max(1, c->num_sms * 8);
     if (m.ne > m.nb) {
+        ScopedTimer tm(c, "mrf_init");
         switch (c->mrf_group) {
             case 4: k_init_labels<4><<<grid, 256, 0, s>>>(m); break;
             case 8: k_init_labels<8><<<grid, 256, 0, s>>>(m); break;
             case 16: k_init_labels<16><<<grid, 256, 0, s>>>(m); break;
             default: k_init_labels<32><<<grid, 256, 0, s>>>(m); break;
         }
+        if (c->mrf_mask_words)
+            k_build_masks<<<(m.ne - m.nb + 255) / 256, 256, 0, s>>>(m, c->mrf_mask.p, c->mrf_mpre.p);
         B2_KERNEL_CHECK();
     }
     c->have_labels = true;
@@ -436,27 +759,11 @@ int mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *efix)
 int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *efix)
 {
     if (!c->mrf_ready) { set_error("mrf_iterate before mrf_init"); return B2TEX_ERR_ARG; }
-    Mrf m = make_mrf(c);
-    cudaStream_t s = c->stream;
-    B2_TRY(set_iter(c, m, t));
-    ScopedTimer tm(c, "mrf_iteration", 14.0 * (double)c->nnz + 20.0 * (double)(c->face_end - c->face_begin));
-    static const bool no_graph = getenv("B2TEX_NO_GRAPH") != nullptr;
-    if (no_graph) {
+    if (t == 0) { set_error("mrf_iterate: iterations are numbered from 1"); return B2TEX_ERR_ARG; }
+    Mrf m = make_mrf(c, t);
+    {
+        ScopedTimer tm(c, "mrf_iteration", 14.0 * (double)c->nnz + 20.0 * (double)(c->face_end - c->face_begin));
         B2_TRY(enqueue_iteration(c, m));
-    } else {
-        if (!c->mrf_graph_exec) {
-            cudaGraph_t graph;
-            B2_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            int rc = enqueue_iteration(c, m);
-            cudaError_t e = cudaStreamEndCapture(s, &graph);
-            if (rc != B2TEX_OK) return rc;
-            B2_CUDA(e);
-            cudaGraphExec_t exec;
-            B2_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-            cudaGraphDestroy(graph);
-            c->mrf_graph_exec = exec;
-        }
-        B2_CUDA(cudaGraphLaunch((cudaGraphExec_t)c->mrf_graph_exec, s));
     }
     return read_energy(c, m, efix);
 }
@@ -465,9 +772,9 @@ int mrf_sample_only(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t, uint32_
 {
     if (!c->mrf_ready) { int64_t e; B2_TRY(mrf_init(c, p, &e)); }
     c->mrf_params = *p;
-    Mrf m = make_mrf(c);
-    B2_TRY(set_iter(c, m, t));
-    B2_TRY(enqueue_forest(c, m));
+    Mrf m = make_mrf(c, t);
+    B2_TRY(c->mrf_queue.zero(c->stream));  // the same (iteration, round) stamps may be replayed
+    if (m.ne > m.nb) B2_TRY(launch_forest(c, m, 0));
     B2_TRY(c->mrf_level.download(level_host, c->F, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     return B2TEX_OK;

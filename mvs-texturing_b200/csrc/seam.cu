@@ -410,7 +410,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
     B2_TRY(prepare_images(c, c->prepared_data_term >= 0 ? c->prepared_data_term : 1));
     const uint32_t Vn = c->Vn;
     ScopedTimer *tm_asm = new ScopedTimer(c, "seam_assembly");
-    DevBuf<uint32_t> cnt, row_vertex;
+    DevBuf<uint32_t> &cnt = c->s_cnt32, &row_vertex = c->s_row_vertex;
     B2_TRY(cnt.alloc((size_t)Vn + 1));
     B2_TRY(cnt.zero(s));
     B2_TRY(c->row_ptr.alloc((size_t)Vn + 1));
@@ -444,7 +444,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
     k_arows<true><<<vb, 128, 0, s>>>(Vn, m, nullptr, c->arow_ptr.p, c->arow_rows.p, c->arow_b.p);
     B2_KERNEL_CHECK();
 
-    DevBuf<uint32_t> rcnt;
+    DevBuf<uint32_t> &rcnt = c->s_rcnt;
     B2_TRY(rcnt.alloc((size_t)R + 1));
     B2_TRY(rcnt.zero(s));
     B2_TRY(c->csr_ptr.alloc((size_t)R + 1));

@@ -33,6 +33,8 @@
 #include <omp.h>
 #endif
 
+/* fork-join per forest level is latency bound: more than 16 threads only add wake-up cost */
+static int g_mrf_threads = 1;
 #define LVL_NONE 0xFFFFFFFFu
 #define LVL_DEAD 0xFFFFFFFEu
 
@@ -114,7 +116,7 @@ static void sample_forest(const mrf_t *m, const orc_mrf_params *pr, uint32_t t, 
         for (uint32_t v = 0; v < F; ++v)
             if (seen(m, v) && (!have_best || prio(v, seed_t) > best_prio)) { best_prio = prio(v, seed_t); have_best = 1; }
     /* round 0: eligibility + roots */
-    #pragma omp parallel for schedule(static)
+    #pragma omp parallel for schedule(static) num_threads(g_mrf_threads) if (F > 8192)
     for (int64_t vv = 0; vv < (int64_t)F; ++vv) {
         uint32_t v = (uint32_t)vv;
         level[v] = LVL_NONE;
@@ -135,7 +137,7 @@ static void sample_forest(const mrf_t *m, const orc_mrf_params *pr, uint32_t t, 
     uint32_t maxl = 0;
     for (uint32_t r = 1; r <= pr->rounds; ++r) {
         int joined = 0;
-        #pragma omp parallel for schedule(static) reduction(|:joined)
+        #pragma omp parallel for schedule(static) reduction(|:joined) num_threads(g_mrf_threads) if (F > 8192)
         for (int64_t vv = 0; vv < (int64_t)F; ++vv) {
             uint32_t v = (uint32_t)vv;
             if (level[v] != LVL_NONE) continue;
@@ -200,7 +202,8 @@ int orc_view_selection(uint32_t F, const uint32_t *adj_ptr, const uint32_t *adj_
                        double *trace, orc_mrf_info *info)
 {
 #ifdef _OPENMP
-    if (num_threads > 0) omp_set_num_threads(num_threads);
+    g_mrf_threads = num_threads > 0 ? num_threads : omp_get_max_threads();
+    if (g_mrf_threads > 16) g_mrf_threads = 16;
 #else
     (void)num_threads;
 #endif
@@ -244,7 +247,7 @@ int orc_view_selection(uint32_t F, const uint32_t *adj_ptr, const uint32_t *adj_
         }
         /* bottom-up min-sum messages */
         for (int64_t r = (int64_t)pr->rounds; r >= 0; --r) {
-            #pragma omp parallel for schedule(dynamic, 256)
+            #pragma omp parallel for schedule(dynamic, 256) num_threads(g_mrf_threads) if (lvl_ptr[r + 1] - lvl_ptr[r] > 2048)
             for (int64_t oi = lvl_ptr[r]; oi < (int64_t)lvl_ptr[r + 1]; ++oi) {
                 uint32_t v = order[oi];
                 float hmin = INFINITY;
@@ -276,7 +279,7 @@ int orc_view_selection(uint32_t F, const uint32_t *adj_ptr, const uint32_t *adj_
         }
         /* top-down assignment */
         for (uint32_t r = 0; r <= pr->rounds; ++r) {
-            #pragma omp parallel for schedule(static)
+            #pragma omp parallel for schedule(static) num_threads(g_mrf_threads) if (lvl_ptr[r + 1] - lvl_ptr[r] > 8192)
             for (int64_t oi = lvl_ptr[r]; oi < (int64_t)lvl_ptr[r + 1]; ++oi) {
                 uint32_t v = order[oi];
                 uint32_t best = (uint32_t)view[ptr[v] + amin[v]] + 1u;

@@ -14,7 +14,7 @@ int main(int argc, char **argv)
     bool link_only = argc > 1 && !std::strcmp(argv[1], "--link-only");
     mve::TriangleMesh::Ptr mesh = mve::TriangleMesh::create();
     float V[4][3] = {{1, 1, 1}, {-1, -1, 1}, {-1, 1, -1}, {1, -1, -1}};
-    unsigned int Fc[4][3] = {{0, 1, 2}, {0, 3, 1}, {0, 2, 3}, {1, 3, 2}};
+    unsigned int Fc[4][3] = {{0, 2, 1}, {0, 1, 3}, {0, 3, 2}, {1, 2, 3}};  // outward normals
     for (auto &v : V) { math::Vec3f p; p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; mesh->get_vertices().push_back(p); }
     for (auto &f : Fc) for (unsigned int k : f) mesh->get_faces().push_back(k);
     mesh->ensure_face_normals();
