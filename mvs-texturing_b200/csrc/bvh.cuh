@@ -33,17 +33,22 @@ __device__ __forceinline__ bool tri_occludes(const float *__restrict__ t9, float
     return t >= tmin && t <= tmax;
 }
 
-__device__ __forceinline__ bool box_hit(const float *lo, const float *hi, float ox, float oy, float oz,
-                                        float ix, float iy, float iz, float t0, float t1)
+// Slab test.  Box culling only has to be conservative, not bit-reproducible, so it uses explicit
+// FMAs ((lo - o) * inv == lo * inv - o * inv up to rounding; boxes are padded and the interval is
+// widened by the caller) and min/max that drop NaNs (0 * inf when the origin lies on a slab plane of
+// an axis-parallel ray): fminf/fmaxf return the non-NaN operand.
+__device__ __forceinline__ bool box_hit(const float *lo, const float *hi, float nox, float noy, float noz,
+                                        float ix, float iy, float iz, float t0, float t1, float sx, float sy,
+                                        float sz)
 {
-    float a, c;
-    a = (lo[0] - ox) * ix; c = (hi[0] - ox) * ix;
-    if (a == a && c == c) { t0 = fmaxf(t0, fminf(a, c)); t1 = fminf(t1, fmaxf(a, c)); }
-    a = (lo[1] - oy) * iy; c = (hi[1] - oy) * iy;
-    if (a == a && c == c) { t0 = fmaxf(t0, fminf(a, c)); t1 = fminf(t1, fmaxf(a, c)); }
-    a = (lo[2] - oz) * iz; c = (hi[2] - oz) * iz;
-    if (a == a && c == c) { t0 = fmaxf(t0, fminf(a, c)); t1 = fminf(t1, fmaxf(a, c)); }
-    return t0 <= t1 * 1.00001f + 1e-30f;
+    const float ax = __fmaf_rn(lo[0], ix, nox), cx = __fmaf_rn(hi[0], ix, nox);
+    const float ay = __fmaf_rn(lo[1], iy, noy), cy = __fmaf_rn(hi[1], iy, noy);
+    const float az = __fmaf_rn(lo[2], iz, noz), cz = __fmaf_rn(hi[2], iz, noz);
+    // per-axis slack s* covers the rounding of -o*inv: an axis the ray is (almost) parallel to gets a
+    // huge slack, i.e. stops culling on that axis only; the other two axes keep culling
+    t0 = fmaxf(t0, fmaxf(fmaxf(fminf(ax, cx) - sx, fminf(ay, cy) - sy), fminf(az, cz) - sz));
+    t1 = fminf(t1, fminf(fminf(fmaxf(ax, cx) + sx, fmaxf(ay, cy) + sy), fmaxf(az, cz) + sz));
+    return t0 <= t1 * 1.0001f + 1e-30f;
 }
 
 // nodes: N-1 internal nodes (root = 0); tri: 9 floats per Morton-ordered triangle.
@@ -56,6 +61,11 @@ __device__ __forceinline__ bool bvh_occluded(const BvhNode *__restrict__ nodes,
     if (num_tris == 1) return tri_occludes(tri, ox, oy, oz, dx, dy, dz, tmin, tmax);
     const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
     const float bt0 = tmin * 0.999f, bt1 = tmax * 1.001f;
+    const float nox = -ox * ix, noy = -oy * iy, noz = -oz * iz;
+    float sx = 1e-6f * fabsf(nox), sy = 1e-6f * fabsf(noy), sz = 1e-6f * fabsf(noz);
+    if (!(sx == sx)) sx = INFINITY;  // NaN (0 * inf): no culling on that axis
+    if (!(sy == sy)) sy = INFINITY;
+    if (!(sz == sz)) sz = INFINITY;
     int stack[100];
     int sp = 0;
     int node = 0;
@@ -65,8 +75,8 @@ __device__ __forceinline__ bool bvh_occluded(const BvhNode *__restrict__ nodes,
         const float lo0[3] = {q0.x, q0.y, q0.z}, hi0[3] = {q0.w, q1.x, q1.y};
         const float lo1[3] = {q1.z, q1.w, q2.x}, hi1[3] = {q2.y, q2.z, q2.w};
         const int left = __float_as_int(q3.x), right = __float_as_int(q3.y);
-        const bool h0 = box_hit(lo0, hi0, ox, oy, oz, ix, iy, iz, bt0, bt1);
-        const bool h1 = box_hit(lo1, hi1, ox, oy, oz, ix, iy, iz, bt0, bt1);
+        const bool h0 = box_hit(lo0, hi0, nox, noy, noz, ix, iy, iz, bt0, bt1, sx, sy, sz);
+        const bool h1 = box_hit(lo1, hi1, nox, noy, noz, ix, iy, iz, bt0, bt1, sx, sy, sz);
         int next = -1;
         if (h0) {
             if (left < 0) {

@@ -229,7 +229,7 @@ __device__ __forceinline__ uint32_t count_in_forest(const Mrf &m, uint32_t v, ui
     return c;
 }
 
-__global__ void __launch_bounds__(1024, 2) k_forest(Mrf m, int do_bucket)
+__global__ void __launch_bounds__(1024, 1) k_forest(Mrf m, int do_bucket)
 {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ uint32_t sm[];  // [rounds+1] counts, [rounds+1] bases
@@ -398,17 +398,24 @@ __global__ void __launch_bounds__(256) k_up(Mrf m)
         if (act) { p0 = m.ptr[v]; p1 = m.ptr[v + 1]; lv = m.level[v]; nb = load_nb(m, v); }
         float bh = INFINITY;
         uint32_t bk = 0xFFFFFFFFu;
-        if (nb.deg <= 3) {
+        if (nb.deg <= 3 && m.mask) {
+            // ---- fast path: manifold degree, label bitmasks; 32-bit offsets inside the node ----
+            const uint32_t n = (uint32_t)(p1 - p0);
+            const float *__restrict__ costv = m.cost + p0;
+            const uint16_t *__restrict__ viewv = m.view + p0;
+            float *Hv = m.H + p0;
             // issue the loads of the first two label chunks now: they overlap the neighbour
             // classification and the flag waits below
-            const uint64_t k0 = p0 + lane, k1 = k0 + G;
             uint32_t lab0 = 0, lab1 = 0;
             float c0 = 0.0f, c1 = 0.0f;
-            if (k0 < p1) { lab0 = (uint32_t)m.view[k0] + 1u; c0 = m.cost[k0]; }
-            if (k1 < p1) { lab1 = (uint32_t)m.view[k1] + 1u; c1 = m.cost[k1]; }
+            if (lane < n) { lab0 = (uint32_t)viewv[lane] + 1u; c0 = costv[lane]; }
+            if (lane + G < n) { lab1 = (uint32_t)viewv[lane + G] + 1u; c1 = costv[lane + G]; }
             // classify the (at most three) neighbours once: 0 = skip (unseen / parent), 1 = child, 2 = fixed
             uint32_t kind[3] = {0, 0, 0}, xw[3] = {0, 0, 0}, wv[3] = {0, 0, 0};
             float hm[3] = {0.0f, 0.0f, 0.0f};
+            const float *Hw[3] = {nullptr, nullptr, nullptr};
+            const uint32_t *mw[3] = {nullptr, nullptr, nullptr};
+            const uint16_t *mp[3] = {nullptr, nullptr, nullptr};
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 if ((uint32_t)i >= nb.deg) continue;
@@ -417,8 +424,14 @@ __global__ void __launch_bounds__(256) k_up(Mrf m)
                 wv[i] = w; xw[i] = x;
                 if (x == 0) continue;  // unseen faces carry no edges (view_selection.cpp:30,35)
                 const uint32_t lw = local_pair(m, v, w) ? m.level[w] : LVL_DEAD;
-                if (lw <= m.rounds) { if (lw > lv) kind[i] = 1; }
-                else kind[i] = 2;
+                if (lw <= m.rounds) {
+                    if (lw > lv) {
+                        kind[i] = 1;
+                        Hw[i] = m.H + m.ptr[w];
+                        mw[i] = m.mask + (size_t)w * m.mask_words;
+                        mp[i] = m.mpre + (size_t)w * m.mask_words;
+                    }
+                } else kind[i] = 2;
             }
             bool any_child = false;
 #pragma unroll
@@ -432,12 +445,17 @@ __global__ void __launch_bounds__(256) k_up(Mrf m)
             for (int i = 0; i < 3; ++i)
                 if (kind[i] == 1) hm[i] = __ldcg(m.hminp1 + wv[i]);
             auto eval = [&](uint32_t lab, float h) -> float {
+                const uint32_t word = lab >> 5, bit = lab & 31u, below = (1u << bit) - 1u;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     if (kind[i] == 1) {  // Potts message min(h_w(lab), hmin_w + 1)
                         float msg = hm[i];
-                        long long j = find_label(m, wv[i], lab);
-                        if (j >= 0) { float hw = __ldcg(m.H + j); if (hw < msg) msg = hw; }
+                        const uint32_t bits = __ldg(mw[i] + word);
+                        if ((bits >> bit) & 1u) {
+                            const uint32_t j = (uint32_t)__ldg(mp[i] + word) + __popc(bits & below);
+                            const float hw = __ldcg(Hw[i] + j);
+                            if (hw < msg) msg = hw;
+                        }
                         h = h + msg;
                     } else if (kind[i] == 2) {
                         h = h + (lab != xw[i] ? 1.0f : 0.0f);
@@ -445,21 +463,21 @@ __global__ void __launch_bounds__(256) k_up(Mrf m)
                 }
                 return h;
             };
-            if (k0 < p1) {
+            if (lane < n) {
                 const float h0 = eval(lab0, c0);
                 float h1 = 0.0f;
-                if (k1 < p1) h1 = eval(lab1, c1);
-                m.H[k0] = h0;
-                if (h0 < bh) { bh = h0; bk = (uint32_t)(k0 - p0); }
-                if (k1 < p1) {
-                    m.H[k1] = h1;
-                    if (h1 < bh) { bh = h1; bk = (uint32_t)(k1 - p0); }
+                if (lane + G < n) h1 = eval(lab1, c1);
+                Hv[lane] = h0;
+                if (h0 < bh) { bh = h0; bk = lane; }
+                if (lane + G < n) {
+                    Hv[lane + G] = h1;
+                    if (h1 < bh) { bh = h1; bk = lane + G; }
                 }
             }
-            for (uint64_t k = k1 + G; k < p1; k += G) {
-                const float h = eval((uint32_t)m.view[k] + 1u, m.cost[k]);
-                m.H[k] = h;
-                if (h < bh) { bh = h; bk = (uint32_t)(k - p0); }
+            for (uint32_t k = lane + 2 * G; k < n; k += G) {
+                const float h = eval((uint32_t)viewv[k] + 1u, costv[k]);
+                Hv[k] = h;
+                if (h < bh) { bh = h; bk = k; }
             }
         } else {
             // generic degree (non-manifold edges): neighbour loop inside the label loop
@@ -605,6 +623,8 @@ int launch_forest(b2tex_ctx *c, Mrf &m, int do_bucket)
     int grid = 0;
     // few fat blocks: the cost of grid.sync() grows with the number of blocks
     B2_TRY(coop_grid(c, k_forest, sh, &grid, 1024));
+    if (grid > c->num_sms) grid = c->num_sms;  // one fat block per SM: cheapest grid.sync()
+    if (const char *e = getenv("B2TEX_FOREST_BLOCKS_PER_SM")) grid = c->num_sms * std::max(1, atoi(e));
     uint32_t n = m.ne - m.nb;
     int need = (int)((n + 1023) / 1024);
     if (grid > need) grid = need > 0 ? need : 1;

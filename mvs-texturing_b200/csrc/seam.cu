@@ -267,10 +267,11 @@ __device__ __forceinline__ void grid_totals(const double *part, int nblocks, dou
     for (int k = 0; k < 6; ++k) out[k] = v[k];
 }
 
-__global__ void __launch_bounds__(256) k_pcg(Pcg q)
+constexpr int PCG_THREADS = 1024;  // one fat block per SM: grid.sync() cost grows with the block count
+__global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg(Pcg q)
 {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double smem[8 * 6];
+    __shared__ double smem[(PCG_THREADS / 32) * 6];
     const uint32_t R = q.R;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     double *partA = q.partials, *partB = q.partials + (size_t)gridDim.x * 8;
@@ -485,10 +486,10 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
     B2_TRY(c->seam_status.zero(s));
     if (R) {
         int per_sm = 0;
-        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, 256, 0));
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, PCG_THREADS, 0));
         if (per_sm < 1) { set_error("k_pcg cannot be resident"); return B2TEX_ERR_CUDA; }
         int grid = c->num_sms * per_sm;
-        int need = (int)((R + 255) / 256);
+        int need = (int)((R + PCG_THREADS - 1) / PCG_THREADS);
         if (grid > need) grid = std::max(1, need);
         B2_TRY(c->seam_partials.alloc(2 * (size_t)grid * 8));
         Pcg q{R, c->csr_ptr.p, c->csr_col.p, c->csr_val.p, c->seam_diag.p, c->seam_rhs.p, c->seam_x.p,
@@ -498,7 +499,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
         B2_CUDA(cudaEventCreate(&e0));
         B2_CUDA(cudaEventCreate(&e1));
         B2_CUDA(cudaEventRecord(e0, s));
-        B2_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg, dim3(grid), dim3(256), args, 0, s));
+        B2_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg, dim3(grid), dim3(PCG_THREADS), args, 0, s));
         B2_CUDA(cudaEventRecord(e1, s));
         uint32_t st[8];
         B2_CUDA(cudaMemcpyAsync(st, c->seam_status.p, sizeof(st), cudaMemcpyDeviceToHost, s));

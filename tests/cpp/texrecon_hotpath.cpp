@@ -46,7 +46,7 @@ int main(int argc, char **argv)
             tv.world_to_cam[4 * r + 3] = -(R[r][0] * pos[0] + R[r][1] * pos[1] + R[r][2] * pos[2]);
         }
         for (int c = 0; c < 3; ++c) { tv.pos[c] = pos[c]; tv.viewdir[c] = zc[c]; }
-        float P[9] = {100, 0, W / 2.0f, 0, 100, H / 2.0f, 0, 0, 1};
+        float P[9] = {55, 0, W / 2.0f, 0, 55, H / 2.0f, 0, 0, 1};
         std::memcpy(tv.projection, P, sizeof(P));
         tv.width = W; tv.height = H; tv.rgb = images[k].data(); tv.id = k;
     }
