@@ -238,10 +238,18 @@ def main():
                     "gbs": pcg_bytes / pcg_ms / 1e6 if pcg_ms else 0.0, "iterations": its})
     kernels.sort(key=lambda k: -k["ms_per_step"])
     dom = kernels[0]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")  # dram bytes/launch from the committed ncu captures
+    if os.path.exists(tp) and args.workload == "C3":
+        key = dom["name"].replace("mrf.", "").split("+")[0].split("<")[0]
+        traffic = json.load(open(tp)).get(key)
+    launches = dom["launch_groups"] / args.steps if dom["name"] != "k_pcg" else 1
     roofline = {"kernel": dom["name"], "bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": dom["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "launches_per_step": dom["launch_groups"] / args.steps if dom["name"] != "k_pcg" else 1,
-                "note": "algorithmic bytes per DESIGN.md section 4; ncu launch list + dram traffic in profiles/"}
+                "frac": dom["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "launches_per_step": launches, "ms_per_launch": dom["ms_per_step"] / launches,
+                "algorithmic_bytes_per_launch": dom["algorithmic_mb_per_step"] * 1e6 / launches,
+                "note": "algorithmic bytes per DESIGN.md section 4 (SURVEY 8d); traffic = dram bytes of one "
+                        "launch from the ncu --set full capture summarised in profiles/ (C3 workload)"}
     stage_ms = {k: 1e3 * v / 1 for k, v in res["stage_s"].items()}
 
     # ---- e2e arm: three one-shot C-ABI calls with pinned HOST buffers ------------------------------

@@ -69,6 +69,7 @@ typedef struct {
     uint32_t window;       /* StopWhenReturnsDiminish(window, ratio) */
     float ratio;
     uint32_t num_parts;    /* logical face partitions (>=1); >1 reproduces the multi-GPU schedule */
+    uint32_t num_views;    /* DataCosts::rows() for the one-shot call; 0 = derive from the entries */
 } b2tex_mrf_params;
 
 typedef struct {
@@ -155,6 +156,13 @@ int b2tex_calculate_data_costs(const float *verts, uint32_t num_verts, const uin
                                const b2tex_view *views, uint32_t num_views,
                                const b2tex_settings *settings, uint64_t **face_ptr_out,
                                uint16_t **view_out, float **cost_out, b2tex_dc_info *info);
+/* same, into caller-owned (ideally pinned) buffers of `capacity` entries: no allocation, no extra copy;
+ * fails with B2TEX_ERR_ARG (info->nnz = required size) when the capacity is too small */
+int b2tex_calculate_data_costs_into(const float *verts, uint32_t num_verts, const uint32_t *faces,
+                                    const float *face_normals, uint32_t num_faces,
+                                    const b2tex_view *views, uint32_t num_views,
+                                    const b2tex_settings *settings, uint64_t *face_ptr, uint16_t *view,
+                                    float *cost, uint64_t capacity, b2tex_dc_info *info);
 /* tex::view_selection: labels_out[F] (0 = unseen, else view index + 1) */
 int b2tex_view_selection(uint32_t num_faces, const uint32_t *adj_ptr, const uint32_t *adj_idx,
                          const uint64_t *face_ptr, const uint16_t *view, const float *cost,

@@ -29,7 +29,8 @@ EXPORTS = [
     "b2tex_data_costs_normalize", "b2tex_data_costs_download", "b2tex_view_selection_run",
     "b2tex_labels_download", "b2tex_mrf_init", "b2tex_mrf_iterate", "b2tex_mrf_sample_forest",
     "b2tex_seam_run", "b2tex_seam_download", "b2tex_seam_matrix_download", "b2tex_device_ptr",
-    "b2tex_calculate_data_costs", "b2tex_view_selection", "b2tex_global_seam_leveling",
+    "b2tex_calculate_data_costs", "b2tex_calculate_data_costs_into", "b2tex_view_selection",
+    "b2tex_global_seam_leveling",
 ]
 
 
@@ -52,7 +53,7 @@ class B2DcInfo(C.Structure):
 class B2MrfParams(C.Structure):
     _fields_ = [("max_iterations", C.c_uint32), ("rounds", C.c_uint32), ("root_div", C.c_uint32),
                 ("seed", C.c_uint32), ("window", C.c_uint32), ("ratio", C.c_float),
-                ("num_parts", C.c_uint32)]
+                ("num_parts", C.c_uint32), ("num_views", C.c_uint32)]
 
 
 class B2MrfInfo(C.Structure):
@@ -333,9 +334,23 @@ def _grab(ptr, ctype, n):
     return a
 
 
-def calculate_data_costs(scene, settings: Settings | None = None) -> DataCosts:
-    """tex::calculate_data_costs (calculate_data_costs.cpp:308-323) through b2tex_calculate_data_costs."""
+def calculate_data_costs(scene, settings: Settings | None = None, out=None) -> DataCosts:
+    """tex::calculate_data_costs (calculate_data_costs.cpp:308-323) through b2tex_calculate_data_costs.
+    `out` = (face_ptr u64[F+1], view u16[cap], cost f32[cap]) caller-owned (pinned) buffers: the
+    result is written in place (b2tex_calculate_data_costs_into), no allocation or extra copy."""
     st = settings or Settings()
+    if out is not None:
+        views = make_views(scene.pos, scene.viewdir, scene.proj, scene.w2c, scene.width, scene.height, scene.images)
+        s = B2Settings(st.data_term, st.outlier_removal, 1 if st.geometric_visibility_test else 0)
+        info = B2DcInfo()
+        v, f, n = _c(scene.verts, np.float32), _c(scene.faces, np.uint32), _c(scene.face_normals, np.float32)
+        fp, vw, cs = out
+        _check(lib().b2tex_calculate_data_costs_into(_p(v), C.c_uint32(v.shape[0]), _p(f), _p(n), C.c_uint32(f.shape[0]),
+                                                     views, C.c_uint32(scene.num_views), C.byref(s), _p(fp), _p(vw),
+                                                     _p(cs), C.c_uint64(len(vw)), C.byref(info)))
+        dc = DataCosts(f.shape[0], scene.num_views, fp, vw[:info.nnz], cs[:info.nnz])
+        dc.info = info
+        return dc
     if scene.num_views > 65535:
         raise RuntimeError("Exeeded maximal number of views")
     views = make_views(scene.pos, scene.viewdir, scene.proj, scene.w2c, scene.width, scene.height, scene.images)
@@ -355,7 +370,7 @@ def calculate_data_costs(scene, settings: Settings | None = None) -> DataCosts:
 
 def view_selection(data_costs: DataCosts, adj_ptr, adj_idx, settings: Settings | None = None, **mrf_kw):
     """tex::view_selection (view_selection.cpp:18-133): returns (labels[F], info)."""
-    p = mrf_params(**mrf_kw)
+    p = mrf_params(num_views=data_costs.rows(), **mrf_kw)
     F = data_costs.cols()
     labels = np.zeros(F, np.uint32)
     info = B2MrfInfo()

@@ -32,6 +32,7 @@ void b2tex_default_mrf_params(b2tex_mrf_params *p)
     p->window = 5;         // view_selection.cpp:84
     p->ratio = 0.01f;
     p->num_parts = 1;
+    p->num_views = 0;
 }
 
 int b2tex_create(int device, b2tex_ctx **out)
@@ -364,9 +365,9 @@ uint64_t b2tex_device_ptr(b2tex_ctx *c, const char *name, uint64_t *n)
 
 // ---- one-shot host-buffer entry points ---------------------------------------------------------
 
-int b2tex_calculate_data_costs(const float *verts, uint32_t nv, const uint32_t *faces, const float *normals,
-                               uint32_t nf, const b2tex_view *views, uint32_t K, const b2tex_settings *st,
-                               uint64_t **face_ptr_out, uint16_t **view_out, float **cost_out, b2tex_dc_info *info)
+static int dc_oneshot(const float *verts, uint32_t nv, const uint32_t *faces, const float *normals, uint32_t nf,
+                      const b2tex_view *views, uint32_t K, const b2tex_settings *st, b2tex_dc_info *info,
+                      b2tex_ctx **out)
 {
     if (K > 65535u) { set_error("Exeeded maximal number of views"); return B2TEX_ERR_LIMITS; }
     b2tex_ctx *c = nullptr;
@@ -374,11 +375,39 @@ int b2tex_calculate_data_costs(const float *verts, uint32_t nv, const uint32_t *
     int rc = b2tex_set_mesh(c, verts, nv, faces, normals, nf);
     if (rc == B2TEX_OK) rc = b2tex_set_views(c, views, K);
     if (rc == B2TEX_OK) rc = b2tex_data_costs_run(c, st, info);
-    if (rc == B2TEX_OK) {
-        *face_ptr_out = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)nf + 1));
-        *view_out = (uint16_t *)malloc(sizeof(uint16_t) * (info->nnz ? info->nnz : 1));
-        *cost_out = (float *)malloc(sizeof(float) * (info->nnz ? info->nnz : 1));
-        rc = b2tex_data_costs_download(c, *face_ptr_out, *view_out, *cost_out, nullptr);
+    if (rc != B2TEX_OK) { b2tex_destroy(c); return rc; }
+    *out = c;
+    return B2TEX_OK;
+}
+
+int b2tex_calculate_data_costs(const float *verts, uint32_t nv, const uint32_t *faces, const float *normals,
+                               uint32_t nf, const b2tex_view *views, uint32_t K, const b2tex_settings *st,
+                               uint64_t **face_ptr_out, uint16_t **view_out, float **cost_out, b2tex_dc_info *info)
+{
+    b2tex_ctx *c = nullptr;
+    B2_TRY(dc_oneshot(verts, nv, faces, normals, nf, views, K, st, info, &c));
+    *face_ptr_out = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)nf + 1));
+    *view_out = (uint16_t *)malloc(sizeof(uint16_t) * (info->nnz ? info->nnz : 1));
+    *cost_out = (float *)malloc(sizeof(float) * (info->nnz ? info->nnz : 1));
+    int rc = b2tex_data_costs_download(c, *face_ptr_out, *view_out, *cost_out, nullptr);
+    b2tex_destroy(c);
+    return rc;
+}
+
+int b2tex_calculate_data_costs_into(const float *verts, uint32_t nv, const uint32_t *faces, const float *normals,
+                                    uint32_t nf, const b2tex_view *views, uint32_t K, const b2tex_settings *st,
+                                    uint64_t *face_ptr, uint16_t *view, float *cost, uint64_t capacity,
+                                    b2tex_dc_info *info)
+{
+    b2tex_ctx *c = nullptr;
+    B2_TRY(dc_oneshot(verts, nv, faces, normals, nf, views, K, st, info, &c));
+    int rc = B2TEX_OK;
+    if (info->nnz > capacity) {
+        set_error("data costs need %llu entries, caller provided %llu", (unsigned long long)info->nnz,
+                  (unsigned long long)capacity);
+        rc = B2TEX_ERR_ARG;
+    } else {
+        rc = b2tex_data_costs_download(c, face_ptr, view, cost, nullptr);
     }
     b2tex_destroy(c);
     return rc;
@@ -391,9 +420,15 @@ int b2tex_view_selection(uint32_t nf, const uint32_t *adj_ptr, const uint32_t *a
     b2tex_ctx *c = nullptr;
     B2_TRY(b2tex_create(0, &c));
     c->F = nf; c->face_begin = 0; c->face_end = nf;
-    uint32_t maxview = 0;
-    for (uint64_t i = 0; i < face_ptr[nf]; ++i) maxview = view[i] > maxview ? view[i] : maxview;
-    c->K = face_ptr[nf] ? maxview + 1 : 0;  // DataCosts::rows() is not part of the CSR; bound from content
+    // DataCosts::rows() (= number of views) is not part of the CSR: params->num_views if the caller
+    // knows it, otherwise bounded from the content (one host pass over nnz)
+    uint32_t K = params ? params->num_views : 0;
+    if (K == 0) {
+        uint32_t maxview = 0;
+        for (uint64_t i = 0; i < face_ptr[nf]; ++i) maxview = view[i] > maxview ? view[i] : maxview;
+        K = face_ptr[nf] ? maxview + 1 : 0;
+    }
+    c->K = K;
     int rc = b2tex_set_data_costs(c, face_ptr, view, cost);
     if (rc == B2TEX_OK) rc = b2tex_set_adjacency(c, adj_ptr, adj_idx);
     if (rc == B2TEX_OK) rc = b2tex_view_selection_run(c, params, info, nullptr);

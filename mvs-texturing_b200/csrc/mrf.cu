@@ -663,10 +663,10 @@ int enqueue_iteration(b2tex_ctx *c, Mrf &m)
     cudaStream_t s = c->stream;
     if (m.ne <= m.nb) return B2TEX_OK;
     {
-        ScopedTimer tf(c, "  mrf.k_forest");
+        ScopedTimer tf(c, "mrf.k_forest+sort", 20.0 * (double)(m.ne - m.nb));
         B2_TRY(launch_forest(c, m, 1));
     }
-    ScopedTimer *tu = new ScopedTimer(c, "  mrf.k_up");
+    ScopedTimer *tu = new ScopedTimer(c, "mrf.k_up", 14.0 * (double)c->nnz);
     switch (c->mrf_group) {
         case 4: B2_TRY(launch_up<4>(c, m)); break;
         case 8: B2_TRY(launch_up<8>(c, m)); break;
@@ -676,7 +676,7 @@ int enqueue_iteration(b2tex_ctx *c, Mrf &m)
     delete tu;
     static const bool repeat_up = getenv("B2TEX_MRF_REPEAT_UP") != nullptr;
     if (repeat_up) {  // experiment: second sweep finds every flag already set (no dataflow waits)
-        ScopedTimer tu2(c, "  mrf.k_up(again)");
+        ScopedTimer tu2(c, "mrf.k_up(again)");
         switch (c->mrf_group) {
             case 4: B2_TRY(launch_up<4>(c, m)); break;
             case 8: B2_TRY(launch_up<8>(c, m)); break;
@@ -685,13 +685,13 @@ int enqueue_iteration(b2tex_ctx *c, Mrf &m)
         }
     }
     {
-        ScopedTimer td(c, "  mrf.k_down");
+        ScopedTimer td(c, "mrf.k_down");
         int grid = 0;
         B2_TRY(coop_grid(c, k_down, 0, &grid));
         void *args[] = {&m};
         B2_CUDA(cudaLaunchCooperativeKernel((void *)k_down, dim3(grid), dim3(256), args, 0, s));
     }
-    ScopedTimer te(c, "  mrf.k_energy");
+    ScopedTimer te(c, "mrf.k_energy");
     B2_CUDA(cudaMemsetAsync(m.energy, 0, sizeof(unsigned long long), s));
     k_energy<<<std::max(1, c->num_sms * 8), 256, 0, s>>>(m);
     B2_KERNEL_CHECK();
@@ -782,7 +782,6 @@ int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *efix)
     if (t == 0) { set_error("mrf_iterate: iterations are numbered from 1"); return B2TEX_ERR_ARG; }
     Mrf m = make_mrf(c, t);
     {
-        ScopedTimer tm(c, "mrf_iteration", 14.0 * (double)c->nnz + 20.0 * (double)(c->face_end - c->face_begin));
         B2_TRY(enqueue_iteration(c, m));
     }
     return read_energy(c, m, efix);

@@ -408,7 +408,8 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
         return B2TEX_ERR_ARG;
     }
     cudaStream_t s = c->stream;
-    B2_TRY(prepare_images(c, c->prepared_data_term >= 0 ? c->prepared_data_term : 1));
+    // only the camera block and the rgb images are needed here (no gradient image)
+    B2_TRY(prepare_images(c, c->prepared_data_term >= 0 ? c->prepared_data_term : 0));
     const uint32_t Vn = c->Vn;
     ScopedTimer *tm_asm = new ScopedTimer(c, "seam_assembly");
     DevBuf<uint32_t> &cnt = c->s_cnt32, &row_vertex = c->s_row_vertex;
