@@ -233,7 +233,9 @@ def main():
     # the PCG kernel is timed by its own events inside seam_run
     pcg_ms = res["seam"].cg_ms
     R, nnzL, its = res["seam"].num_rows, res["seam"].nnz_full, res["seam"].cg_launch_iterations
-    pcg_bytes = its * (8.0 * nnzL + 4.0 * (R + 1) + 13 * 4.0 * R * 3)
+    # SURVEY 8d formula with the storage actually used: 4 B per Laplacian entry (column | weight class)
+    # + 4 B diagonal value per row instead of 8 B (value + column) per entry
+    pcg_bytes = its * (4.0 * nnzL + 4.0 * R + 4.0 * (R + 1) + 13 * 4.0 * R * 3)
     kernels.append({"name": "k_pcg", "launch_groups": 1, "ms_per_step": pcg_ms, "algorithmic_mb_per_step": pcg_bytes / 1e6,
                     "gbs": pcg_bytes / pcg_ms / 1e6 if pcg_ms else 0.0, "iterations": its})
     kernels.sort(key=lambda k: -k["ms_per_step"])

@@ -147,7 +147,7 @@ struct b2tex_ctx {
     bool bvh_built = false;
     b2::DevBuf<uint32_t> vrank, vorder;  // Morton rank of every vertex and its inverse
     // persistent scratch (grow only): cudaMalloc/cudaFree inside a stage would serialise the device
-    b2::DevBuf<uint32_t> s_bnd, s_ids_in, s_ids_out, s_counters, s_vi_in, s_cnt32, s_row_vertex, s_rcnt;
+    b2::DevBuf<uint32_t> s_bnd, s_ids_in, s_ids_out, s_counters, s_vi_in, s_cnt32, s_row_vertex, s_rcnt, s_pass_bits;
     b2::DevBuf<uint64_t> s_keys_in, s_keys_out, s_vk_in, s_vk_out, s_cnt64;
     b2::DevBuf<int> s_parent_internal, s_parent_leaf;
 
@@ -195,7 +195,8 @@ struct b2tex_ctx {
     bool have_rings = false;
     b2::DevBuf<uint32_t> row_ptr, row_label, arow_ptr, arow_rows;
     b2::DevBuf<float> arow_b;
-    b2::DevBuf<uint32_t> csr_ptr, csr_col;
+    b2::DevBuf<uint32_t> csr_ptr, csr_col, csr_enc;
+    b2::DevBuf<float> seam_dval;
     b2::DevBuf<float> csr_val, seam_diag, seam_rhs, seam_x, seam_r, seam_t;
     b2::DevBuf<float4> seam_p;
     b2::DevBuf<double> seam_partials;

@@ -96,9 +96,24 @@ __device__ __forceinline__ void load_face(const float *__restrict__ verts, const
 }
 
 // calculate_data_costs.cpp:179-191; returns true if the pair survives culling and projects validly
-__device__ __forceinline__ bool cull_pair(const ViewDev &V, const FaceGeom &g, float cos_thr)
+__device__ __forceinline__ bool cull_pair(const ViewDev &V, const FaceGeom &g, float cos_thr, float margin)
 {
     float ftv[3] = {V.pos[0] - g.c[0], V.pos[1] - g.c[1], V.pos[2] - g.c[2]};
+    {
+        // Conservative pre-rejects on the UNNORMALISED vector (no sqrt, no divisions).  They only fire
+        // when the exact test below is certain to fail: `margin` (1e-5 * max(1,|n|)) is > 10x the
+        // worst-case rounding difference between dot(ftv/|ftv|, n) and dot(ftv, n)/|ftv|.  Everything
+        // else takes the exact path, so the surviving set is unchanged (bit-exact vs the oracle).
+        const float d0 = ftv[0] * g.n[0] + ftv[1] * g.n[1] + ftv[2] * g.n[2];
+        const float len2 = ftv[0] * ftv[0] + ftv[1] * ftv[1] + ftv[2] * ftv[2];
+        const float m2 = margin * margin * len2;
+        if (d0 < 0.0f && d0 * d0 > m2) return false;                        // back face (:183-185)
+        const float ct = cos_thr - margin;
+        if (d0 >= 0.0f && ct > 0.0f && d0 * d0 < ct * ct * len2) return false;  // > 75 degrees (:187)
+        const float dd = V.dir[0] * ftv[0] + V.dir[1] * ftv[1] + V.dir[2] * ftv[2];
+        const float dir2 = V.dir[0] * V.dir[0] + V.dir[1] * V.dir[1] + V.dir[2] * V.dir[2];
+        if (dd > 0.0f && dd * dd > 1e-10f * fmaxf(1.0f, dir2) * len2) return false;  // behind the camera
+    }
     float nrm = sqrtf(((0.0f + ftv[0] * ftv[0]) + ftv[1] * ftv[1]) + ftv[2] * ftv[2]);
     ftv[0] = ftv[0] / nrm; ftv[1] = ftv[1] / nrm; ftv[2] = ftv[2] / nrm;
     float viewing_angle = ((0.0f + ftv[0] * g.n[0]) + ftv[1] * g.n[1]) + ftv[2] * g.n[2];
@@ -122,21 +137,34 @@ __global__ void __launch_bounds__(256) k_cull(const float *__restrict__ verts, c
                                               uint32_t K, uint32_t face_begin, uint32_t face_end, float cos_thr,
                                               uint64_t *cand_cnt, const uint64_t *__restrict__ cand_ptr,
                                               uint16_t *cand_view, uint32_t *cand_face, uint32_t *need_bits,
-                                              uint32_t vwords, const uint32_t *__restrict__ vrank)
+                                              uint32_t vwords, const uint32_t *__restrict__ vrank,
+                                              uint32_t *pass_bits, uint32_t kwords)
 {
     uint32_t f = face_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= face_end) return;
     FaceGeom g;
     uint32_t vid[3];
-    load_face(verts, faces, normals, f, g, vid);
+    load_face(verts, faces, FILL ? nullptr : normals, f, g, vid);
+    const float margin = FILL ? 0.0f
+                              : 1e-5f * fmaxf(1.0f, sqrtf(g.n[0] * g.n[0] + g.n[1] * g.n[1] + g.n[2] * g.n[2]));
     uint64_t base = FILL ? cand_ptr[f] : 0;
     uint32_t count = 0;
     // ray bitmaps are indexed by the Morton rank of the vertex so that a warp of k_rays traces 32
     // spatially adjacent origins towards the same camera
     uint32_t vr[3] = {0, 0, 0};
     if (FILL && need_bits) { vr[0] = vrank[vid[0]]; vr[1] = vrank[vid[1]]; vr[2] = vrank[vid[2]]; }
+    uint32_t bits = 0;
     for (uint32_t j = 0; j < K; ++j) {
-        if (!cull_pair(views[j], g, cos_thr)) continue;
+        // the count pass records which views survive; the fill pass only replays the set bits
+        if (FILL) {
+            if ((j & 31u) == 0) bits = pass_bits[(size_t)(f - face_begin) * kwords + (j >> 5)];
+            if (!((bits >> (j & 31u)) & 1u)) continue;
+        } else {
+            const bool pass = cull_pair(views[j], g, cos_thr, margin);
+            if (pass) bits |= 1u << (j & 31u);
+            if ((j & 31u) == 31u || j + 1 == K) { pass_bits[(size_t)(f - face_begin) * kwords + (j >> 5)] = bits; bits = 0; }
+            if (!pass) continue;
+        }
         if (FILL) {
             cand_view[base + count] = (uint16_t)j;
             cand_face[base + count] = f;
@@ -419,6 +447,8 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     const uint32_t F = c->F, K = c->K, fb = c->face_begin, fe = c->face_end;
     const uint32_t nf = fe - fb;
     const uint32_t vwords = (c->Vn + 31) / 32;
+    const uint32_t kwords = (c->K + 31) / 32;
+    B2_TRY(c->s_pass_bits.alloc((size_t)(c->face_end - c->face_begin) * kwords));
     static const float cos_thr = cos75_threshold();
 
     B2_TRY(c->cand_ptr.alloc((size_t)F + 1));
@@ -433,7 +463,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     if (nf) {
         ScopedTimer tm(c, "k_cull<count>", mesh_bytes + 8.0 * nf);
         k_cull<false><<<blocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->normals.p, c->views_dev.p, K, fb, fe,
-                                             cos_thr, cnt.p, nullptr, nullptr, nullptr, nullptr, vwords, nullptr);
+                                             cos_thr, cnt.p, nullptr, nullptr, nullptr, nullptr, vwords, nullptr, c->s_pass_bits.p, kwords);
     }
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u64(c, cnt.p, c->cand_ptr.p, (size_t)F + 1));
@@ -453,7 +483,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
         ScopedTimer tm(c, "k_cull<fill>", mesh_bytes + 6.0 * (double)num_cand);
         k_cull<true><<<blocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->normals.p, c->views_dev.p, K, fb, fe,
                                             cos_thr, nullptr, c->cand_ptr.p, c->cand_view.p, c->cand_face.p,
-                                            vis ? c->need_bits.p : nullptr, vwords, c->vrank.p);
+                                            vis ? c->need_bits.p : nullptr, vwords, c->vrank.p, c->s_pass_bits.p, kwords);
     }
     B2_KERNEL_CHECK();
     unsigned long long *ray_count = reinterpret_cast<unsigned long long *>(c->scalars.p + 2);

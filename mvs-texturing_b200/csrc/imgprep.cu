@@ -113,11 +113,10 @@ __global__ void __launch_bounds__(256) k_lum_sobel_vec(const uint8_t *__restrict
                 int g = lum[ly + 2][lx], hh = lum[ly + 2][lx + 1], k = lum[ly + 2][lx + 2];
                 int sx = (c - a) + 2 * (f - d) + (k - g);
                 int sy = (g - a) + 2 * (hh - b) + (k - c);
-                int ss = sx * sx + sy * sy;
-                int r = (int)sqrtf((float)ss);
-                while (r * r > ss) --r;
-                while ((r + 1) * (r + 1) <= ss) ++r;
-                out = (uint8_t)(r < 255 ? r : 255);
+                const int ss = sx * sx + sy * sy;  // < 2^24: exact in fp32
+                // floor(sqrt(ss)) for ss < 255^2: the correctly rounded fp32 root of an integer below
+                // 2^16 cannot round up to the next integer (k - sqrt(k^2-1) > 1/(2k) >> ulp)
+                out = ss >= 255 * 255 ? (uint8_t)255 : (uint8_t)(int)__fsqrt_rn((float)ss);
             }
             o[j] = out;
         }

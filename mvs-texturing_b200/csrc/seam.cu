@@ -183,7 +183,8 @@ template <bool FILL>
 __global__ void k_matrix(uint32_t R, SeamMesh m, const uint32_t *__restrict__ row_vertex,
                          const uint32_t *__restrict__ arow_ptr, const uint32_t *__restrict__ arow_rows,
                          const float *__restrict__ arow_b, uint32_t *cnt, const uint32_t *__restrict__ csr_ptr,
-                         uint32_t *csr_col, float *csr_val, float *inv_diag, float *rhs /* [3][R] */)
+                         uint32_t *csr_col, float *csr_val, float *inv_diag, float *rhs /* [3][R] */,
+                         uint32_t *csr_enc, float *diag_val)
 {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
@@ -198,7 +199,7 @@ __global__ void k_matrix(uint32_t R, SeamMesh m, const uint32_t *__restrict__ ro
         if (adj == i) continue;
         uint32_t c = find_row(m, adj, label);
         if (c == 0xFFFFFFFFu) continue;
-        if (FILL) { csr_col[o] = c; csr_val[o] = -lam2; ++o; }
+        if (FILL) { csr_col[o] = c; csr_val[o] = -lam2; csr_enc[o] = c; ++o; }
         gsum += lam2;
         ++n;
     }
@@ -207,7 +208,7 @@ __global__ void k_matrix(uint32_t R, SeamMesh m, const uint32_t *__restrict__ ro
         uint32_t ra = arow_rows[2 * (size_t)a], rb = arow_rows[2 * (size_t)a + 1];
         if (ra != r && rb != r) continue;
         if (FILL) {
-            csr_col[o] = (ra == r) ? rb : ra; csr_val[o] = -1.0f; ++o;
+            csr_col[o] = (ra == r) ? rb : ra; csr_val[o] = -1.0f; csr_enc[o] = csr_col[o] | 0x80000000u; ++o;
             for (int c = 0; c < 3; ++c) {
                 float b = arow_b[3 * (size_t)a + c];
                 rh[c] = (ra == r) ? rh[c] + b : rh[c] - b;
@@ -220,6 +221,8 @@ __global__ void k_matrix(uint32_t R, SeamMesh m, const uint32_t *__restrict__ ro
     float diag = (float)na + gsum;
     csr_col[csr_ptr[r]] = r;
     csr_val[csr_ptr[r]] = diag;
+    csr_enc[csr_ptr[r]] = r;  // first entry of every row = the diagonal (value in diag_val)
+    diag_val[r] = diag;
     inv_diag[r] = diag != 0.0f ? 1.0f / diag : 1.0f;  // Eigen DiagonalPreconditioner
     for (int c = 0; c < 3; ++c) rhs[(size_t)c * R + r] = rh[c];
 }
@@ -229,8 +232,8 @@ __global__ void k_matrix(uint32_t R, SeamMesh m, const uint32_t *__restrict__ ro
 // ---------------------------------------------------------------------------------------------
 struct Pcg {
     uint32_t R;
-    const uint32_t *csr_ptr, *csr_col;
-    const float *csr_val, *inv_diag, *rhs;
+    const uint32_t *csr_ptr, *csr_enc;  // enc = column | (weight class << 31): the Laplacian has only two
+    const float *diag_val, *inv_diag, *rhs;  // off-diagonal values (-1 seam rows, -lambda^2 regulariser): 4 B per entry
     float *x, *r, *t;       // [3][R]
     float4 *p;              // [R] (x,y,z = channels)
     double *partials;       // [2][grid][8]
@@ -312,14 +315,17 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg(Pcg q)
         // phase 1: t = A p, p.t
         for (int k = 0; k < 6; ++k) acc[k] = 0.0;
         for (uint32_t i = tid; i < R; i += nth) {
-            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
             const uint32_t e1 = q.csr_ptr[i + 1];
-            for (uint32_t e = q.csr_ptr[i]; e < e1; ++e) {
-                const float a = q.csr_val[e];
-                const float4 pv = q.p[q.csr_col[e]];
+            const float4 pi = q.p[i];
+            const float dv = q.diag_val[i];
+            float s0 = 0.0f + dv * pi.x, s1 = 0.0f + dv * pi.y, s2 = 0.0f + dv * pi.z;  // diagonal first
+            const float lam2 = 0.1f * 0.1f;
+            for (uint32_t e = q.csr_ptr[i] + 1; e < e1; ++e) {
+                const uint32_t enc = q.csr_enc[e];
+                const float a = (enc >> 31) ? -1.0f : -lam2;
+                const float4 pv = q.p[enc & 0x7FFFFFFFu];
                 s0 += a * pv.x; s1 += a * pv.y; s2 += a * pv.z;
             }
-            const float4 pi = q.p[i];
             q.t[i] = s0; q.t[(size_t)R + i] = s1; q.t[2 * (size_t)R + i] = s2;
             acc[0] += (double)pi.x * s0; acc[1] += (double)pi.y * s1; acc[2] += (double)pi.z * s2;
         }
@@ -453,7 +459,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
     const uint32_t rb = (R + 127) / 128;
     if (R)
         k_matrix<false><<<rb, 128, 0, s>>>(R, m, row_vertex.p, c->arow_ptr.p, c->arow_rows.p, c->arow_b.p, rcnt.p,
-                                           nullptr, nullptr, nullptr, nullptr, nullptr);
+                                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u32(c, rcnt.p, c->csr_ptr.p, (size_t)R + 1));
     uint32_t nnzL = 0;
@@ -462,6 +468,8 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
     c->nnz_L = nnzL;
     B2_TRY(c->csr_col.alloc(nnzL));
     B2_TRY(c->csr_val.alloc(nnzL));
+    B2_TRY(c->csr_enc.alloc(nnzL));
+    B2_TRY(c->seam_dval.alloc(R));
     B2_TRY(c->seam_diag.alloc(R));
     B2_TRY(c->seam_rhs.alloc(3 * (size_t)R));
     B2_TRY(c->seam_x.alloc(3 * (size_t)R));
@@ -470,7 +478,8 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
     B2_TRY(c->seam_p.alloc(R));
     if (R)
         k_matrix<true><<<rb, 128, 0, s>>>(R, m, row_vertex.p, c->arow_ptr.p, c->arow_rows.p, c->arow_b.p, nullptr,
-                                          c->csr_ptr.p, c->csr_col.p, c->csr_val.p, c->seam_diag.p, c->seam_rhs.p);
+                                          c->csr_ptr.p, c->csr_col.p, c->csr_val.p, c->seam_diag.p, c->seam_rhs.p, c->csr_enc.p,
+                                          c->seam_dval.p);
     B2_KERNEL_CHECK();
 
     // Gamma rows = sum over rows of Gamma neighbours / 2
@@ -493,7 +502,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
         int need = (int)((R + PCG_THREADS - 1) / PCG_THREADS);
         if (grid > need) grid = std::max(1, need);
         B2_TRY(c->seam_partials.alloc(2 * (size_t)grid * 8));
-        Pcg q{R, c->csr_ptr.p, c->csr_col.p, c->csr_val.p, c->seam_diag.p, c->seam_rhs.p, c->seam_x.p,
+        Pcg q{R, c->csr_ptr.p, c->csr_enc.p, c->seam_dval.p, c->seam_diag.p, c->seam_rhs.p, c->seam_x.p,
               c->seam_r.p, c->seam_t.p, c->seam_p.p, c->seam_partials.p, c->seam_status.p, 1000u, 0.0001f};
         void *args[] = {&q};
         cudaEvent_t e0, e1;
