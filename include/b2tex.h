@@ -137,6 +137,8 @@ int b2tex_labels_download(b2tex_ctx *ctx, uint32_t *labels);
  * labels between iterations; view_selection_run = init + loop(iterate, energy) */
 int b2tex_mrf_init(b2tex_ctx *ctx, const b2tex_mrf_params *params, int64_t *energy_fixed);
 int b2tex_mrf_iterate(b2tex_ctx *ctx, uint32_t iteration, int64_t *energy_fixed);
+/* energy of the owned faces under the labels currently on the device (call after a label exchange) */
+int b2tex_mrf_energy(b2tex_ctx *ctx, int64_t *energy_fixed);
 int b2tex_mrf_sample_forest(b2tex_ctx *ctx, const b2tex_mrf_params *params, uint32_t iteration,
                             uint32_t *level_out_host);
 

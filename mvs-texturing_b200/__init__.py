@@ -27,7 +27,7 @@ EXPORTS = [
     "b2tex_set_vertex_rings", "b2tex_set_data_costs", "b2tex_set_labels", "b2tex_set_face_range",
     "b2tex_data_costs_run", "b2tex_data_costs_qualities", "b2tex_data_costs_histogram",
     "b2tex_data_costs_normalize", "b2tex_data_costs_download", "b2tex_view_selection_run",
-    "b2tex_labels_download", "b2tex_mrf_init", "b2tex_mrf_iterate", "b2tex_mrf_sample_forest",
+    "b2tex_labels_download", "b2tex_mrf_init", "b2tex_mrf_iterate", "b2tex_mrf_energy", "b2tex_mrf_sample_forest",
     "b2tex_seam_run", "b2tex_seam_download", "b2tex_seam_matrix_download", "b2tex_device_ptr",
     "b2tex_calculate_data_costs", "b2tex_calculate_data_costs_into", "b2tex_view_selection",
     "b2tex_global_seam_leveling",
@@ -254,6 +254,11 @@ class Context:
     def mrf_iterate(self, t):
         e = C.c_int64()
         _check(lib().b2tex_mrf_iterate(self._h, C.c_uint32(t), C.byref(e)))
+        return e.value
+
+    def mrf_energy(self):
+        e = C.c_int64()
+        _check(lib().b2tex_mrf_energy(self._h, C.byref(e)))
         return e.value
 
     def mrf_sample_forest(self, iteration, **kw):

@@ -258,6 +258,11 @@ int b2tex_mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *efix)
     B2_CUDA(cudaSetDevice(c->device));
     return mrf_iterate(c, t, efix);
 }
+int b2tex_mrf_energy(b2tex_ctx *c, int64_t *efix)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return mrf_energy_only(c, efix);
+}
 int b2tex_mrf_sample_forest(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t, uint32_t *level)
 {
     B2_CUDA(cudaSetDevice(c->device));

@@ -233,6 +233,7 @@ int data_costs_histogram(b2tex_ctx *c, float gmax);
 int data_costs_normalize(b2tex_ctx *c, float gmax, const uint32_t *bins_host, b2tex_dc_info *info);
 int mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *energy_fixed);
 int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *energy_fixed);
+int mrf_energy_only(b2tex_ctx *c, int64_t *energy_fixed);
 int mrf_sample_only(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t, uint32_t *level_host);
 int mrf_energy_double(b2tex_ctx *c, double *e, uint64_t *unseen);
 int seam_run(b2tex_ctx *c, b2tex_seam_info *info);

@@ -787,6 +787,18 @@ int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *efix)
     return read_energy(c, m, efix);
 }
 
+// fixed-point energy of the owned nodes with the labels currently in the context (a sharded run calls
+// this after the boundary-label exchange, so that cut edges see the neighbours' NEW labels)
+int mrf_energy_only(b2tex_ctx *c, int64_t *efix)
+{
+    if (!c->mrf_ready) { set_error("mrf_energy before mrf_init"); return B2TEX_ERR_ARG; }
+    Mrf m = make_mrf(c, 1);
+    B2_CUDA(cudaMemsetAsync(m.energy, 0, sizeof(unsigned long long), c->stream));
+    if (m.ne > m.nb) k_energy<<<std::max(1, c->num_sms * 8), 256, 0, c->stream>>>(m);
+    B2_KERNEL_CHECK();
+    return read_energy(c, m, efix);
+}
+
 int mrf_sample_only(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t, uint32_t *level_host)
 {
     if (!c->mrf_ready) { int64_t e; B2_TRY(mrf_init(c, p, &e)); }

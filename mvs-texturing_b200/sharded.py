@@ -117,7 +117,7 @@ class ShardedPipeline:
         P, psz, F = self.world, self.psz, self.F
         p = b2.mrf_params(num_parts=P)
         ratio = float(np.float32(p.ratio))
-        efix = [self._allreduce_energy(c.mrf_init(num_parts=P))]
+        c.mrf_init(num_parts=P)
         lp, ln = c.device_ptr("labels")
         labels = torch.as_tensor(_DevArray(lp, ln, "<i4"), device=dev)
         gathered = torch.zeros(P * psz, dtype=torch.int32, device=dev)
@@ -127,12 +127,14 @@ class ShardedPipeline:
             gather_label_ranges(dist, labels, mine, gathered, self.fb, self.fe, F)
             torch.cuda.current_stream().synchronize()
 
+        # the energy of cut edges needs the neighbours' NEW labels: evaluate it after every exchange
         exchange()
+        efix = [self._allreduce_energy(c.mrf_energy())]
         t = 1
         while t <= p.max_iterations:
-            e = c.mrf_iterate(t)
+            c.mrf_iterate(t)
             exchange()
-            efix.append(self._allreduce_energy(e))
+            efix.append(self._allreduce_energy(c.mrf_energy()))
             if returns_diminish(efix, t, p.window, ratio):
                 break
             t += 1
