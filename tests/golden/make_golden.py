@@ -18,7 +18,7 @@ import oracle as O  # noqa: E402
 
 scene = importlib.import_module("mvs-texturing_b200.scene")
 out = {}
-for name in ["tiny", "small", "C1", "C1d", "C2s"]:
+for name in ["tiny", "small", "C1", "C1d", "C2s", "C3s"]:
     s = scene.config(name)
     dc = O.data_costs(s)
     ap, ai = scene.face_adjacency(s.faces)
