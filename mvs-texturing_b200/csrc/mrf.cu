@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) k_scatter_order(Mrf m)
 
 // ---- bottom-up min-sum messages, dataflow over the forest -------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(256) k_up(Mrf m)
+__global__ void __launch_bounds__(256, 8) k_up(Mrf m)
 {
     constexpr uint32_t GPW = 32 / G;  // nodes per warp
     const uint32_t lane = threadIdx.x & (G - 1);
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(256) k_up(Mrf m)
 }
 
 // ---- top-down assignment, dataflow: one thread per node waits for its parent ---------------------------
-__global__ void __launch_bounds__(256) k_down(Mrf m)
+__global__ void __launch_bounds__(256, 8) k_down(Mrf m)
 {
     const uint32_t total = m.ctl[CTL_TOTAL];
     const uint32_t stamp = m.iter;
