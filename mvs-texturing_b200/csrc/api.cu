@@ -62,7 +62,6 @@ void b2tex_destroy(b2tex_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->mrf_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)c->mrf_graph_exec);
     cudaStreamSynchronize(c->stream);
     cudaStreamDestroy(c->stream);
     delete c;

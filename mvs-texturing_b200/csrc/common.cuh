@@ -176,7 +176,7 @@ struct b2tex_ctx {
 
     // mrf scratch
     b2::DevBuf<float> mrf_H, mrf_hminp1;
-    b2::DevBuf<uint32_t> mrf_amin, mrf_level, mrf_order, mrf_lvlptr, mrf_cursor;
+    b2::DevBuf<uint32_t> mrf_amin, mrf_level, mrf_order, mrf_flags, mrf_ctl;
     b2::DevBuf<unsigned long long> mrf_energy;
     b2::DevBuf<uint32_t> mrf_mask;     // per-node label bitmasks
     b2::DevBuf<uint16_t> mrf_mpre;     // labels in lower mask words
@@ -186,8 +186,6 @@ struct b2tex_ctx {
     b2::DevBuf<uint32_t> mrf_sort;     // radix sort keys/values of the level bucketing
     b2tex_mrf_params mrf_params{};
     bool mrf_ready = false;
-    void *mrf_graph_exec = nullptr;    // cudaGraphExec_t of one iteration
-    uint32_t mrf_graph_rounds = 0;
     int mrf_group = 32;
 
     // seam

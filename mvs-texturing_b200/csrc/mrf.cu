@@ -24,6 +24,8 @@
 #include <cub/cub.cuh>
 #include <stdlib.h>
 
+#include <memory>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -232,7 +234,7 @@ __device__ __forceinline__ uint32_t count_in_forest(const Mrf &m, uint32_t v, ui
 __global__ void __launch_bounds__(1024, 1) k_forest(Mrf m, int do_bucket)
 {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ uint32_t sm[];  // [rounds+1] counts, [rounds+1] bases
+    extern __shared__ uint32_t sm[];  // [rounds+1] level counts
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const uint32_t seed_t = iter_seed(m.seed, m.iter);
     unsigned long long *maxprio = reinterpret_cast<unsigned long long *>(m.ctl + CTL_MAXPRIO);
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(1024, 1) k_forest(Mrf m, int do_bucket)
     if (!do_bucket) return;
 
     // ---- bucket the forest nodes by level: deepest level first, levels padded to 32 entries ----
-    uint32_t *cnt = sm, *base = sm + (m.rounds + 1);
+    uint32_t *cnt = sm;
     for (uint32_t i = threadIdx.x; i <= m.rounds; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
     for (uint32_t v = m.nb + tid; v < m.ne; v += nth) {
@@ -356,7 +358,6 @@ __global__ void __launch_bounds__(1024, 1) k_forest(Mrf m, int do_bucket)
     // sort keys: a stable radix sort by (rounds - level) keeps node ids ascending inside a level, so
     // that consecutive order entries touch neighbouring rows of every per-node array (the sweeps are
     // bound by scattered DRAM sectors, not by arithmetic)
-    (void)base;
     for (uint32_t v = m.nb + tid; v < m.ne; v += nth) {
         uint32_t l = m.level[v];
         m.sort_key_in[v - m.nb] = l <= m.rounds ? m.rounds - l : m.rounds + 1u;
@@ -586,8 +587,8 @@ Mrf make_mrf(b2tex_ctx *c, uint32_t iter)
     m.adj4 = c->mrf_adj4.p;
     m.ptr = c->dc_ptr.p; m.view = c->dc_view.p; m.cost = c->dc_cost.p;
     m.H = c->mrf_H.p; m.hminp1 = c->mrf_hminp1.p; m.amin = c->mrf_amin.p; m.level = c->mrf_level.p;
-    m.labels = c->labels.p; m.order = c->mrf_order.p; m.ctl = c->mrf_cursor.p;
-    m.flag_up = c->mrf_lvlptr.p; m.flag_dn = c->mrf_lvlptr.p + c->F;
+    m.labels = c->labels.p; m.order = c->mrf_order.p; m.ctl = c->mrf_ctl.p;
+    m.flag_up = c->mrf_flags.p; m.flag_dn = c->mrf_flags.p + c->F;
     m.queue = c->mrf_queue.p; m.qstamp = c->mrf_queue.p + 2 * (size_t)c->F;
     m.sort_key_in = c->mrf_sort.p; m.sort_key_out = c->mrf_sort.p + c->F;
     m.sort_val_in = c->mrf_sort.p + 2 * (size_t)c->F; m.sort_val_out = c->mrf_sort.p + 3 * (size_t)c->F;
@@ -619,7 +620,7 @@ int coop_grid(b2tex_ctx *c, K kernel, size_t smem, int *grid, int threads = 256)
 int launch_forest(b2tex_ctx *c, Mrf &m, int do_bucket)
 {
     cudaStream_t s = c->stream;
-    size_t sh = 2 * (size_t)(m.rounds + 1) * sizeof(uint32_t);
+    size_t sh = (size_t)(m.rounds + 1) * sizeof(uint32_t);
     int grid = 0;
     // few fat blocks: the cost of grid.sync() grows with the number of blocks
     B2_TRY(coop_grid(c, k_forest, sh, &grid, 1024));
@@ -666,14 +667,14 @@ int enqueue_iteration(b2tex_ctx *c, Mrf &m)
         ScopedTimer tf(c, "mrf.k_forest+sort", 20.0 * (double)(m.ne - m.nb));
         B2_TRY(launch_forest(c, m, 1));
     }
-    ScopedTimer *tu = new ScopedTimer(c, "mrf.k_up", 14.0 * (double)c->nnz);
+    std::unique_ptr<ScopedTimer> tu(new ScopedTimer(c, "mrf.k_up", 14.0 * (double)c->nnz));
     switch (c->mrf_group) {
         case 4: B2_TRY(launch_up<4>(c, m)); break;
         case 8: B2_TRY(launch_up<8>(c, m)); break;
         case 16: B2_TRY(launch_up<16>(c, m)); break;
         default: B2_TRY(launch_up<32>(c, m)); break;
     }
-    delete tu;
+    tu.reset();
     static const bool repeat_up = getenv("B2TEX_MRF_REPEAT_UP") != nullptr;
     if (repeat_up) {  // experiment: second sweep finds every flag already set (no dataflow waits)
         ScopedTimer tu2(c, "mrf.k_up(again)");
@@ -713,9 +714,9 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
     B2_TRY(c->mrf_sort.alloc(4 * F));    // sort keys/values in/out
     B2_TRY(c->mrf_queue.alloc(3 * F));   // frontier lists [2][F] | qstamp [F]
     B2_TRY(c->mrf_queue.zero(c->stream));
-    B2_TRY(c->mrf_lvlptr.alloc(2 * F));  // flag_up | flag_dn
-    B2_TRY(c->mrf_lvlptr.zero(c->stream));
-    B2_TRY(c->mrf_cursor.alloc(CTL_WORDS));
+    B2_TRY(c->mrf_flags.alloc(2 * F));  // flag_up | flag_dn (iteration stamps)
+    B2_TRY(c->mrf_flags.zero(c->stream));
+    B2_TRY(c->mrf_ctl.alloc(CTL_WORDS));
     B2_TRY(c->mrf_energy.alloc(4));
     B2_TRY(c->mrf_adj4.alloc(F));
     if (F) k_build_adj4<<<(unsigned)((F + 255) / 256), 256, 0, c->stream>>>((uint32_t)F, c->adj_ptr.p, c->adj_idx.p, c->mrf_adj4.p);

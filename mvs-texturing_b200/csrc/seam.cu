@@ -13,6 +13,8 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
+#include <memory>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -417,7 +419,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
     // only the camera block and the rgb images are needed here (no gradient image)
     B2_TRY(prepare_images(c, c->prepared_data_term >= 0 ? c->prepared_data_term : 0));
     const uint32_t Vn = c->Vn;
-    ScopedTimer *tm_asm = new ScopedTimer(c, "seam_assembly");
+    std::unique_ptr<ScopedTimer> tm_asm(new ScopedTimer(c, "seam_assembly"));
     DevBuf<uint32_t> &cnt = c->s_cnt32, &row_vertex = c->s_row_vertex;
     B2_TRY(cnt.alloc((size_t)Vn + 1));
     B2_TRY(cnt.zero(s));
@@ -491,7 +493,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
     info->cg_launch_iterations = 0;
     info->cg_ms = 0.0f;
 
-    delete tm_asm;
+    tm_asm.reset();
     B2_TRY(c->seam_status.alloc(16));
     B2_TRY(c->seam_status.zero(s));
     if (R) {
