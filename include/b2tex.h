@@ -48,7 +48,7 @@ typedef struct {
 /* the fields of tex::Settings the path reads (libs/tex/settings.h:82-94) */
 typedef struct {
     int32_t data_term;                 /* 0 DATA_TERM_AREA, 1 DATA_TERM_GMI */
-    int32_t outlier_removal;           /* 0 NONE (others: B2TEX_ERR_UNSUPPORTED) */
+    int32_t outlier_removal;           /* 0 NONE, 1 GAUSS_DAMPING, 2 GAUSS_CLAMPING (settings.h:70-74) */
     int32_t geometric_visibility_test; /* bool */
 } b2tex_settings;
 

@@ -204,8 +204,8 @@ class Context:
         return out
 
     # ---- stages ----
-    def data_costs_run(self, data_term=1, visibility=True):
-        st = B2Settings(data_term, 0, 1 if visibility else 0)
+    def data_costs_run(self, data_term=1, visibility=True, outlier_removal=0):
+        st = B2Settings(data_term, outlier_removal, 1 if visibility else 0)
         info = B2DcInfo()
         _check(lib().b2tex_data_costs_run(self._h, C.byref(st), C.byref(info)))
         return info
@@ -304,7 +304,7 @@ class Context:
 class Settings:
     """tex::Settings (libs/tex/settings.h:82-94), the fields this path reads."""
     DATA_TERM_AREA, DATA_TERM_GMI = 0, 1
-    OUTLIER_REMOVAL_NONE = 0
+    OUTLIER_REMOVAL_NONE, OUTLIER_REMOVAL_GAUSS_DAMPING, OUTLIER_REMOVAL_GAUSS_CLAMPING = 0, 1, 2
 
     def __init__(self, data_term=1, outlier_removal=0, geometric_visibility_test=True):
         self.data_term = data_term

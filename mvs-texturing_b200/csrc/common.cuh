@@ -162,7 +162,8 @@ struct b2tex_ctx {
     b2::DevBuf<uint64_t> cand_ptr;     // F+1
     b2::DevBuf<uint16_t> cand_view;
     b2::DevBuf<uint32_t> cand_face;
-    b2::DevBuf<float> cand_q;
+    b2::DevBuf<float> cand_q, cand_ycc;   // cand_ycc: mean YCbCr per candidate (outlier removal only)
+    b2::DevBuf<uint8_t> cand_flag;
     b2::DevBuf<uint32_t> need_bits, occ_bits;
     b2::DevBuf<uint32_t> hist;         // 10000 bins
     b2::DevBuf<uint32_t> scalars;      // misc device scalars

@@ -247,7 +247,22 @@ __device__ __forceinline__ uint8_t linear_at_u8(const uint8_t *__restrict__ img,
 }
 
 // texture_view.cpp:134-251 for outlier_removal == NONE
-__device__ float face_quality(const ViewDev &V, Px p1, Px p2, Px p3, int data_term)
+// mve::Image<uint8_t>::linear_at on one channel of the interleaved rgb image
+__device__ __forceinline__ uint8_t linear_at_rgb(const uint8_t *__restrict__ img, int w, int h, float x, float y, int ch)
+{
+    x = fmaxf(0.0f, fminf((float)(w - 1), x));
+    y = fmaxf(0.0f, fminf((float)(h - 1), y));
+    int fx = (int)x, fy = (int)y;
+    int fx1 = min(fx + 1, w - 1), fy1 = min(fy + 1, h - 1);
+    float w1 = x - (float)fx, w0 = 1.0f - w1;
+    float w3 = y - (float)fy, w2 = 1.0f - w3;
+    float r = (float)img[3 * (fx + (size_t)fy * w) + ch] * (w0 * w2) + (float)img[3 * (fx1 + (size_t)fy * w) + ch] * (w1 * w2)
+        + (float)img[3 * (fx + (size_t)fy1 * w) + ch] * (w0 * w3) + (float)img[3 * (fx1 + (size_t)fy1 * w) + ch] * (w1 * w3) + 0.5f;
+    return (uint8_t)r;
+}
+
+// mean_color != nullptr <=> outlier removal on: colours are sampled even for DATA_TERM_AREA (:159)
+__device__ float face_quality(const ViewDev &V, Px p1, Px p2, Px p3, int data_term, float *mean_color)
 {
     Tri2 t;
     t.v1x = p1.x; t.v1y = p1.y; t.v2x = p2.x; t.v2y = p2.y; t.v3x = p3.x; t.v3y = p3.y;
@@ -263,10 +278,11 @@ __device__ float face_quality(const ViewDev &V, Px p1, Px p2, Px p3, int data_te
         area = 0.5f * fabsf(u0 * v1 - u1 * v0);
     }
     if (area < 1.1920928955078125e-07f) return 0.0f;  // FLT_EPSILON :150
-    if (data_term != 1) return area;                  // DATA_TERM_AREA, no sampling (:159,:248)
+    if (data_term != 1 && !mean_color) return area;   // DATA_TERM_AREA, no sampling (:159,:248)
 
     unsigned long long num_samples = 0;
     double gmi = 0.0;
+    double colors[3] = {0.0, 0.0, 0.0};
     const uint8_t *__restrict__ grad = V.grad;
     const int w = V.w;
     if (area > 0.5f) {
@@ -305,11 +321,28 @@ __device__ float face_quality(const ViewDev &V, Px p1, Px p2, Px p3, int data_te
                 const float cx = (float)x + 0.5f;
                 const float cy = (float)y + 0.5f;
                 if (!fast && !tri_inside(t, cx, cy)) continue;
-                gmi += (double)grad[(size_t)x + (size_t)y * w] / 255.0;
+                if (mean_color) {  // :207-212
+                    const uint8_t *px = V.rgb + 3 * ((size_t)x + (size_t)y * w);
+                    colors[0] += (double)px[0] / 255.0; colors[1] += (double)px[1] / 255.0; colors[2] += (double)px[2] / 255.0;
+                }
+                if (data_term == 1) gmi += (double)grad[(size_t)x + (size_t)y * w] / 255.0;
                 ++num_samples;
             }
         }
     }
+    if (mean_color) {  // :233-245
+        if (num_samples > 0) {
+            for (int i = 0; i < 3; ++i) mean_color[i] = (float)(colors[i] / (double)num_samples);
+        } else {
+            for (int i = 0; i < 3; ++i) {
+                double c1 = (double)linear_at_rgb(V.rgb, V.w, V.h, p1.x, p1.y, i) / 255.0;
+                double c2 = (double)linear_at_rgb(V.rgb, V.w, V.h, p2.x, p2.y, i) / 255.0;
+                double c3 = (double)linear_at_rgb(V.rgb, V.w, V.h, p3.x, p3.y, i) / 255.0;
+                mean_color[i] = (float)((c1 + c2 + c3) / 3.0);
+            }
+        }
+    }
+    if (data_term != 1) return area;
     if (num_samples > 0) {
         gmi = (gmi / (double)num_samples) * (double)area;
     } else {
@@ -327,7 +360,8 @@ __global__ void __launch_bounds__(256) k_quality(const float *__restrict__ verts
                                                  const uint32_t *__restrict__ cand_face, uint64_t num_cand,
                                                  const uint32_t *__restrict__ occ_bits, uint32_t vwords,
                                                  const uint32_t *__restrict__ vrank,
-                                                 int data_term, float *cand_q, uint32_t *max_q_bits)
+                                                 int data_term, float *cand_q, uint32_t *max_q_bits,
+                                                 float *cand_ycc /* [ncand][3] or null */)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float q = 0.0f;
@@ -348,12 +382,131 @@ __global__ void __launch_bounds__(256) k_quality(const float *__restrict__ verts
         if (visible) {
             const ViewDev &V = views[j];
             Px p1 = pixel_coords(V, g.v[0]), p2 = pixel_coords(V, g.v[1]), p3 = pixel_coords(V, g.v[2]);
-            q = face_quality(V, p1, p2, p3, data_term);
+            float mc[3] = {0.0f, 0.0f, 0.0f};
+            q = face_quality(V, p1, p2, p3, data_term, cand_ycc ? mc : nullptr);
+            if (cand_ycc) {  // mve::image::color_rgb_to_ycbcr<float> (:225)
+                cand_ycc[3 * i + 0] = (mc[0] * 0.299f + mc[1] * 0.587f) + mc[2] * 0.114f;
+                cand_ycc[3 * i + 1] = ((mc[0] * -0.168736f + mc[1] * -0.331264f) + mc[2] * 0.5f) + 0.5f;
+                cand_ycc[3 * i + 2] = ((mc[0] * 0.5f + mc[1] * -0.418688f) + mc[2] * -0.081312f) + 0.5f;
+            }
         }
         cand_q[i] = q;
     }
     // qualities are >= 0 (or NaN, which the reference's std::max also ignores): uint order == float order
     uint32_t qb = (q == q) ? __float_as_uint(q) : 0u;
+    for (int s = 16; s; s >>= 1) qb = max(qb, __shfl_xor_sync(0xffffffffu, qb, s));
+    if ((threadIdx.x & 31) == 0 && qb && !cand_ycc) atomicMax(max_q_bits, qb);  // with outlier removal the
+}                                                                             // maximum is taken afterwards
+
+// ---- photometric outlier detection (calculate_data_costs.cpp:35-129), one thread per face ------------
+// Restates oracle/datacosts.c photometric_outlier_detection operation by operation (fp64, no FMA):
+// sequential mean / covariance sums over the face's infos in ascending view order, FullPivLU<3x3>
+// inverse (full pivoting, rank threshold eps*3*|max pivot|), exp((-0.5 d) Cinv d^T).
+__device__ bool lu3_inverse(const double *A, double *inv)
+{
+    double lu[9];
+    for (int i = 0; i < 9; ++i) lu[i] = A[i];
+    int rt[3], ct[3];
+    double maxpivot = 0.0;
+    int nonzero = 3;
+    for (int k = 0; k < 3; ++k) {
+        int br = k, bc = k;
+        double biggest = -1.0;
+        for (int cc = k; cc < 3; ++cc)
+            for (int rr = k; rr < 3; ++rr) {
+                double a = fabs(lu[rr * 3 + cc]);
+                if (a > biggest) { biggest = a; br = rr; bc = cc; }
+            }
+        if (biggest == 0.0) { nonzero = k; for (int i = k; i < 3; ++i) { rt[i] = i; ct[i] = i; } break; }
+        if (biggest > maxpivot) maxpivot = biggest;
+        rt[k] = br; ct[k] = bc;
+        if (br != k) for (int cc = 0; cc < 3; ++cc) { double t = lu[k * 3 + cc]; lu[k * 3 + cc] = lu[br * 3 + cc]; lu[br * 3 + cc] = t; }
+        if (bc != k) for (int rr = 0; rr < 3; ++rr) { double t = lu[rr * 3 + k]; lu[rr * 3 + k] = lu[rr * 3 + bc]; lu[rr * 3 + bc] = t; }
+        for (int rr = k + 1; rr < 3; ++rr) lu[rr * 3 + k] = lu[rr * 3 + k] / lu[k * 3 + k];
+        for (int rr = k + 1; rr < 3; ++rr)
+            for (int cc = k + 1; cc < 3; ++cc) lu[rr * 3 + cc] = lu[rr * 3 + cc] - lu[rr * 3 + k] * lu[k * 3 + cc];
+    }
+    int rank = 0;
+    const double thr = maxpivot * (2.220446049250313e-16 * 3.0);
+    for (int i = 0; i < nonzero; ++i) if (fabs(lu[i * 3 + i]) > thr) ++rank;
+    if (rank != 3) return false;
+    for (int col = 0; col < 3; ++col) {
+        double c[3] = {0.0, 0.0, 0.0};
+        c[col] = 1.0;
+        for (int k = 0; k < 3; ++k) if (rt[k] != k) { double t = c[k]; c[k] = c[rt[k]]; c[rt[k]] = t; }
+        for (int i = 1; i < 3; ++i) for (int j = 0; j < i; ++j) c[i] = c[i] - lu[i * 3 + j] * c[j];
+        for (int i = 2; i >= 0; --i) {
+            for (int j = i + 1; j < 3; ++j) c[i] = c[i] - lu[i * 3 + j] * c[j];
+            c[i] = c[i] / lu[i * 3 + i];
+        }
+        for (int k = 2; k >= 0; --k) if (ct[k] != k) { double t = c[k]; c[k] = c[ct[k]]; c[ct[k]] = t; }
+        for (int i = 0; i < 3; ++i) inv[i * 3 + col] = c[i];
+    }
+    return true;
+}
+
+__device__ __forceinline__ double gauss3(const float *x, const double *mu, const double *ci)
+{
+    double d[3], t[3], r[3];
+    for (int i = 0; i < 3; ++i) { d[i] = (double)x[i] - mu[i]; t[i] = -0.5 * d[i]; }
+    for (int j = 0; j < 3; ++j) r[j] = (t[0] * ci[0 * 3 + j] + t[1] * ci[1 * 3 + j]) + t[2] * ci[2 * 3 + j];
+    return exp((r[0] * d[0] + r[1] * d[1]) + r[2] * d[2]);
+}
+
+__global__ void __launch_bounds__(128) k_outlier(const uint64_t *__restrict__ cand_ptr, float *cand_q,
+                                                 const float *__restrict__ cand_ycc, uint8_t *flag,
+                                                 uint32_t face_begin, uint32_t face_end, int mode,
+                                                 uint32_t *max_q_bits)
+{
+    const uint32_t f = face_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    float qmax = 0.0f;
+    if (f < face_end) {
+        const uint64_t a = cand_ptr[f], b = cand_ptr[f + 1];
+        // infos of this face = candidates with quality != 0 (:222), ascending view order
+        uint32_t n = 0;
+        for (uint64_t i = a; i < b; ++i) { const bool in = cand_q[i] != 0.0f; flag[i] = in ? 1 : 2; n += in; }  // 2 = not an info
+        const double gauss_rejection_threshold = 6e-3, minimal_covariance = 5e-4;
+        const double factor = mode == 2 ? 1.0 : (double)0.2f;
+        bool done = n == 0;
+        uint32_t rows = n;
+        double mean[3], cov[9], cinv[9];
+        for (int it = 0; it < 10 && !done; ++it) {
+            if (rows < 4u) { done = true; break; }
+            for (int i = 0; i < 3; ++i) mean[i] = 0.0;
+            for (uint64_t i = a; i < b; ++i) if (flag[i] == 1) for (int k = 0; k < 3; ++k) mean[k] += (double)cand_ycc[3 * i + k];
+            for (int i = 0; i < 3; ++i) mean[i] = mean[i] / (double)rows;
+            for (int i = 0; i < 9; ++i) cov[i] = 0.0;
+            for (uint64_t i = a; i < b; ++i) if (flag[i] == 1) {
+                double c[3];
+                for (int k = 0; k < 3; ++k) c[k] = (double)cand_ycc[3 * i + k] - mean[k];
+                for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) cov[k * 3 + j] += c[k] * c[j];
+            }
+            double maxabs = 0.0;
+            for (int i = 0; i < 9; ++i) { cov[i] = cov[i] / (double)(rows - 1); if (fabs(cov[i]) > maxabs) maxabs = fabs(cov[i]); }
+            if (maxabs < minimal_covariance) {
+                for (uint64_t i = a; i < b; ++i) if (flag[i] == 0) cand_q[i] = 0.0f;
+                done = true;
+                break;
+            }
+            if (!lu3_inverse(cov, cinv)) { done = true; break; }
+            rows = 0;
+            for (uint64_t i = a; i < b; ++i) if (flag[i] != 2) {
+                const uint8_t in = gauss3(cand_ycc + 3 * i, mean, cinv) >= gauss_rejection_threshold ? 1 : 0;
+                flag[i] = in;
+                rows += in;
+            }
+        }
+        if (!done) {
+            for (int i = 0; i < 9; ++i) cinv[i] = cinv[i] * factor;
+            for (uint64_t i = a; i < b; ++i) if (flag[i] != 2) {
+                const double g = gauss3(cand_ycc + 3 * i, mean, cinv);
+                if (mode == 1) cand_q[i] = (float)((double)cand_q[i] * g);
+                else if (g < gauss_rejection_threshold) cand_q[i] = 0.0f;
+            }
+        }
+        for (uint64_t i = a; i < b; ++i) { const float q = cand_q[i]; if (q == q) qmax = fmaxf(qmax, q); }
+    }
+    uint32_t qb = __float_as_uint(qmax);
     for (int s = 16; s; s >>= 1) qb = max(qb, __shfl_xor_sync(0xffffffffu, qb, s));
     if ((threadIdx.x & 31) == 0 && qb) atomicMax(max_q_bits, qb);
 }
@@ -435,7 +588,8 @@ float cos75_threshold()
 int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *info)
 {
     if (!c->F || !c->K) { set_error("data costs: mesh and views must be set first"); return B2TEX_ERR_ARG; }
-    if (st->outlier_removal != 0) { set_error("outlier removal is not implemented"); return B2TEX_ERR_UNSUPPORTED; }
+    if (st->outlier_removal < 0 || st->outlier_removal > 2) { set_error("unknown outlier removal mode"); return B2TEX_ERR_UNSUPPORTED; }
+    const bool outlier = st->outlier_removal != 0;
     if (c->K > 65535u) { set_error("Exeeded maximal number of views"); return B2TEX_ERR_LIMITS; }
     cudaStream_t s = c->stream;
     // image preparation and the BVH are part of the stage in the reference
@@ -474,6 +628,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     B2_TRY(c->cand_view.alloc(num_cand));
     B2_TRY(c->cand_face.alloc(num_cand));
     B2_TRY(c->cand_q.alloc(num_cand));
+    if (outlier) { B2_TRY(c->cand_ycc.alloc(3 * num_cand)); B2_TRY(c->cand_flag.alloc(num_cand)); }
     if (vis) {
         B2_TRY(c->need_bits.alloc((size_t)K * vwords));
         B2_TRY(c->occ_bits.alloc((size_t)K * vwords));
@@ -502,7 +657,14 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
         k_quality<<<(unsigned)qblocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->views_dev.p, c->cand_view.p,
                                                     c->cand_face.p, num_cand, vis ? c->occ_bits.p : nullptr, vwords,
                                                     c->vrank.p,
-                                                    st->data_term, c->cand_q.p, c->scalars.p);
+                                                    st->data_term, c->cand_q.p, c->scalars.p,
+                                                    outlier ? c->cand_ycc.p : nullptr);
+        B2_KERNEL_CHECK();
+    }
+    if (outlier && nf) {
+        ScopedTimer tm(c, "k_outlier", 16.0 * (double)num_cand);
+        k_outlier<<<(nf + 127) / 128, 128, 0, s>>>(c->cand_ptr.p, c->cand_q.p, c->cand_ycc.p, c->cand_flag.p, fb, fe,
+                                                   st->outlier_removal, c->scalars.p);
         B2_KERNEL_CHECK();
     }
     {

@@ -106,9 +106,26 @@ static uint8_t linear_at_u8(const uint8_t *img, int w, int h, float x, float y)
     return (uint8_t)r;
 }
 
-/* texture_view.cpp:134-251 (GMI / AREA, outlier removal NONE) on already projected points */
+/* mve::Image<uint8_t>::linear_at on one channel of the interleaved rgb image [UPSTREAM-RECALL] */
+static uint8_t linear_at_rgb(const uint8_t *img, int w, int h, float x, float y, int ch)
+{
+    x = fmaxf(0.0f, fminf((float)(w - 1), x));
+    y = fmaxf(0.0f, fminf((float)(h - 1), y));
+    int fx = (int)x, fy = (int)y;
+    int fx1 = fx + 1 < w - 1 ? fx + 1 : w - 1;
+    int fy1 = fy + 1 < h - 1 ? fy + 1 : h - 1;
+    float w1 = x - (float)fx, w0 = 1.0f - w1;
+    float w3 = y - (float)fy, w2 = 1.0f - w3;
+    float r = (float)img[3 * (fx + (size_t)fy * w) + ch] * (w0 * w2) + (float)img[3 * (fx1 + (size_t)fy * w) + ch] * (w1 * w2)
+        + (float)img[3 * (fx + (size_t)fy1 * w) + ch] * (w0 * w3) + (float)img[3 * (fx1 + (size_t)fy1 * w) + ch] * (w1 * w3)
+        + 0.5f;
+    return (uint8_t)r;
+}
+
+/* texture_view.cpp:134-251 on already projected points; mean_color != NULL <=> outlier removal on
+ * (colours are then sampled even for DATA_TERM_AREA, :159) */
 static float face_quality_px(const orc_view *v, const uint8_t *grad, float p1[2], float p2[2],
-                             float p3[2], int data_term)
+                             float p3[2], int data_term, float *mean_color)
 {
     tri2 tri;
     tri_init(&tri, p1, p2, p3);
@@ -117,7 +134,8 @@ static float face_quality_px(const orc_view *v, const uint8_t *grad, float p1[2]
 
     size_t num_samples = 0;
     double gmi = 0.0;
-    int sampling_necessary = data_term != 0;
+    double colors[3] = {0.0, 0.0, 0.0};
+    int sampling_necessary = data_term != 0 || mean_color != NULL;
     int w = v->width;
 
     if (sampling_necessary && area > 0.5f) {
@@ -158,12 +176,26 @@ static float face_quality_px(const orc_view *v, const uint8_t *grad, float p1[2]
                 float cx = (float)x + 0.5f;
                 float cy = (float)y + 0.5f;
                 if (!fast && !tri_inside(&tri, cx, cy)) continue;
+                if (mean_color) /* :207-212 */
+                    for (int i = 0; i < 3; ++i) colors[i] += (double)v->rgb[3 * (x + (size_t)y * w) + i] / 255.0;
                 if (data_term == 1) gmi += (double)grad[x + (size_t)y * w] / 255.0;
                 ++num_samples;
             }
         }
     }
 
+    if (mean_color) { /* :233-245 */
+        if (num_samples > 0) {
+            for (int i = 0; i < 3; ++i) mean_color[i] = (float)(colors[i] / (double)num_samples);
+        } else {
+            for (int i = 0; i < 3; ++i) {
+                double c1 = (double)linear_at_rgb(v->rgb, v->width, v->height, p1[0], p1[1], i) / 255.0;
+                double c2 = (double)linear_at_rgb(v->rgb, v->width, v->height, p2[0], p2[1], i) / 255.0;
+                double c3 = (double)linear_at_rgb(v->rgb, v->width, v->height, p3[0], p3[1], i) / 255.0;
+                mean_color[i] = (float)((c1 + c2 + c3) / 3.0);
+            }
+        }
+    }
     if (data_term == 1) {
         if (num_samples > 0) {
             gmi = (gmi / (double)num_samples) * (double)area;
@@ -185,7 +217,7 @@ float orc_face_quality(const orc_view *v, const uint8_t *grad, const float v1[3]
     orc_pixel_coords(v, v1, p1);
     orc_pixel_coords(v, v2, p2);
     orc_pixel_coords(v, v3, p3);
-    return face_quality_px(v, grad, p1, p2, p3, data_term);
+    return face_quality_px(v, grad, p1, p2, p3, data_term, NULL);
 }
 
 static inline float norm3(const float a[3]) { return sqrtf(((0.0f + a[0] * a[0]) + a[1] * a[1]) + a[2] * a[2]); }
@@ -217,10 +249,112 @@ float orc_histogram_percentile(const float *values, uint64_t n, float vmax, int 
     return result;
 }
 
-typedef struct { uint32_t face; float q; } fq;
+/* ---- photometric outlier detection, calculate_data_costs.cpp:35-129 ------------------------------
+ * Eigen pieces restated [UPSTREAM-RECALL]: colwise().mean(), (C^T C)/(n-1) with sequential sums,
+ * FullPivLU<Matrix3d> (full pivoting, rank threshold eps*3*|max pivot|, inverse by P/L/U/Q solves),
+ * multi_gauss_unnormalized (util.h:60-66) = exp((-0.5*d) * Cinv * d^T), evaluated left to right.
+ * Per-face infos are processed in ascending view order (the reference's order depends on the OpenMP
+ * merge, calculate_data_costs.cpp:241-249, i.e. is not deterministic there). */
+static int lu3_inverse(const double A[9], double inv[9])
+{
+    double lu[9];
+    memcpy(lu, A, sizeof(lu));
+    int rt[3], ct[3];
+    double maxpivot = 0.0;
+    int nonzero = 3;
+    for (int k = 0; k < 3; ++k) {
+        int br = k, bc = k;
+        double biggest = -1.0;
+        for (int cc = k; cc < 3; ++cc)      /* column-major visiting order, first strict maximum */
+            for (int rr = k; rr < 3; ++rr) {
+                double a = fabs(lu[rr * 3 + cc]);
+                if (a > biggest) { biggest = a; br = rr; bc = cc; }
+            }
+        if (biggest == 0.0) { nonzero = k; for (int i = k; i < 3; ++i) { rt[i] = i; ct[i] = i; } break; }
+        if (biggest > maxpivot) maxpivot = biggest;
+        rt[k] = br; ct[k] = bc;
+        if (br != k) for (int cc = 0; cc < 3; ++cc) { double t = lu[k * 3 + cc]; lu[k * 3 + cc] = lu[br * 3 + cc]; lu[br * 3 + cc] = t; }
+        if (bc != k) for (int rr = 0; rr < 3; ++rr) { double t = lu[rr * 3 + k]; lu[rr * 3 + k] = lu[rr * 3 + bc]; lu[rr * 3 + bc] = t; }
+        for (int rr = k + 1; rr < 3; ++rr) lu[rr * 3 + k] = lu[rr * 3 + k] / lu[k * 3 + k];
+        for (int rr = k + 1; rr < 3; ++rr)
+            for (int cc = k + 1; cc < 3; ++cc) lu[rr * 3 + cc] = lu[rr * 3 + cc] - lu[rr * 3 + k] * lu[k * 3 + cc];
+    }
+    int rank = 0;
+    double thr = maxpivot * (2.220446049250313e-16 * 3.0);
+    for (int i = 0; i < nonzero; ++i) if (fabs(lu[i * 3 + i]) > thr) ++rank;
+    if (rank != 3) return 0;
+    /* inverse = solve(Identity): c = P*I; L c = ..; U c = ..; result = Q c */
+    for (int col = 0; col < 3; ++col) {
+        double c[3] = {0.0, 0.0, 0.0};
+        c[col] = 1.0;
+        for (int k = 0; k < 3; ++k) if (rt[k] != k) { double t = c[k]; c[k] = c[rt[k]]; c[rt[k]] = t; }
+        for (int i = 1; i < 3; ++i) for (int j = 0; j < i; ++j) c[i] = c[i] - lu[i * 3 + j] * c[j];
+        for (int i = 2; i >= 0; --i) {
+            for (int j = i + 1; j < 3; ++j) c[i] = c[i] - lu[i * 3 + j] * c[j];
+            c[i] = c[i] / lu[i * 3 + i];
+        }
+        for (int k = 2; k >= 0; --k) if (ct[k] != k) { double t = c[k]; c[k] = c[ct[k]]; c[ct[k]] = t; }
+        for (int i = 0; i < 3; ++i) inv[i * 3 + col] = c[i];
+    }
+    return 1;
+}
+
+static double gauss3(const float x[3], const double mu[3], const double ci[9])
+{
+    double d[3], t[3], r[3];
+    for (int i = 0; i < 3; ++i) { d[i] = (double)x[i] - mu[i]; t[i] = -0.5 * d[i]; }
+    for (int j = 0; j < 3; ++j) r[j] = (t[0] * ci[0 * 3 + j] + t[1] * ci[1 * 3 + j]) + t[2] * ci[2 * 3 + j];
+    return exp((r[0] * d[0] + r[1] * d[1]) + r[2] * d[2]);
+}
+
+/* returns like the reference's bool; q and ycc hold the n infos of one face */
+static int photometric_outlier_detection(float *q, const float *ycc, uint32_t n, int mode, uint8_t *is_inlier)
+{
+    if (n == 0) return 1;
+    const double gauss_rejection_threshold = 6e-3, minimal_covariance = 5e-4;
+    const int iterations = 10, minimal_num_inliers = 4;
+    double factor = mode == 2 ? 1.0 : 0.2; /* (float)0.2f in the reference: outlier_removal_factor is float */
+    if (mode == 1) factor = (double)0.2f;
+    for (uint32_t r = 0; r < n; ++r) is_inlier[r] = 1;
+    uint32_t rows = n;
+    double mean[3], cov[9], cinv[9];
+    for (int it = 0; it < iterations; ++it) {
+        if (rows < (uint32_t)minimal_num_inliers) return 0;
+        for (int i = 0; i < 3; ++i) mean[i] = 0.0;
+        for (uint32_t r = 0; r < n; ++r) if (is_inlier[r]) for (int i = 0; i < 3; ++i) mean[i] += (double)ycc[3 * r + i];
+        for (int i = 0; i < 3; ++i) mean[i] = mean[i] / (double)rows;
+        for (int i = 0; i < 9; ++i) cov[i] = 0.0;
+        for (uint32_t r = 0; r < n; ++r) if (is_inlier[r]) {
+            double c[3];
+            for (int i = 0; i < 3; ++i) c[i] = (double)ycc[3 * r + i] - mean[i];
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) cov[i * 3 + j] += c[i] * c[j];
+        }
+        double maxabs = 0.0;
+        for (int i = 0; i < 9; ++i) { cov[i] = cov[i] / (double)(rows - 1); if (fabs(cov[i]) > maxabs) maxabs = fabs(cov[i]); }
+        if (maxabs < minimal_covariance) {
+            for (uint32_t r = 0; r < n; ++r) if (!is_inlier[r]) q[r] = 0.0f;
+            return 1;
+        }
+        if (!lu3_inverse(cov, cinv)) return 0;
+        rows = 0;
+        for (uint32_t r = 0; r < n; ++r) {
+            is_inlier[r] = gauss3(ycc + 3 * r, mean, cinv) >= gauss_rejection_threshold ? 1 : 0;
+            rows += is_inlier[r];
+        }
+    }
+    for (int i = 0; i < 9; ++i) cinv[i] = cinv[i] * factor;
+    for (uint32_t r = 0; r < n; ++r) {
+        double g = gauss3(ycc + 3 * r, mean, cinv);
+        if (mode == 1) q[r] = (float)((double)q[r] * g);           /* info.quality *= gauss_value */
+        else if (g < gauss_rejection_threshold) q[r] = 0.0f;
+    }
+    return 1;
+}
+
+typedef struct { uint32_t face; float q; float ycc[3]; } fq;
 typedef struct { fq *data; size_t n, cap; } fqvec;
 
-static void fq_push(fqvec *v, uint32_t f, float q)
+static void fq_push(fqvec *v, uint32_t f, float q, const float *ycc)
 {
     if (v->n == v->cap) {
         v->cap = v->cap ? v->cap * 2 : 1024;
@@ -228,6 +362,7 @@ static void fq_push(fqvec *v, uint32_t f, float q)
     }
     v->data[v->n].face = f;
     v->data[v->n].q = q;
+    for (int i = 0; i < 3; ++i) v->data[v->n].ycc[i] = ycc ? ycc[i] : 0.0f;
     v->n++;
 }
 
@@ -240,7 +375,8 @@ int orc_data_costs(const float *verts, uint32_t num_verts, const uint32_t *faces
     (void)num_verts;
     /* calculate_data_costs.cpp:315-318 */
     if (num_views > 65535u) return 2;
-    if (settings->outlier_removal != 0) return 3; /* not restated (off by default, settings.h:87) */
+    if (settings->outlier_removal < 0 || settings->outlier_removal > 2) return 3;
+    const int outlier = settings->outlier_removal;
 
     orc_bvh *bvh = orc_bvh_build(verts, faces, num_faces); /* :144 */
     fqvec *per_view = (fqvec *)calloc(num_views ? num_views : 1, sizeof(fqvec));
@@ -305,9 +441,14 @@ int orc_data_costs(const float *verts, uint32_t num_verts, const uint32_t *faces
                 }
                 if (!visible) continue;
             }
-            float q = face_quality_px(tv, grad, p1, p2, p3, settings->data_term); /* :220 */
+            float mc[3] = {0.0f, 0.0f, 0.0f}, ycc[3];
+            float q = face_quality_px(tv, grad, p1, p2, p3, settings->data_term, outlier ? mc : NULL); /* :220 */
             if (q == 0.0f) continue;                                                /* :222 */
-            fq_push(&per_view[jj], face_id, q);
+            /* mve::image::color_rgb_to_ycbcr<float> (:225) [UPSTREAM-RECALL] */
+            ycc[0] = (mc[0] * 0.299f + mc[1] * 0.587f) + mc[2] * 0.114f;
+            ycc[1] = ((mc[0] * -0.168736f + mc[1] * -0.331264f) + mc[2] * 0.5f) + 0.5f;
+            ycc[2] = ((mc[0] * 0.5f + mc[1] * -0.418688f) + mc[2] * -0.081312f) + 0.5f;
+            fq_push(&per_view[jj], face_id, q, ycc);
         }
         free(mask);
         free(grad);
@@ -326,6 +467,7 @@ int orc_data_costs(const float *verts, uint32_t num_verts, const uint32_t *faces
     uint16_t *vw = (uint16_t *)malloc(sizeof(uint16_t) * (nnz ? nnz : 1));
     float *ql = (float *)malloc(sizeof(float) * (nnz ? nnz : 1));
     float *cs = (float *)malloc(sizeof(float) * (nnz ? nnz : 1));
+    float *yc = outlier ? (float *)malloc(sizeof(float) * 3 * (nnz ? nnz : 1)) : NULL;
     uint64_t *pos = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)num_faces + 1));
     memcpy(pos, face_ptr, sizeof(uint64_t) * ((size_t)num_faces + 1));
     for (uint32_t j = 0; j < num_views; ++j) {
@@ -333,12 +475,28 @@ int orc_data_costs(const float *verts, uint32_t num_verts, const uint32_t *faces
             uint64_t p = pos[per_view[j].data[i].face]++;
             vw[p] = (uint16_t)j;
             ql[p] = per_view[j].data[i].q;
+            if (yc) for (int c = 0; c < 3; ++c) yc[3 * p + c] = per_view[j].data[i].ycc[c];
         }
         free(per_view[j].data);
     }
     free(per_view);
     free(pos);
     free(cnt);
+    if (outlier) { /* :265-271: detection per face, then drop quality == 0 */
+        uint8_t *flags = (uint8_t *)malloc(num_views ? num_views : 1);
+        uint64_t o = 0;
+        for (uint32_t f = 0; f < num_faces; ++f) {
+            uint64_t a = face_ptr[f], b = face_ptr[f + 1];
+            photometric_outlier_detection(ql + a, yc + 3 * a, (uint32_t)(b - a), outlier, flags);
+            face_ptr[f] = o;
+            for (uint64_t i = a; i < b; ++i)
+                if (ql[i] != 0.0f) { vw[o] = vw[i]; ql[o] = ql[i]; ++o; }
+        }
+        face_ptr[num_faces] = o;
+        nnz = o;
+        free(flags);
+        free(yc);
+    }
 
     float max_quality = 0.0f; /* :278-281 */
     for (uint64_t i = 0; i < nnz; ++i) max_quality = fmaxf(max_quality, ql[i]);

@@ -34,7 +34,7 @@ typedef struct {
 
 typedef struct {
     int32_t data_term;        /* 0 AREA, 1 GMI (settings.h:59-62) */
-    int32_t outlier_removal;  /* 0 NONE (only NONE implemented) */
+    int32_t outlier_removal;  /* 0 NONE, 1 GAUSS_DAMPING, 2 GAUSS_CLAMPING (settings.h:70-74) */
     int32_t geometric_visibility_test;
     uint32_t face_begin, face_end; /* bounded sample for CPU timing: only faces in [begin,end) are
                                       evaluated (occlusion still against the whole mesh); 0,0 = all */

@@ -122,10 +122,10 @@ def gradient_magnitude(rgb):
     return g
 
 
-def data_costs(scene, data_term=1, visibility=True, threads=0, images=None, face_range=(0, 0)):
+def data_costs(scene, data_term=1, visibility=True, threads=0, images=None, face_range=(0, 0), outlier_removal=0):
     L = lib()
     views, keep = make_views(scene, images)
-    st = Settings(data_term, 0, 1 if visibility else 0, face_range[0], face_range[1])
+    st = Settings(data_term, outlier_removal, 1 if visibility else 0, face_range[0], face_range[1])
     F = scene.num_faces
     face_ptr = np.zeros(F + 1, np.uint64)
     vw, cs, ql = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -254,3 +254,45 @@ def test_full_size_properties_C2(b2, scene_mod):
     m4, tr4 = c.view_selection_run(num_parts=4)
     assert np.all(np.diff(tr4) <= 1e-9) and m4.energy_final < 1.02 * minfo.energy_final
     c.close()
+
+
+def _outlier_scene(scene_mod):
+    """near-constant images (so that colours agree across views) with one strongly tinted view"""
+    s = scene_mod.sphere_scene(6, 90, 120, 90, name="outlier")   # 720 faces, ~20 views per face
+    rng = np.random.RandomState(11)
+    imgs = np.empty_like(s.images)
+    for k in range(s.num_views):
+        base = np.array([120, 130, 140], np.int32) + rng.randint(-2, 3, size=3)
+        noise = rng.randint(-3, 4, size=s.images.shape[1:]).astype(np.int32)
+        imgs[k] = np.clip(base[None, None, :] + noise, 1, 255).astype(np.uint8)
+    imgs[3] = np.clip(imgs[3].astype(np.int32) + np.array([70, -40, 30]), 1, 255).astype(np.uint8)
+    s.images = imgs
+    return s
+
+
+@pytest.mark.parametrize("mode,data_term", [(1, 0), (2, 0), (1, 1), (2, 1)])
+def test_photometric_outlier_removal(b2, scene_mod, orc, mode, data_term):
+    """calculate_data_costs.cpp:35-129 (GAUSS_DAMPING = 1, GAUSS_CLAMPING = 2), both data terms."""
+    s = _outlier_scene(scene_mod) if data_term == 0 else scene_mod.sphere_scene(8, 30, 240, 180, displace=0.04, name="o2")
+    o = orc.data_costs(s, data_term=data_term, outlier_removal=mode)
+    base = orc.data_costs(s, data_term=data_term)
+    c = _ctx(b2, s)
+    info = c.data_costs_run(data_term=data_term, outlier_removal=mode)
+    g = c.data_costs_download(info.nnz, quality=True)
+    assert np.array_equal(g["face_ptr"], o["face_ptr"]) and np.array_equal(g["view"], o["view"])
+    # fp64 exp() of libm and of the device may differ in the last bit; after the cast to fp32 that
+    # shows up (if ever) as a 1-ulp quality difference: compare with 2 ulp slack, costs likewise
+    assert np.max(np.abs(g["quality"].view(np.int32).astype(np.int64) - o["quality"].view(np.int32))) <= 2
+    assert np.allclose(g["cost"], o["cost"], rtol=0, atol=1e-6)
+    if data_term == 0 and mode == 2:
+        assert len(o["view"]) < len(base["view"])          # the tinted view is clamped away somewhere
+        removed = set(zip(*[a.tolist() for a in _pairs(base)])) - set(zip(*[a.tolist() for a in _pairs(o)]))
+        assert removed and all(v == 3 for _, v in removed)
+    if mode == 1:
+        assert o["quality"].sum() < base["quality"].sum()   # damping only ever lowers qualities
+    c.close()
+
+
+def _pairs(dc):
+    fp = dc["face_ptr"].astype(np.int64)
+    return np.repeat(np.arange(len(fp) - 1), np.diff(fp)), dc["view"].astype(np.int64)
