@@ -179,6 +179,19 @@ int b2tex_global_seam_leveling(const float *verts, uint32_t num_verts, const uin
                                uint32_t *row_ptr_out, uint32_t **row_label_out, float **x_out,
                                b2tex_seam_info *info);
 
+/* The three stages back to back on one upload -- what texrecon does between texrecon.cpp:100 and :171
+ * when it writes no intermediate results (--no_intermediate_results, arguments.cpp:88-89): the mesh and
+ * the images cross PCIe once, DataCosts stay on the device, only labels[F] and the per-(vertex,label)
+ * adjust values come back.  Optional outputs may be NULL.  row_label/x are malloc'ed (b2tex_free). */
+int b2tex_texture_hot_path(const float *verts, uint32_t num_verts, const uint32_t *faces,
+                           const float *face_normals, uint32_t num_faces, const b2tex_view *views,
+                           uint32_t num_views, const uint32_t *adj_ptr, const uint32_t *adj_idx,
+                           const uint32_t *vf_ptr, const uint32_t *vf_idx, const uint32_t *vv_ptr,
+                           const uint32_t *vv_idx, const b2tex_settings *settings,
+                           const b2tex_mrf_params *mrf_params_or_null, uint32_t *labels_out,
+                           uint32_t *row_ptr_out, uint32_t **row_label_out, float **x_out,
+                           b2tex_dc_info *dc_info, b2tex_mrf_info *mrf_info, b2tex_seam_info *seam_info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,7 +30,7 @@ EXPORTS = [
     "b2tex_labels_download", "b2tex_mrf_init", "b2tex_mrf_iterate", "b2tex_mrf_energy", "b2tex_mrf_sample_forest",
     "b2tex_seam_run", "b2tex_seam_download", "b2tex_seam_matrix_download", "b2tex_device_ptr",
     "b2tex_calculate_data_costs", "b2tex_calculate_data_costs_into", "b2tex_view_selection",
-    "b2tex_global_seam_leveling",
+    "b2tex_global_seam_leveling", "b2tex_texture_hot_path",
 ]
 
 
@@ -401,3 +401,27 @@ def global_seam_leveling(scene, rings, labels):
     R = int(info.num_rows)
     return dict(row_ptr=row_ptr, row_label=_grab(rl, C.c_uint32, R),
                 x=_grab(x, C.c_float, 3 * R).reshape(R, 3), info=info)
+
+
+def texture_hot_path(scene, adj, rings, settings: Settings | None = None, **mrf_kw):
+    """calculate_data_costs -> view_selection -> global_seam_leveling on ONE upload
+    (b2tex_texture_hot_path): host buffers in, labels + adjust values out, DataCosts stay on the device."""
+    st = settings or Settings()
+    views = make_views(scene.pos, scene.viewdir, scene.proj, scene.w2c, scene.width, scene.height, scene.images)
+    s = B2Settings(st.data_term, st.outlier_removal, 1 if st.geometric_visibility_test else 0)
+    p = mrf_params(**mrf_kw)
+    v, f, n = _c(scene.verts, np.float32), _c(scene.faces, np.uint32), _c(scene.face_normals, np.float32)
+    ap, ai = _c(adj[0], np.uint32), _c(adj[1], np.uint32)
+    vf_ptr, vf_idx, vv_ptr, vv_idx = [_c(a, np.uint32) for a in rings]
+    Vn, F = v.shape[0], f.shape[0]
+    labels = np.zeros(F, np.uint32)
+    row_ptr = np.zeros(Vn + 1, np.uint32)
+    rl, x = C.c_void_p(), C.c_void_p()
+    dci, mi, si = B2DcInfo(), B2MrfInfo(), B2SeamInfo()
+    _check(lib().b2tex_texture_hot_path(_p(v), C.c_uint32(Vn), _p(f), _p(n), C.c_uint32(F), views,
+                                        C.c_uint32(scene.num_views), _p(ap), _p(ai), _p(vf_ptr), _p(vf_idx),
+                                        _p(vv_ptr), _p(vv_idx), C.byref(s), C.byref(p), _p(labels), _p(row_ptr),
+                                        C.byref(rl), C.byref(x), C.byref(dci), C.byref(mi), C.byref(si)))
+    R = int(si.num_rows)
+    return dict(labels=labels, row_ptr=row_ptr, row_label=_grab(rl, C.c_uint32, R),
+                x=_grab(x, C.c_float, 3 * R).reshape(R, 3), dc_info=dci, mrf_info=mi, seam_info=si)

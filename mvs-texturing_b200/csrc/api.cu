@@ -54,6 +54,9 @@ int b2tex_create(int device, b2tex_ctx **out)
     B2_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    B2_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    B2_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    B2_CUDA(cudaEventCreateWithFlags(&c->ev_grad, cudaEventDisableTiming));
     *out = c;
     return B2TEX_OK;
 }
@@ -63,6 +66,10 @@ void b2tex_destroy(b2tex_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream2);
+    cudaStreamDestroy(c->stream2);
+    cudaEventDestroy(c->ev_main);
+    cudaEventDestroy(c->ev_grad);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -457,6 +464,37 @@ int b2tex_global_seam_leveling(const float *verts, uint32_t nv, const uint32_t *
     if (rc == B2TEX_OK) {
         *row_label_out = (uint32_t *)malloc(sizeof(uint32_t) * (info->num_rows ? info->num_rows : 1));
         *x_out = (float *)malloc(sizeof(float) * 3 * (info->num_rows ? info->num_rows : 1));
+        rc = b2tex_seam_download(c, row_ptr_out, *row_label_out, *x_out, nullptr);
+    }
+    b2tex_destroy(c);
+    return rc;
+}
+
+int b2tex_texture_hot_path(const float *verts, uint32_t nv, const uint32_t *faces, const float *normals, uint32_t nf,
+                           const b2tex_view *views, uint32_t K, const uint32_t *adj_ptr, const uint32_t *adj_idx,
+                           const uint32_t *vf_ptr, const uint32_t *vf_idx, const uint32_t *vv_ptr,
+                           const uint32_t *vv_idx, const b2tex_settings *st, const b2tex_mrf_params *mp,
+                           uint32_t *labels_out, uint32_t *row_ptr_out, uint32_t **row_label_out, float **x_out,
+                           b2tex_dc_info *dci, b2tex_mrf_info *mi, b2tex_seam_info *si)
+{
+    if (K > 65535u) { set_error("Exeeded maximal number of views"); return B2TEX_ERR_LIMITS; }
+    b2tex_ctx *c = nullptr;
+    B2_TRY(b2tex_create(0, &c));
+    b2tex_dc_info dc_local; b2tex_mrf_info mrf_local; b2tex_seam_info seam_local;
+    if (!dci) dci = &dc_local;
+    if (!mi) mi = &mrf_local;
+    if (!si) si = &seam_local;
+    int rc = b2tex_set_mesh(c, verts, nv, faces, normals, nf);
+    if (rc == B2TEX_OK) rc = b2tex_set_views(c, views, K);
+    if (rc == B2TEX_OK) rc = b2tex_set_adjacency(c, adj_ptr, adj_idx);
+    if (rc == B2TEX_OK) rc = b2tex_set_vertex_rings(c, vf_ptr, vf_idx, vv_ptr, vv_idx);
+    if (rc == B2TEX_OK) rc = b2tex_data_costs_run(c, st, dci);
+    if (rc == B2TEX_OK) rc = b2tex_view_selection_run(c, mp, mi, nullptr);
+    if (rc == B2TEX_OK && labels_out) rc = b2tex_labels_download(c, labels_out);
+    if (rc == B2TEX_OK) rc = b2tex_seam_run(c, si);
+    if (rc == B2TEX_OK && row_ptr_out && row_label_out && x_out) {
+        *row_label_out = (uint32_t *)malloc(sizeof(uint32_t) * (si->num_rows ? si->num_rows : 1));
+        *x_out = (float *)malloc(sizeof(float) * 3 * (si->num_rows ? si->num_rows : 1));
         rc = b2tex_seam_download(c, row_ptr_out, *row_label_out, *x_out, nullptr);
     }
     b2tex_destroy(c);

@@ -237,6 +237,28 @@ def e2e_host_path(b2, torch, s, adj, rings, steps=1, warmup=1):
               (mesh_b + sp.images.nbytes + sum(r.nbytes for r in pr) + labels.nbytes)
         d2h = dc_b + 2 * labels.nbytes + g["row_ptr"].nbytes + g["row_label"].nbytes + g["x"].nbytes
     t = sum(times) / len(times)
+    three = {"value": s.num_faces / t, "unit": "faces/s", "h2d_bytes_per_step": int(h2d),
+             "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t, "stage_ms_per_step": stages,
+             "path": "b2tex_calculate_data_costs_into -> b2tex_view_selection -> b2tex_global_seam_leveling "
+                     "(DataCosts cross PCIe twice, images are uploaded twice)"}
+    # ---- the same three stages on one upload (b2tex_texture_hot_path): the headline e2e ----
+    ftimes = []
+    for i in range(warmup + steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = b2.texture_hot_path(sp, (ap, ai), pr)
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ftimes.append(time.perf_counter() - t0)
+    tf = sum(ftimes) / len(ftimes)
+    mesh_b = sp.verts.nbytes + sp.faces.nbytes + sp.face_normals.nbytes
+    return {"value": s.num_faces / tf, "unit": "faces/s",
+            "h2d_bytes_per_step": int(mesh_b + sp.images.nbytes + ap.nbytes + ai.nbytes + sum(a.nbytes for a in pr)),
+            "d2h_bytes_per_step": int(r["labels"].nbytes + r["row_ptr"].nbytes + r["row_label"].nbytes + r["x"].nbytes),
+            "ms_per_step": 1e3 * tf,
+            "path": "b2tex_texture_hot_path: pinned host mesh/images/graph in, labels + adjust values out "
+                    "(what texrecon does with --no_intermediate_results)",
+            "three_call_path": three}
     return {"value": s.num_faces / t, "unit": "faces/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t, "stage_ms_per_step": stages,
             "path": "b2tex_calculate_data_costs_into -> b2tex_view_selection -> b2tex_global_seam_leveling, pinned host buffers"}

@@ -296,3 +296,15 @@ def test_photometric_outlier_removal(b2, scene_mod, orc, mode, data_term):
 def _pairs(dc):
     fp = dc["face_ptr"].astype(np.int64)
     return np.repeat(np.arange(len(fp) - 1), np.diff(fp)), dc["view"].astype(np.int64)
+
+
+def test_fused_hot_path_equals_three_calls(b2, get_scene, oracle_pipeline):
+    name = "C1d"
+    s = get_scene(name)
+    r = oracle_pipeline(name)
+    f = b2.texture_hot_path(s, r["adj"], r["rings"])
+    assert np.array_equal(f["labels"], r["mrf"]["labels"])
+    assert f["dc_info"].nnz == len(r["dc"]["view"])
+    assert np.array_equal(f["row_ptr"], r["seam"]["row_ptr"]) and np.array_equal(f["row_label"], r["seam"]["row_label"])
+    g = b2.global_seam_leveling(s, r["rings"], f["labels"])
+    assert np.array_equal(f["x"].view(np.uint32), g["x"].view(np.uint32))   # same kernels, same inputs
