@@ -1,0 +1,210 @@
+"""oracle/patches.py -- TEST INFRASTRUCTURE (see oracle/oracle.h).
+
+Pure-Python restatement (small scenes only) of the step that sits between view selection and seam
+leveling in the reference, and of the patch-based colour sampling that global_seam_leveling really does:
+
+  generate_texture_patches   libs/tex/generate_texture_patches.cpp:453-538 (no hole filling: every face
+                             of the test scenes is seen), generate_candidate :78-138,
+                             UniGraph::get_subgraphs uni_graph.cpp:21-55,
+                             merge_vertex_projection_infos :40-65
+  find_mesh_edge_projections libs/tex/seam_leveling.cpp:61-91
+  sample_edge / calculate_difference   libs/tex/global_seam_leveling.cpp:26-43, 86-138
+  TexturePatch::get_pixel_value        libs/tex/texture_patch.cpp:162-169 (FloatImage::linear_at)
+
+Purpose: pin the "stage-isolated" shortcut used by oracle/seam.c and by the CUDA path (colours sampled
+from the whole view of a label at get_pixel_coords(vertex)) against the patch-relative sampling of the
+reference.  tests/test_oracle_cpu.py::test_patch_sampling_equals_view_sampling compares Rhs = A^T b.
+Patch ids are assigned in ascending label order (the reference's order depends on OpenMP scheduling,
+generate_texture_patches.cpp:469,514-518; ids only name patches, they do not enter the arithmetic).
+"""
+from __future__ import annotations
+
+import collections
+import ctypes as C
+
+import numpy as np
+
+f32 = np.float32
+BORDER = 1  # texture_patch.h:21
+
+
+def _pixel_coords(O, view, x):
+    out = (C.c_float * 2)()
+    O.lib().orc_pixel_coords(C.byref(view), (C.c_float * 3)(*[float(v) for v in x]), out)
+    return f32(out[0]), f32(out[1])
+
+
+def get_subgraphs(adj_ptr, adj_idx, labels, label):
+    """uni_graph.cpp:21-55: BFS components of one label, in the reference's visiting order"""
+    used = np.zeros(len(labels), bool)
+    comps = []
+    for i in np.flatnonzero(labels == label):
+        if used[i]:
+            continue
+        comp, queue = [], collections.deque([int(i)])
+        used[i] = True
+        while queue:
+            node = queue.popleft()
+            comp.append(node)
+            for a in adj_idx[adj_ptr[node]:adj_ptr[node + 1]]:
+                if labels[a] == label and not used[a]:
+                    queue.append(int(a))
+                    used[a] = True
+        comps.append(comp)
+    return comps
+
+
+class Patch:
+    def __init__(self, label, faces, texcoords, image, bbox):
+        self.label, self.faces, self.texcoords, self.image, self.bbox = label, faces, texcoords, image, bbox
+
+
+def generate_candidate(O, scene, views, label, faces_list):
+    """generate_texture_patches.cpp:78-138"""
+    view = views[label - 1]
+    W, H = scene.width, scene.height
+    min_x, min_y, max_x, max_y = W, H, 0, 0
+    tex = []
+    for f in faces_list:
+        for j in range(3):
+            px, py = _pixel_coords(O, view, scene.verts[scene.faces[f, j]])
+            tex.append([px, py])
+            min_x = min(int(np.floor(px)), min_x); min_y = min(int(np.floor(py)), min_y)
+            max_x = max(int(np.ceil(px)), max_x); max_y = max(int(np.ceil(py)), max_y)
+    width, height = max_x - min_x + 1 + 2 * BORDER, max_y - min_y + 1 + 2 * BORDER
+    min_x -= BORDER; min_y -= BORDER
+    tex = np.array(tex, f32) - np.array([min_x, min_y], f32)          # relative texcoords (:121-124)
+    # mve::image::crop with (255,0,255) outside the view, then byte_to_float_image (:126-128)
+    img = np.empty((height, width, 3), np.uint8)
+    img[:] = np.array([255, 0, 255], np.uint8)
+    x0, y0 = max(min_x, 0), max(min_y, 0)
+    x1, y1 = min(min_x + width, W), min(min_y + height, H)
+    if x1 > x0 and y1 > y0:
+        img[y0 - min_y:y1 - min_y, x0 - min_x:x1 - min_x] = scene.images[label - 1][y0:y1, x0:x1]
+    fimg = (img.astype(f32) / f32(255.0)).astype(f32)
+    return Patch(label, list(faces_list), tex, fimg, [min_x, min_y, max_x, max_y])
+
+
+def generate_texture_patches(O, scene, adj, labels):
+    """returns (patches, vertex_projection_infos) -- generate_texture_patches.cpp:453-538"""
+    adj_ptr, adj_idx = adj
+    views, _keep = O.make_views(scene)
+    patches = []
+    vpi = [dict() for _ in range(scene.verts.shape[0])]   # vertex -> {patch_id: (projection, [faces])}
+    for label in range(1, scene.num_views + 1):
+        cands = [generate_candidate(O, scene, views, label, comp)
+                 for comp in get_subgraphs(adj_ptr, adj_idx, labels, label)]
+        # merge candidates whose bounding box lies inside another one (:484-508)
+        i = 0
+        while i < len(cands):
+            it = cands[i]
+            j = 0
+            while j < len(cands):
+                sit = cands[j]
+                b, ob = sit.bbox, it.bbox
+                if sit is not it and b[0] >= ob[0] and b[2] <= ob[2] and b[1] >= ob[1] and b[3] <= ob[3]:
+                    it.faces += sit.faces
+                    off = np.array([b[0] - ob[0], b[1] - ob[1]], f32)
+                    it.texcoords = np.concatenate([it.texcoords, (sit.texcoords + off).astype(f32)], 0)
+                    del cands[j]
+                    if j < i:
+                        i -= 1
+                else:
+                    j += 1
+            i += 1
+        for cand in cands:
+            pid = len(patches)
+            patches.append(cand)
+            for k, f in enumerate(cand.faces):
+                for j in range(3):
+                    v = int(scene.faces[f, j])
+                    proj = cand.texcoords[3 * k + j]
+                    if pid not in vpi[v]:                     # merge_vertex_projection_infos (:40-65):
+                        vpi[v][pid] = (proj, [f])             # first projection wins, faces are appended
+                    else:
+                        vpi[v][pid][1].append(f)
+    return patches, vpi
+
+
+def _linear_at(img, x, y):
+    """mve::FloatImage::linear_at [UPSTREAM-RECALL], fp32"""
+    h, w, _ = img.shape
+    x = max(f32(0.0), min(f32(w - 1), x)); y = max(f32(0.0), min(f32(h - 1), y))
+    fx, fy = int(x), int(y)
+    fx1, fy1 = min(fx + 1, w - 1), min(fy + 1, h - 1)
+    w1 = f32(x - f32(fx)); w0 = f32(f32(1.0) - w1)
+    w3 = f32(y - f32(fy)); w2 = f32(f32(1.0) - w3)
+    return ((img[fy, fx] * f32(w0 * w2) + img[fy, fx1] * f32(w1 * w2)).astype(f32)
+            + img[fy1, fx] * f32(w0 * w3) + img[fy1, fx1] * f32(w1 * w3)).astype(f32)
+
+
+def sample_edge(patch, p1, p2):
+    """global_seam_leveling.cpp:26-43"""
+    p12 = (p2 - p1).astype(f32)
+    nrm = f32(np.sqrt(f32(f32(p12[0] * p12[0]) + f32(p12[1] * p12[1]))))
+    n = int(f32(max(nrm, f32(1.0)) * f32(2.0)))
+    acc, wsum = np.zeros(3, f32), f32(0.0)
+    for s in range(n):
+        fraction = f32(f32(s) / f32(n - 1))
+        sp = (p1 + (p12 * fraction).astype(f32)).astype(f32)
+        col = _linear_at(patch.image, sp[0], sp[1])
+        wgt = f32(f32(1.0) - fraction)
+        acc = (acc + (col * wgt).astype(f32)).astype(f32)
+        wsum = f32(wsum + wgt)
+    return (acc / wsum).astype(f32)
+
+
+def find_mesh_edge_projections(vpi, v1, v2):
+    """seam_leveling.cpp:61-91: one entry per patch that holds both vertices through a common face"""
+    out = {}
+    for pid, (p1, faces1) in vpi[v1].items():
+        if pid in vpi[v2]:
+            p2, faces2 = vpi[v2][pid]
+            if set(faces1) & set(faces2):
+                out[pid] = (p1, p2)
+    return [(pid, *out[pid]) for pid in sorted(out)]
+
+
+def seam_rhs_from_patches(O, scene, adj, rings, labels, row_ptr, row_label):
+    """Rhs = A^T b (global_seam_leveling.cpp:211-237,266-270) with colours sampled from texture patches."""
+    patches, vpi = generate_texture_patches(O, scene, adj, labels)
+    vf_ptr, vf_idx, vv_ptr, vv_idx = rings
+    R = len(row_label)
+    rhs = np.zeros((R, 3), f32)
+    for i in range(scene.verts.shape[0]):
+        rows = range(int(row_ptr[i]), int(row_ptr[i + 1]))
+        for j in rows:
+            for k in rows:
+                l1, l2 = int(row_label[j]), int(row_label[k])
+                if not l1 < l2:
+                    continue
+                c1, c2, w1, w2, any_edge = np.zeros(3, f32), np.zeros(3, f32), f32(0), f32(0), False
+                for adjv in vv_idx[vv_ptr[i]:vv_ptr[i + 1]]:
+                    adjv = int(adjv)
+                    if adjv == i:
+                        continue
+                    ef = [int(f) for f in vf_idx[vf_ptr[i]:vf_ptr[i + 1]] if adjv in scene.faces[f]]
+                    for x in range(len(ef)):
+                        for y in range(x + 1, len(ef)):
+                            fl = sorted((int(labels[ef[x]]), int(labels[ef[y]])))
+                            if fl[0] != l1 or fl[1] != l2:
+                                continue
+                            d = (scene.verts[adjv] - scene.verts[i]).astype(f32)
+                            length = f32(np.sqrt(f32(f32(f32(d[0] * d[0]) + f32(d[1] * d[1])) + f32(d[2] * d[2]))))
+                            if length == 0:
+                                continue
+                            any_edge = True
+                            n_used = 0
+                            for pid, p1, p2 in find_mesh_edge_projections(vpi, i, adjv):
+                                pl = patches[pid].label
+                                if pl == l1:
+                                    c1 = (c1 + (sample_edge(patches[pid], p1, p2) * length).astype(f32)).astype(f32); w1 = f32(w1 + length); n_used += 1
+                                if pl == l2:
+                                    c2 = (c2 + (sample_edge(patches[pid], p1, p2) * length).astype(f32)).astype(f32); w2 = f32(w2 + length); n_used += 1
+                            assert n_used == 2                       # global_seam_leveling.cpp:124
+                if not any_edge:
+                    continue
+                b = ((c2 / w2).astype(f32) - (c1 / w1).astype(f32)).astype(f32)
+                rhs[j] = (rhs[j] + b).astype(f32)
+                rhs[k] = (rhs[k] - b).astype(f32)
+    return rhs, patches, vpi

@@ -308,3 +308,27 @@ def test_fused_hot_path_equals_three_calls(b2, get_scene, oracle_pipeline):
     assert np.array_equal(f["row_ptr"], r["seam"]["row_ptr"]) and np.array_equal(f["row_label"], r["seam"]["row_label"])
     g = b2.global_seam_leveling(s, r["rings"], f["labels"])
     assert np.array_equal(f["x"].view(np.uint32), g["x"].view(np.uint32))   # same kernels, same inputs
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "C1d", "C2s"])
+def test_cuda_path_matches_committed_golden_snapshots(b2, scene_mod, get_scene, name):
+    """CUDA outputs against tests/golden/oracle_snapshots.json directly (no oracle run involved)."""
+    import json, os, zlib
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_snapshots.json")))[name]
+    s = get_scene(name)
+    c = _ctx(b2, s)
+    c.set_adjacency(*scene_mod.face_adjacency(s.faces))
+    c.set_vertex_rings(*scene_mod.vertex_rings(s.faces, s.verts.shape[0]))
+    info = c.data_costs_run()
+    d = c.data_costs_download(info.nnz)
+    assert info.nnz == gold["nnz"]
+    assert zlib.crc32(d["face_ptr"].tobytes()) == gold["crc_face_ptr"]
+    assert zlib.crc32(d["view"].tobytes()) == gold["crc_view"]
+    assert zlib.crc32(d["cost"].tobytes()) == gold["crc_cost"]
+    minfo, _ = c.view_selection_run()
+    assert minfo.iterations == gold["mrf_iterations"]
+    assert zlib.crc32(c.labels_download().tobytes()) == gold["crc_labels"]
+    assert int(round(minfo.energy_final * 4294967296.0)) == gold["mrf_energy_fixed"]
+    sinfo = c.seam_run()
+    assert sinfo.num_rows == gold["seam_rows"] and sinfo.num_a_rows == gold["seam_a_rows"]
+    c.close()

@@ -412,3 +412,33 @@ def test_oracle_matches_golden_snapshots(orc, scene_mod, oracle_pipeline):
         assert m["energy"] == pytest.approx(g["mrf_energy"], rel=1e-12)
         assert len(sm["row_label"]) == g["seam_rows"]
         assert list(sm["iterations"]) == g["cg_iterations"]
+
+
+# ---- texture patches: the reference's patch-relative colour sampling vs the stage-isolated shortcut ----
+@pytest.mark.parametrize("name", ["tiny", "small", "C1d"])
+def test_patch_sampling_equals_view_sampling(orc, scene_mod, oracle_pipeline, get_scene, name):
+    """oracle/seam.c and the CUDA path sample seam colours from the whole view of a label; the reference
+    samples cropped float patches at patch-relative coordinates (generate_texture_patches.cpp:78-138,
+    seam_leveling.cpp:61-91).  Same image content, different coordinate frame: Rhs = A^T b must agree."""
+    import patches as P   # oracle/patches.py
+    s = get_scene(name)
+    r = oracle_pipeline(name)
+    o = r["seam"]
+    rhs_p, patches, vpi = P.seam_rhs_from_patches(orc, s, r["adj"], r["rings"], r["mrf"]["labels"],
+                                                   o["row_ptr"], o["row_label"])
+    # structure: every seen face is in exactly one patch of its own label; texcoords stay inside the patch
+    owner = {}
+    for pid, p in enumerate(patches):
+        h, w, _ = p.image.shape
+        assert p.texcoords.min() >= 0 and p.texcoords[:, 0].max() <= w - 1 and p.texcoords[:, 1].max() <= h - 1
+        for f in p.faces:
+            assert f not in owner and r["mrf"]["labels"][f] == p.label
+            owner[f] = pid
+    assert len(owner) == int(np.sum(r["mrf"]["labels"] != 0))
+    # every (vertex, label) unknown of the seam system corresponds to >= 1 (vertex, patch) projection
+    for v in range(s.verts.shape[0]):
+        labs = {patches[pid].label for pid in vpi[v]}
+        assert labs == set(o["row_label"][o["row_ptr"][v]:o["row_ptr"][v + 1]].tolist())
+    scale = np.abs(o["rhs"]).max()
+    assert scale > 0
+    assert np.abs(rhs_p - o["rhs"]).max() < 2e-6 * max(1.0, scale)   # measured 1.5e-7 .. 2.7e-7
