@@ -54,9 +54,6 @@ int b2tex_create(int device, b2tex_ctx **out)
     B2_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    B2_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    B2_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
-    B2_CUDA(cudaEventCreateWithFlags(&c->ev_grad, cudaEventDisableTiming));
     *out = c;
     return B2TEX_OK;
 }
@@ -66,10 +63,6 @@ void b2tex_destroy(b2tex_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaStreamSynchronize(c->stream2);
-    cudaStreamDestroy(c->stream2);
-    cudaEventDestroy(c->ev_main);
-    cudaEventDestroy(c->ev_grad);
     cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -126,9 +126,6 @@ struct b2tex_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;     // side stream: gradient images are computed while the BVH is built
-    cudaEvent_t ev_main = nullptr, ev_grad = nullptr;
-    bool grad_pending = false;          // ev_grad recorded and not yet waited for on `stream`
 
     // mesh
     uint32_t Vn = 0, F = 0;

@@ -652,10 +652,6 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
         B2_KERNEL_CHECK();
     }
     if (num_cand) {
-        if (c->grad_pending) {  // join the side stream that computes the gradient images
-            B2_CUDA(cudaStreamWaitEvent(s, c->ev_grad, 0));
-            c->grad_pending = false;
-        }
         size_t qblocks = (num_cand + 255) / 256;
         ScopedTimer tm(c, "k_quality", 10.0 * (double)num_cand + mesh_bytes);
         k_quality<<<(unsigned)qblocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->views_dev.p, c->cand_view.p,
@@ -673,7 +669,6 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     }
     {
         ScopedTimer tm(c, "k_count_survivors", 4.0 * (double)num_cand + 16.0 * F);
-        if (c->grad_pending) { B2_CUDA(cudaStreamWaitEvent(s, c->ev_grad, 0)); c->grad_pending = false; }
         k_count_survivors<<<(F + 1 + 255) / 256, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, fb, fe, F, cnt.p);
     }
     B2_KERNEL_CHECK();

@@ -233,11 +233,7 @@ int prepare_images(b2tex_ctx *c, int data_term, bool force)
 
     if (data_term == 1) {
         B2_TRY(c->grad.alloc(total_px));
-        // The gradient images are only consumed by k_quality, far down the stage: compute them on a side
-        // stream so that they overlap the BVH build and the cull passes (none of which touch them).
-        B2_CUDA(cudaEventRecord(c->ev_main, s));          // earlier readers of grad (previous call) are done
-        B2_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_main, 0));
-        cudaStream_t s2 = c->stream2;
+        ScopedTimer tm(c, "k_lum_sobel", 4.0 * (double)total_px);  // 3 B rgb read + 1 B gradient written
         bool uniform = true;
         for (uint32_t v = 1; v < K; ++v)
             uniform = uniform && c->views_host[v].width == c->views_host[0].width
@@ -246,17 +242,15 @@ int prepare_images(b2tex_ctx *c, int data_term, bool force)
         if (uniform && K <= 65535u && !scalar_sobel) {  // one launch for all views (blockIdx.z = view)
             int w = c->views_host[0].width, h = c->views_host[0].height;
             dim3 grid((w + TW2 - 1) / TW2, (h + TH2 - 1) / TH2, K);
-            k_lum_sobel_vec<<<grid, 256, 0, s2>>>(c->rgb.p, c->grad.p, w, h, (size_t)w * h, c->rgb.p,
+            k_lum_sobel_vec<<<grid, 256, 0, s>>>(c->rgb.p, c->grad.p, w, h, (size_t)w * h, c->rgb.p,
                                                  c->rgb.p + c->rgb.n);
         } else {
             for (uint32_t v = 0; v < K; ++v) {
                 int w = c->views_host[v].width, h = c->views_host[v].height;
                 dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH);
-                k_lum_sobel<<<grid, 256, 0, s2>>>(c->rgb.p + 3 * c->img_off[v], c->grad.p + c->img_off[v], w, h);
+                k_lum_sobel<<<grid, 256, 0, s>>>(c->rgb.p + 3 * c->img_off[v], c->grad.p + c->img_off[v], w, h);
             }
         }
-        B2_CUDA(cudaEventRecord(c->ev_grad, s2));
-        c->grad_pending = true;
         B2_KERNEL_CHECK();
     }
 
