@@ -208,3 +208,83 @@ def seam_rhs_from_patches(O, scene, adj, rings, labels, row_ptr, row_label):
                 rhs[j] = (rhs[j] + b).astype(f32)
                 rhs[k] = (rhs[k] - b).astype(f32)
     return rhs, patches, vpi
+
+
+# ---- TexturePatch::adjust_colors (libs/tex/texture_patch.cpp:41-116) --------------------------------
+SQRT2 = f32(np.sqrt(2))
+
+
+def _bary(v1, v2, v3, detT, x, y):
+    """Tri::get_barycentric_coords (tri.h:50-56), fp32"""
+    x, y = f32(x), f32(y)
+    alpha = f32(f32(f32(f32(v2[1] - v3[1]) * f32(x - v3[0])) + f32(f32(v3[0] - v2[0]) * f32(y - v3[1]))) / detT)
+    beta = f32(f32(f32(f32(v3[1] - v1[1]) * f32(x - v3[0])) + f32(f32(v1[0] - v3[0]) * f32(y - v3[1]))) / detT)
+    gamma = f32(f32(f32(1.0) - alpha) - beta)
+    return alpha, beta, gamma
+
+
+def adjust_colors(patch, adjust_values):
+    """Rasterises barycentric-interpolated per-vertex adjust values into the patch (pixels within
+    sqrt(2) of a triangle are extrapolated and marked 64 in the blending mask), adds them to the image
+    and zeroes pixels no triangle reaches.  adjust_values: (3 * num_faces, 3) fp32, one row per
+    face corner in texcoord order.  Returns (image, validity_mask, blending_mask)."""
+    h, w, _ = patch.image.shape
+    validity = np.zeros((h, w), np.uint8)
+    blending = np.zeros((h, w), np.uint8)
+    iadj = np.zeros((h, w, 3), f32)
+    tc = patch.texcoords
+    for i in range(0, len(tc), 3):
+        v1, v2, v3 = tc[i], tc[i + 1], tc[i + 2]
+        detT = f32(f32(f32(v1[0] - v3[0]) * f32(v2[1] - v3[1])) - f32(f32(v1[1] - v3[1]) * f32(v2[0] - v3[0])))
+        u, v = (v2 - v1).astype(f32), (v3 - v1).astype(f32)
+        area = f32(f32(0.5) * abs(f32(f32(u[0] * v[1]) - f32(u[1] * v[0]))))
+        if area < np.finfo(np.float32).eps:
+            continue
+        min_x = int(np.floor(min(v1[0], v2[0], v3[0]))) - BORDER
+        min_y = int(np.floor(min(v1[1], v2[1], v3[1]))) - BORDER
+        max_x = int(np.ceil(max(v1[0], v2[0], v3[0]))) + BORDER
+        max_y = int(np.ceil(max(v1[1], v2[1], v3[1]))) + BORDER
+        assert 0 <= min_x and max_x <= w and 0 <= min_y and max_y <= h          # texture_patch.cpp:63-64
+        n23 = f32(np.sqrt(f32(f32((v2 - v3)[0] ** 2) + f32((v2 - v3)[1] ** 2))))
+        n13 = f32(np.sqrt(f32(f32((v1 - v3)[0] ** 2) + f32((v1 - v3)[1] ** 2))))
+        n12 = f32(np.sqrt(f32(f32((v1 - v2)[0] ** 2) + f32((v1 - v2)[1] ** 2))))
+        a0, a1, a2 = adjust_values[i], adjust_values[i + 1], adjust_values[i + 2]
+        for y in range(min_y, max_y):
+            for x in range(min_x, max_x):
+                b0, b1, b2 = _bary(v1, v2, v3, detT, x, y)
+                inside = min(b0, b1, b2) >= 0
+                if not inside:
+                    if validity[y, x] == 255:
+                        continue
+                    ha = f32(f32(f32(f32(2.0) * -b0) * area) / n23)
+                    hb = f32(f32(f32(f32(2.0) * -b1) * area) / n13)
+                    hc = f32(f32(f32(f32(2.0) * -b2) * area) / n12)
+                    if ha > SQRT2 or hb > SQRT2 or hc > SQRT2:
+                        continue
+                iadj[y, x] = ((a0 * b0).astype(f32) + (a1 * b1).astype(f32) + (a2 * b2).astype(f32)).astype(f32)
+                validity[y, x] = 255
+                blending[y, x] = 255 if inside else 64
+    img = patch.image.copy()
+    valid = validity != 0
+    img[valid] = (img[valid] + iadj[valid]).astype(f32)
+    img[~valid] = 0
+    return img, validity, blending
+
+
+def apply_adjust_values(scene, patches, row_ptr, row_label, x):
+    """global_seam_leveling.cpp:293-323: gather the per-(vertex,label) offsets of every face corner of a
+    patch and call adjust_colors; returns new Patch objects with adjusted images."""
+    out = []
+    for p in patches:
+        adj = np.zeros((3 * len(p.faces), 3), f32)
+        for k, f in enumerate(p.faces):
+            for j in range(3):
+                v = int(scene.faces[f, j])
+                rows = range(int(row_ptr[v]), int(row_ptr[v + 1]))
+                r = next(r for r in rows if int(row_label[r]) == p.label)   # adjust_values[vertex].find(label)
+                adj[3 * k + j] = x[r]
+        img, validity, blending = adjust_colors(p, adj)
+        q = Patch(p.label, p.faces, p.texcoords, img, p.bbox)
+        q.validity, q.blending = validity, blending
+        out.append(q)
+    return out

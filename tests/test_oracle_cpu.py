@@ -442,3 +442,52 @@ def test_patch_sampling_equals_view_sampling(orc, scene_mod, oracle_pipeline, ge
     scale = np.abs(o["rhs"]).max()
     assert scale > 0
     assert np.abs(rhs_p - o["rhs"]).max() < 2e-6 * max(1.0, scale)   # measured 1.5e-7 .. 2.7e-7
+
+
+def test_adjust_colors_known_answers(orc):
+    """TexturePatch::adjust_colors (texture_patch.cpp:41-116): constant offsets and a linear ramp."""
+    import patches as P
+    tc = np.array([[3.2, 3.1], [12.7, 4.4], [5.9, 11.6], [12.7, 4.4], [13.8, 12.9], [5.9, 11.6]], np.float32)
+    img = np.full((18, 18, 3), 0.25, np.float32)
+    p = P.Patch(1, [0, 1], tc, img, [0, 0, 17, 17])
+    out, validity, blending = P.adjust_colors(p, np.full((6, 3), 0.125, np.float32))
+    inside = blending == 255
+    assert inside.sum() > 40 and np.all(validity[inside] == 255)
+    assert np.allclose(out[validity == 255], 0.375, atol=1e-6)       # image + constant everywhere it is valid
+    assert np.all(out[validity == 0] == 0)                           # untouched pixels are zeroed (:110-114)
+    ring = blending == 64                                             # <= sqrt(2) px outside: extrapolated
+    assert ring.sum() > 10 and np.all(validity[ring] == 255)
+    assert not validity[0, 0] and not validity[17, 17]
+    # linear ramp a(x,y) = 0.01 x - 0.02 y + 0.3 is reproduced exactly by barycentric interpolation,
+    # also on the extrapolated ring
+    ramp = lambda q: (0.01 * q[:, 0] - 0.02 * q[:, 1] + 0.3).astype(np.float32)
+    adj = np.repeat(ramp(tc)[:, None], 3, 1).astype(np.float32)
+    out, validity, blending = P.adjust_colors(p, adj)
+    ys, xs = np.nonzero(validity)
+    expect = 0.25 + 0.01 * xs - 0.02 * ys + 0.3
+    assert np.allclose(out[ys, xs, 0], expect, atol=2e-5)
+
+
+def test_global_seam_leveling_reduces_seam_differences(orc, scene_mod, oracle_pipeline, get_scene):
+    """End to end on the oracle: apply the solved offsets to the texture patches (adjust_colors) and
+    re-measure the colour differences across the seams -- the quantity the solve minimises."""
+    import patches as P
+    name = "small"
+    s = get_scene(name)
+    r = oracle_pipeline(name)
+    o, labels = r["seam"], r["mrf"]["labels"]
+    rhs0, patches, vpi = P.seam_rhs_from_patches(orc, s, r["adj"], r["rings"], labels, o["row_ptr"], o["row_label"])
+    adjusted = P.apply_adjust_values(s, patches, o["row_ptr"], o["row_label"], o["x"])
+    for q in adjusted:   # every face corner lies in the valid area of its adjusted patch
+        xi = np.clip(np.floor(q.texcoords[:, 0]).astype(int), 0, q.image.shape[1] - 1)
+        yi = np.clip(np.floor(q.texcoords[:, 1]).astype(int), 0, q.image.shape[0] - 1)
+        assert np.all(q.validity[yi, xi] == 255)
+    # same seam measurement on the adjusted patch images
+    P_generate = P.generate_texture_patches
+    try:
+        P.generate_texture_patches = lambda *a, **k: (adjusted, vpi)
+        rhs1, _, _ = P.seam_rhs_from_patches(orc, s, r["adj"], r["rings"], labels, o["row_ptr"], o["row_label"])
+    finally:
+        P.generate_texture_patches = P_generate
+    n0, n1 = np.linalg.norm(rhs0), np.linalg.norm(rhs1)
+    assert n1 < 0.35 * n0, (n0, n1)
