@@ -288,3 +288,192 @@ def apply_adjust_values(scene, patches, row_ptr, row_label, x):
         q.validity, q.blending = validity, blending
         out.append(q)
     return out
+
+
+# =====================================================================================================
+# local seam leveling (libs/tex/local_seam_leveling.cpp:105-204, poisson_blending.cpp:49-138,
+# texture_patch.cpp:171-178,180-192,197-297, seam_leveling.cpp:16-59)
+# Eigen::SparseLU<.., COLAMDOrdering> is absent: scipy.sparse.linalg.splu stands in (a direct solve of the
+# same fp32 system; results agree up to rounding).  Small scenes only (pure Python loops).
+# =====================================================================================================
+STRIP_SIZE = 20  # local_seam_leveling.cpp:18
+
+
+def find_seam_edges(scene, adj, labels):
+    """seam_leveling.cpp:16-59: one MeshEdge (v1 < v2) per pair of adjacent faces with different labels"""
+    adj_ptr, adj_idx = adj
+    out = []
+    for node in range(scene.num_faces):
+        for a in adj_idx[adj_ptr[node]:adj_ptr[node + 1]]:
+            a = int(a)
+            if node > a or labels[node] == labels[a]:
+                continue
+            shared = [int(v) for v in scene.faces[node] if v in scene.faces[a]]
+            assert len(shared) == 2 and shared[0] != shared[1]
+            out.append((min(shared), max(shared)))
+    return out
+
+
+def _get_pixel_value(patch, p):
+    return _linear_at(patch.image, f32(p[0]), f32(p[1]))
+
+
+def _set_pixel_value(patch, x, y, color):
+    """TexturePatch::set_pixel_value (texture_patch.cpp:171-178)"""
+    patch.image[y, x] = color
+    patch.blending[y, x] = 128
+
+
+def draw_line(patch, p1, p2, edge_color):
+    """local_seam_leveling.cpp:39-92 (Bresenham with colours interpolated along the edge samples)"""
+    x0, y0 = int(np.floor(f32(p1[0] + f32(0.5)))), int(np.floor(f32(p1[1] + f32(0.5))))
+    x1, y1 = int(np.floor(f32(p2[0] + f32(0.5)))), int(np.floor(f32(p2[1] + f32(0.5))))
+    tdx, tdy = f32(x1 - x0), f32(y1 - y0)
+    length = f32(np.sqrt(f32(f32(tdx * tdx) + f32(tdy * tdy))))
+    dx, dy = abs(x1 - x0), abs(y1 - y0)
+    sx, sy = (1 if x0 < x1 else -1), (1 if y0 < y1 else -1)
+    err = dx - dy
+    x, y = x0, y0
+    while True:
+        tdx, tdy = f32(x1 - x), f32(y1 - y)
+        t = f32(np.sqrt(f32(f32(tdx * tdx) + f32(tdy * tdy))) / length) if length != 0 else f32(0.5)
+        if t < 1.0 and len(edge_color) > 1:
+            idx = int(np.floor(f32(t * f32(len(edge_color) - 1))))
+            color = (f32(f32(1.0) - t) * edge_color[idx] + t * edge_color[idx + 1]).astype(f32)
+        else:
+            color = edge_color[-1]
+        _set_pixel_value(patch, x, y, color)
+        if x == x1 and y == y1:
+            break
+        e2 = 2 * err
+        if e2 > -dy:
+            err -= dy; x += sx
+        if e2 < dx:
+            err += dx; y += sy
+
+
+def prepare_blending_mask(patch, strip_width=STRIP_SIZE):
+    """texture_patch.cpp:197-297: keep a strip of `strip_width` pixels along the valid border"""
+    validity, blending = patch.validity, patch.blending
+    h, w = validity.shape
+    border = set()
+    for y in range(h):
+        for x in range(w):
+            if validity[y, x] == 0:
+                continue
+            if x == 0 or x == w - 1 or y == 0 or y == h - 1:
+                border.add((x, y)); continue
+            if np.any(validity[y - 1:y + 2, x - 1:x + 2] == 0):
+                border.add((x, y))
+    inner = validity.copy()
+    for _ in range(strip_width):
+        new_invalid = sorted(border)
+        border = set()
+        for x, y in new_invalid:
+            inner[y, x] = 0
+        for x, y in new_invalid:
+            for j in (-1, 0, 1):
+                for i in (-1, 0, 1):
+                    nx, ny = x + i, y + j
+                    if 0 <= nx < w and 0 <= ny < h and inner[ny, nx] == 255:
+                        border.add((nx, ny))
+    for y in range(1, h - 1):          # sanitize: a 128 pixel surrounded by 255 becomes 255
+        for x in range(1, w - 1):
+            if blending[y, x] == 128 and all(v == 255 for v in (blending[y, x - 1], blending[y, x + 1],
+                                                                 blending[y - 1, x], blending[y + 1, x])):
+                blending[y, x] = 255
+    blending[inner == 255] = 0
+    for x, y in border:
+        blending[y, x] = 128
+
+
+def poisson_blend(src, mask, dest, alpha=1.0):
+    """poisson_blending.cpp:49-138: unknown per mask != 0 pixel; identity rows for 128/64, 5-point
+    Laplacian rows for 255; rhs = alpha * lap(src) + (1 - alpha) * lap(dest); solved per channel"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    h, w, _ = dest.shape
+    idx = -np.ones(h * w, np.int64)
+    nzpix = np.flatnonzero(mask.ravel() != 0)
+    idx[nzpix] = np.arange(len(nzpix))
+    n = len(nzpix)
+    if n == 0:
+        return
+    m = mask.ravel()
+    d = dest.reshape(-1, 3)
+    s_ = src.reshape(-1, 3)
+    rows, cols, vals = [], [], []
+    b = np.zeros((n, 3), f32)
+    alpha = f32(alpha)
+    for i in nzpix:
+        r = idx[i]
+        if m[i] in (128, 64):
+            rows.append(r); cols.append(r); vals.append(1.0)
+            b[r] = d[i]
+        if m[i] == 255:
+            nb = [i - w, i - 1, i, i + 1, i + w]
+            assert all(idx[k] != -1 for k in nb)                     # poisson_blending.cpp:98
+            for k, v in zip(nb, (1.0, 1.0, -4.0, 1.0, 1.0)):
+                rows.append(r); cols.append(idx[k]); vals.append(v)
+            lap = lambda im: (f32(-4.0) * im[i] + im[i - w] + im[i - 1] + im[i + 1] + im[i + w]).astype(f32)
+            b[r] = (alpha * lap(s_) + f32(f32(1.0) - alpha) * lap(d)).astype(f32)
+    A = sp.csc_matrix((np.array(vals, f32), (np.array(rows), np.array(cols))), shape=(n, n))
+    lu = spl.splu(A.astype(np.float64))
+    for ch in range(3):
+        x = lu.solve(b[:, ch].astype(np.float64)).astype(f32)
+        d[nzpix, ch] = x
+
+
+def local_seam_leveling(scene, adj, labels, patches, vpi):
+    """local_seam_leveling.cpp:105-204 on patches that went through adjust_colors (they carry .validity
+    and .blending).  Mutates the patch images; returns the list of seam edges."""
+    seam_edges = find_seam_edges(scene, adj, labels)
+    lines = [[] for _ in patches]
+    pixels = [[] for _ in patches]
+    for (v1, v2) in seam_edges:
+        infos = find_mesh_edge_projections(vpi, v1, v2)
+        max_length = f32(1.0)
+        for pid, p1, p2 in infos:
+            d = (p1 - p2).astype(f32)
+            max_length = max(max_length, f32(np.sqrt(f32(f32(d[0] * d[0]) + f32(d[1] * d[1])))))
+        n = int(np.ceil(f32(max_length * f32(2.0))))
+        edge_color = []
+        for j in range(n):
+            t = f32(f32(j) / f32(n - 1))
+            acc, wsum = np.zeros(3, f32), f32(0)
+            for pid, p1, p2 in infos:                                    # mean_color_of_edge_point :20-37
+                if patches[pid].label == 0:
+                    continue
+                pix = ((p1 * t).astype(f32) + (f32(f32(1.0) - t) * p2).astype(f32)).astype(f32)
+                acc = (acc + _get_pixel_value(patches[pid], pix)).astype(f32); wsum = f32(wsum + 1)
+            edge_color.append((acc / wsum).astype(f32))
+        for pid, p1, p2 in infos:
+            lines[pid].append(((p1 + f32(0.5)).astype(f32), (p2 + f32(0.5)).astype(f32), edge_color))
+    vertex_colors = {}
+    for v in range(scene.verts.shape[0]):                                # :155-176
+        if len(vpi[v]) <= 1:
+            continue
+        acc, wsum = np.zeros(3, f32), f32(0)
+        for pid, (proj, _faces) in sorted(vpi[v].items()):
+            if patches[pid].label == 0:
+                continue
+            acc = (acc + _get_pixel_value(patches[pid], proj)).astype(f32); wsum = f32(wsum + 1)
+        if wsum == 0:
+            continue
+        vertex_colors[v] = (acc / wsum).astype(f32)
+        for pid, (proj, _faces) in sorted(vpi[v].items()):
+            q = (proj + f32(0.5)).astype(f32)
+            pixels[pid].append((int(q[0]), int(q[1]), vertex_colors[v]))   # math::Vec2i(Vec2f): truncation
+    for pid, patch in enumerate(patches):                                # :179-203
+        orig = patch.image.copy()
+        for x, y, col in pixels[pid]:
+            _set_pixel_value(patch, x, y, col)
+        for (a, b_, col) in lines[pid]:
+            # Line.from/to are Vec2i: the +0.5 shifted projections are truncated, draw_line then takes
+            # floor(p + 0.5) of those integers (identity)
+            draw_line(patch, np.array([int(a[0]), int(a[1])], f32), np.array([int(b_[0]), int(b_[1])], f32), col)
+        if patch.label != 0:
+            prepare_blending_mask(patch, STRIP_SIZE)
+        poisson_blend(orig, patch.blending, patch.image, 1.0)             # TexturePatch::blend :180-192
+        patch.validity[patch.blending == 64] = 0
+    return seam_edges

@@ -491,3 +491,61 @@ def test_global_seam_leveling_reduces_seam_differences(orc, scene_mod, oracle_pi
         P.generate_texture_patches = P_generate
     n0, n1 = np.linalg.norm(rhs0), np.linalg.norm(rhs1)
     assert n1 < 0.35 * n0, (n0, n1)
+
+
+def test_poisson_blend_known_answers():
+    """poisson_blending.cpp:49-138: with alpha = 1 the interior takes the source's Laplacian; Dirichlet
+    pixels (mask 128/64) keep the destination's values."""
+    import patches as P
+    rng = np.random.RandomState(2)
+    src = rng.uniform(0.2, 0.8, size=(14, 16, 3)).astype(np.float32)
+    mask = np.zeros((14, 16), np.uint8)
+    mask[2:12, 2:14] = 128
+    mask[3:11, 3:13] = 255
+    dest = src.copy()
+    P.poisson_blend(src, mask, dest, 1.0)
+    assert np.allclose(dest, src, atol=2e-5)                       # same boundary, same Laplacian -> same image
+    dest = src.copy()
+    ring = mask == 128
+    dest[ring] += np.float32(0.1)                                   # shift the Dirichlet ring by a constant
+    P.poisson_blend(src, mask, dest, 1.0)
+    assert np.allclose(dest[mask == 255], src[mask == 255] + 0.1, atol=5e-5)
+    assert np.allclose(dest[mask == 0], src[mask == 0])            # pixels outside the mask are untouched
+
+
+def test_local_seam_leveling_makes_patches_agree_on_seams(orc, scene_mod, oracle_pipeline, get_scene):
+    """local_seam_leveling.cpp:105-204 after global leveling: on every seam edge the two patches hold the
+    same colours along the projected edge (they are overwritten with the mean), and the blend only touches
+    the 20-pixel strip."""
+    import patches as P
+    name = "tiny"
+    s = get_scene(name)
+    r = oracle_pipeline(name)
+    o, labels = r["seam"], r["mrf"]["labels"]
+    patches, vpi = P.generate_texture_patches(orc, s, r["adj"], labels)
+    patches = P.apply_adjust_values(s, patches, o["row_ptr"], o["row_label"], o["x"])
+    before = [p.image.copy() for p in patches]
+    seam_edges = P.find_seam_edges(s, r["adj"], labels)
+    assert len(seam_edges) > 10
+
+    def seam_gap(ps):
+        gaps = []
+        for v1, v2 in seam_edges:
+            infos = P.find_mesh_edge_projections(vpi, v1, v2)
+            if len(infos) != 2:
+                continue
+            cols = []
+            for pid, p1, p2 in infos:   # colour at the stamped pixel of the edge midpoint
+                mid = ((p1 + p2) * np.float32(0.5)).astype(np.float32) + np.float32(0.5)
+                cols.append(ps[pid].image[int(mid[1]), int(mid[0])])
+            gaps.append(np.abs(cols[0] - cols[1]).max())
+        return np.array(gaps)
+
+    g0 = seam_gap(patches)
+    P.local_seam_leveling(s, r["adj"], labels, patches, vpi)
+    g1 = seam_gap(patches)
+    assert len(g1) > 10 and np.median(g1) < 0.25 * np.median(g0) and np.median(g1) < 0.02
+    for p, b in zip(patches, before):
+        changed = np.abs(p.image - b).max(axis=2) > 1e-6
+        assert not np.any(changed & (p.blending == 0))             # only masked pixels are re-solved
+        assert np.isfinite(p.image).all()
