@@ -260,6 +260,34 @@ def sphere_scene(nu, k, width, height, displace=0.0, dist=3.0, fill=0.8, axis_ca
     return _assemble(name, V, F, cams, width, height, with_images)
 
 
+def occluder_scene(nu, k, width, height, plates=5, displace=0.05, dist=3.0, name="occ", with_images=True):
+    """Displaced sphere plus `plates` floating square plates (2 large triangles each, facing outwards) at
+    radius 1.7: every plate hides part of the sphere from the cameras behind it, so the geometric
+    visibility test (calculate_data_costs.cpp:194-215) rejects faces that pass all other culls, and the
+    BVH holds triangles of very different sizes."""
+    V, F = icosphere(nu, displace)
+    V = V.astype(np.float64)
+    Vs, Fs = [V], [F.astype(np.int64)]
+    base = len(V)
+    for d in fibonacci_dirs(plates) * np.array([1.0, 1.0, 0.6]):
+        d = d / np.linalg.norm(d)
+        a = np.cross(d, [0.0, 0.0, 1.0] if abs(d[2]) < 0.9 else [1.0, 0.0, 0.0])
+        a /= np.linalg.norm(a)
+        b = np.cross(d, a)
+        c = d * 1.7
+        h = 0.4
+        quad = np.stack([c - h * a - h * b, c + h * a - h * b, c + h * a + h * b, c - h * a + h * b])
+        Vs.append(quad)
+        Fs.append(np.array([[0, 1, 2], [0, 2, 3]], np.int64) + base)   # normal = a x b = +d (outwards)
+        base += 4
+    V = np.concatenate(Vs, 0).astype(np.float32)
+    F = np.concatenate(Fs, 0).astype(np.uint32)
+    half = 0.8 * min(width, height) / 2.0
+    flen = half / np.tan(np.arcsin(min(0.99, 2.0 / dist)))
+    cams = [look_at_camera(dd * dist, (0, 0, 0), flen, width, height) for dd in fibonacci_dirs(k)]
+    return _assemble(name, V, F, cams, width, height, with_images)
+
+
 def terrain_scene(n, k, width, height, dist=3.2, name="terrain", with_images=True):
     V, F = terrain(n)
     dirs = fibonacci_dirs(k, hemisphere=True)
@@ -274,6 +302,10 @@ def config(name: str, with_images=True) -> Scene:
         return sphere_scene(4, 6, 160, 120, axis_cams=True, name=name, with_images=with_images)
     if name == "small":     # 2 000 faces, 12 views
         return sphere_scene(10, 12, 320, 240, displace=0.05, name=name, with_images=with_images)
+    if name == "occ":       # 2 010 faces, 12 views, floating plates: real occlusion
+        return occluder_scene(10, 12, 320, 240, plates=9, name=name, with_images=with_images)
+    if name == "occ2":      # 32 030 faces, 24 views
+        return occluder_scene(40, 24, 640, 480, plates=15, name=name, with_images=with_images)
     if name == "C1":
         return sphere_scene(22, 6, 640, 480, axis_cams=True, name=name, with_images=with_images)
     if name == "C1d":       # C1 with displacement + more views: exercises occlusion

@@ -1,0 +1,187 @@
+/* oracle/ref_glue.cpp -- TEST INFRASTRUCTURE (see oracle.h, refshim/README.md).
+ *
+ * C entry points over the reference's own translation units (compiled unmodified from
+ * /root/reference/libs/tex against the dependency shims in oracle/refshim/), so that tests can pin
+ * the oracle's restatement against the code it restates.  Built by `make -C oracle ref` into
+ * oracle/_ref/libtexref.so; never linked or loaded by the product path.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <string>
+
+#include "oracle.h"
+
+#include "tex/texturing.h"
+#include "tex/histogram.h"
+#include "tex/tri.h"
+
+namespace mve { namespace image {
+std::map<std::string, ByteImage::Ptr>& refshim_registry() {
+    static std::map<std::string, ByteImage::Ptr> reg;
+    return reg;
+}
+} }
+
+namespace {
+
+std::string view_name(uint32_t j) { std::ostringstream s; s << "refshim://view/" << j; return s.str(); }
+
+/* tex::TextureView from the flat view record (texture_view.cpp:20-40 via the CameraInfo shim) */
+void make_views(const orc_view* views, uint32_t num_views, tex::TextureViews* out) {
+    out->clear();
+    out->reserve(num_views);
+    for (uint32_t j = 0; j < num_views; ++j) {
+        const orc_view& v = views[j];
+        mve::ByteImage::Ptr img = mve::ByteImage::create(v.width, v.height, 3);
+        std::memcpy(img->get_data_pointer(), v.rgb, static_cast<std::size_t>(v.width) * v.height * 3);
+        mve::image::refshim_registry()[view_name(j)] = img;
+        mve::CameraInfo cam;
+        std::memcpy(cam.calibration, v.proj, sizeof(cam.calibration));
+        std::memcpy(cam.position, v.pos, sizeof(cam.position));
+        std::memcpy(cam.viewdir, v.viewdir, sizeof(cam.viewdir));
+        std::memcpy(cam.world_to_cam, v.w2c, sizeof(cam.world_to_cam));
+        out->push_back(tex::TextureView(j, cam, view_name(j)));
+    }
+}
+
+mve::TriangleMesh::Ptr make_mesh(const float* verts, uint32_t num_verts, const uint32_t* faces,
+                                 const float* face_normals, uint32_t num_faces) {
+    mve::TriangleMesh::Ptr mesh = mve::TriangleMesh::create();
+    mesh->get_vertices().resize(num_verts);
+    for (uint32_t i = 0; i < num_verts; ++i) mesh->get_vertices()[i] = math::Vec3f(verts + 3 * static_cast<std::size_t>(i));
+    mesh->get_faces().assign(faces, faces + 3 * static_cast<std::size_t>(num_faces));
+    if (face_normals) {
+        mesh->get_face_normals().resize(num_faces);
+        for (uint32_t i = 0; i < num_faces; ++i) mesh->get_face_normals()[i] = math::Vec3f(face_normals + 3 * static_cast<std::size_t>(i));
+    }
+    return mesh;
+}
+
+tex::Settings make_settings(const orc_settings* st) {
+    tex::Settings s;
+    s.data_term = st->data_term == 0 ? tex::DATA_TERM_AREA : tex::DATA_TERM_GMI;
+    s.outlier_removal = st->outlier_removal == 0 ? tex::OUTLIER_REMOVAL_NONE
+        : (st->outlier_removal == 1 ? tex::OUTLIER_REMOVAL_GAUSS_DAMPING : tex::OUTLIER_REMOVAL_GAUSS_CLAMPING);
+    s.geometric_visibility_test = st->geometric_visibility_test != 0;
+    return s;
+}
+
+/* stdout of the reference (progress counters, timings) is noise for the tests */
+struct Quiet {
+    std::streambuf* old;
+    std::ostringstream sink;
+    Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
+    ~Quiet() { std::cout.rdbuf(old); }
+};
+
+}  // namespace
+
+extern "C" {
+
+void ref_free(void* p) { std::free(p); }
+
+/* tex::calculate_data_costs (calculate_data_costs.cpp:308-323), result flattened to the CSR the
+ * oracle returns: per face, entries in DataCosts::col(face) order (ascending view after :273). */
+int ref_data_costs(const float* verts, uint32_t num_verts, const uint32_t* faces, const float* face_normals,
+                   uint32_t num_faces, const orc_view* views, uint32_t num_views, const orc_settings* st,
+                   uint64_t* face_ptr, uint16_t** view_out, float** cost_out)
+{
+    try {
+        Quiet q;
+        mve::TriangleMesh::Ptr mesh = make_mesh(verts, num_verts, faces, face_normals, num_faces);
+        tex::TextureViews tvs;
+        make_views(views, num_views, &tvs);
+        tex::Settings settings = make_settings(st);
+        tex::DataCosts data_costs(num_faces, num_views);
+        tex::calculate_data_costs(mesh, &tvs, settings, &data_costs);
+        std::size_t nnz = data_costs.get_nnz();
+        uint16_t* vw = static_cast<uint16_t*>(std::malloc(sizeof(uint16_t) * (nnz ? nnz : 1)));
+        float* cs = static_cast<float*>(std::malloc(sizeof(float) * (nnz ? nnz : 1)));
+        uint64_t o = 0;
+        for (uint32_t f = 0; f < num_faces; ++f) {
+            face_ptr[f] = o;
+            tex::DataCosts::Column const& col = data_costs.col(f);
+            for (std::size_t k = 0; k < col.size(); ++k) { vw[o] = col[k].first; cs[o] = col[k].second; ++o; }
+        }
+        face_ptr[num_faces] = o;
+        *view_out = vw; *cost_out = cs;
+        return 0;
+    } catch (std::exception& e) {
+        std::fprintf(stderr, "ref_data_costs: %s\n", e.what());
+        return 1;
+    }
+}
+
+/* TextureView::generate_validity_mask [+ erode_validity_mask] (texture_view.cpp:42-94,109-132), read
+ * back through export_validity_mask (:305-313) */
+int ref_validity_mask(const orc_view* view, int erode, uint8_t* mask_out)
+{
+    Quiet q;
+    tex::TextureViews tvs;
+    make_views(view, 1, &tvs);
+    tvs[0].load_image();
+    tvs[0].generate_validity_mask();
+    if (erode) tvs[0].erode_validity_mask();
+    tvs[0].export_validity_mask("refshim://mask");
+    mve::ByteImage::Ptr m = mve::image::refshim_registry()["refshim://mask"];
+    for (int i = 0; i < m->get_pixel_amount(); ++i) mask_out[i] = m->at(i) ? 1 : 0;
+    return 0;
+}
+
+/* TextureView::get_pixel_coords (texture_view.h:161-166) */
+void ref_pixel_coords(const orc_view* view, const float x[3], float out[2])
+{
+    tex::TextureViews tvs;
+    make_views(view, 1, &tvs);
+    math::Vec2f p = tvs[0].get_pixel_coords(math::Vec3f(x));
+    out[0] = p[0]; out[1] = p[1];
+}
+
+/* TextureView::get_face_info (texture_view.cpp:134-251) for a batch of world-space triangles of one
+ * view; with_mask = generate (and for GMI erode) the validity mask first, as calculate_data_costs does.
+ * quality_out[i] = NaN when the triangle does not project inside the view (get_face_info asserts). */
+int ref_face_infos(const orc_view* view, int data_term, int outlier_removal, const float* tris /* n x 9 */, uint32_t n,
+                   float* quality_out, float* mean_color_out /* n x 3 or NULL */)
+{
+    Quiet q;
+    tex::TextureViews tvs;
+    make_views(view, 1, &tvs);
+    tex::TextureView& tv = tvs[0];
+    orc_settings os = { data_term, outlier_removal, 0, 0, 0 };
+    tex::Settings settings = make_settings(&os);
+    tv.load_image();
+    tv.generate_validity_mask();
+    if (settings.data_term == tex::DATA_TERM_GMI) { tv.generate_gradient_magnitude(); tv.erode_validity_mask(); }
+    for (uint32_t i = 0; i < n; ++i) {
+        math::Vec3f v1(tris + 9 * i), v2(tris + 9 * i + 3), v3(tris + 9 * i + 6);
+        if (!tv.inside(v1, v2, v3)) { quality_out[i] = std::numeric_limits<float>::quiet_NaN(); continue; }
+        tex::FaceProjectionInfo info = { 0, 0.0f, math::Vec3f(0.0f, 0.0f, 0.0f) };
+        tv.get_face_info(v1, v2, v3, &info, settings);
+        quality_out[i] = info.quality;
+        if (mean_color_out) for (int k = 0; k < 3; ++k) mean_color_out[3 * i + k] = info.mean_color[k];
+    }
+    return 0;
+}
+
+/* Tri (tri.h:50-84, tri.cpp:12-24) */
+float ref_tri_area(const float p1[2], const float p2[2], const float p3[2])
+{
+    return Tri(math::Vec2f(p1), math::Vec2f(p2), math::Vec2f(p3)).get_area();
+}
+int ref_tri_inside(const float p1[2], const float p2[2], const float p3[2], float x, float y)
+{
+    return Tri(math::Vec2f(p1), math::Vec2f(p2), math::Vec2f(p3)).inside(x, y) ? 1 : 0;
+}
+
+/* Histogram (histogram.cpp:22-63) used as calculate_data_costs.cpp:283-288 does */
+float ref_histogram_percentile(const float* values, uint64_t n, float vmax, int bins, float p)
+{
+    Histogram h(0.0f, vmax, static_cast<std::size_t>(bins));
+    for (uint64_t i = 0; i < n; ++i) h.add_value(values[i]);
+    return h.get_approx_percentile(p);
+}
+
+}  // extern "C"

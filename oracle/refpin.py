@@ -1,0 +1,122 @@
+"""ctypes binding of oracle/_ref/libtexref.so -- TEST INFRASTRUCTURE.
+
+libtexref.so = the reference's own translation units (compiled unmodified from /root/reference/libs/tex)
++ the dependency shims in oracle/refshim/ + oracle/ref_glue.cpp.  It exists to pin the oracle: tests compare
+oracle results with the code the oracle restates.  /root/reference is only present in the build container;
+on the GPU box the prebuilt .so (git-ignored, not gpurun-ignored) is used as is.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import oracle as O
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libtexref.so")
+REFERENCE = os.environ.get("B2TEX_REFERENCE", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.exists(_SO) or os.path.isdir(os.path.join(REFERENCE, "libs", "tex"))
+
+
+def build() -> str | None:
+    """(Re)build when the reference sources are here; otherwise use the prebuilt library if there is one."""
+    if os.path.isdir(os.path.join(REFERENCE, "libs", "tex")):
+        O.build()
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", f"REF={REFERENCE}"])
+    return _SO if os.path.exists(_SO) else None
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = build()
+        if so is None:
+            raise RuntimeError("oracle/_ref/libtexref.so missing and no reference checkout to build it from")
+        O.lib()
+        _lib = C.CDLL(so)
+        _lib.ref_tri_area.restype = C.c_float
+        _lib.ref_histogram_percentile.restype = C.c_float
+    return _lib
+
+
+_p = O._p
+
+
+def data_costs(scene, data_term=1, visibility=True, outlier_removal=0, images=None):
+    L = lib()
+    views, keep = O.make_views(scene, images)
+    st = O.Settings(data_term, outlier_removal, 1 if visibility else 0, 0, 0)
+    F = scene.num_faces
+    face_ptr = np.zeros(F + 1, np.uint64)
+    vw, cs = C.c_void_p(), C.c_void_p()
+    rc = L.ref_data_costs(_p(scene.verts), C.c_uint32(scene.verts.shape[0]), _p(scene.faces), _p(scene.face_normals),
+                          C.c_uint32(F), views, C.c_uint32(scene.num_views), C.byref(st), _p(face_ptr),
+                          C.byref(vw), C.byref(cs))
+    if rc:
+        raise RuntimeError(f"ref_data_costs rc={rc}")
+    n = int(face_ptr[-1])
+    view = np.ctypeslib.as_array(C.cast(vw, C.POINTER(C.c_uint16)), (max(n, 1),))[:n].copy()
+    cost = np.ctypeslib.as_array(C.cast(cs, C.POINTER(C.c_float)), (max(n, 1),))[:n].copy()
+    L.ref_free(vw); L.ref_free(cs)
+    return dict(face_ptr=face_ptr, view=view, cost=cost)
+
+
+def _one_view(scene, k, image=None):
+    v = O.View()
+    v.pos[:] = scene.pos[k].tolist(); v.viewdir[:] = scene.viewdir[k].tolist()
+    v.proj[:] = scene.proj[k].tolist(); v.w2c[:] = scene.w2c[k].tolist()
+    img = np.ascontiguousarray(scene.images[k] if image is None else image)
+    v.height, v.width = img.shape[0], img.shape[1]
+    v.rgb = img.ctypes.data
+    return v, img
+
+
+def validity_mask(rgb, erode=False):
+    h, w, _ = rgb.shape
+    v = O.View()
+    rgb = np.ascontiguousarray(rgb)
+    v.width, v.height, v.rgb = w, h, rgb.ctypes.data
+    m = np.empty((h, w), np.uint8)
+    lib().ref_validity_mask(C.byref(v), 1 if erode else 0, _p(m))
+    return m
+
+
+def face_infos(scene, k, tris, data_term=1, outlier_removal=0, image=None):
+    v, keep = _one_view(scene, k, image)
+    tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+    q = np.empty(len(tris), np.float32)
+    mc = np.zeros((len(tris), 3), np.float32)
+    lib().ref_face_infos(C.byref(v), data_term, outlier_removal, _p(tris), C.c_uint32(len(tris)), _p(q), _p(mc))
+    return q, mc
+
+
+def pixel_coords(scene, k, x):
+    v, keep = _one_view(scene, k)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty(2, np.float32)
+    lib().ref_pixel_coords(C.byref(v), _p(x), _p(out))
+    return out
+
+
+def tri_area(p1, p2, p3):
+    a = [np.ascontiguousarray(p, np.float32) for p in (p1, p2, p3)]
+    return float(lib().ref_tri_area(_p(a[0]), _p(a[1]), _p(a[2])))
+
+
+def tri_inside(p1, p2, p3, x, y):
+    a = [np.ascontiguousarray(p, np.float32) for p in (p1, p2, p3)]
+    return int(lib().ref_tri_inside(_p(a[0]), _p(a[1]), _p(a[2]), C.c_float(x), C.c_float(y)))
+
+
+def histogram_percentile(values, vmax, bins=10000, p=0.995):
+    v = np.ascontiguousarray(values, np.float32)
+    return float(lib().ref_histogram_percentile(_p(v), C.c_uint64(len(v)), C.c_float(vmax), bins, C.c_float(p)))

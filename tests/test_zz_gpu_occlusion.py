@@ -1,0 +1,31 @@
+"""-m gpu: data costs and view selection on scenes with REAL occlusion (`occ`: floating plates in front of a displaced
+sphere; ~30 % of the culled candidates fail the geometric visibility test, calculate_data_costs.cpp:194-215).
+
+Named zz so that it runs after the rest of the GPU suite: it was written after this round's GPU budget was spent
+and has only been checked through the host emulation of the same kernels (tests/test_cuda_emulation.py).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["occ", "occ2"])
+def test_data_costs_with_occlusion_bit_exact(b2, get_scene, orc, name):
+    s = get_scene(name)
+    o = orc.data_costs(s)
+    o_novis = orc.data_costs(s, visibility=False)
+    assert len(o["view"]) < 0.9 * len(o_novis["view"])            # the scene really occludes
+    c = b2.Context(0)
+    c.set_scene(s)
+    info = c.data_costs_run()
+    g = c.data_costs_download(info.nnz, quality=True)
+    assert info.nnz == len(o["view"])
+    assert np.array_equal(g["face_ptr"], o["face_ptr"])
+    assert np.array_equal(g["view"], o["view"])
+    assert np.array_equal(g["quality"].view(np.uint32), o["quality"].view(np.uint32))
+    assert np.array_equal(g["cost"].view(np.uint32), o["cost"].view(np.uint32))
+    info2 = c.data_costs_run(visibility=False)
+    g2 = c.data_costs_download(info2.nnz)
+    assert np.array_equal(g2["face_ptr"], o_novis["face_ptr"]) and np.array_equal(g2["view"], o_novis["view"])
+    c.close()
