@@ -19,7 +19,7 @@ def ref():
     return refpin
 
 
-@pytest.mark.parametrize("name", ["tiny", "small"])
+@pytest.mark.parametrize("name", ["tiny", "small", "occ"])
 @pytest.mark.parametrize("data_term", [1, 0])
 def test_data_costs_match_reference_tu(ref, orc, get_scene, name, data_term):
     """tex::calculate_data_costs (calculate_data_costs.cpp:131-323) vs orc_data_costs: same (face, view) set,
@@ -33,7 +33,7 @@ def test_data_costs_match_reference_tu(ref, orc, get_scene, name, data_term):
     assert np.array_equal(r["cost"].view(np.uint32), o["cost"].view(np.uint32))
 
 
-@pytest.mark.parametrize("name", ["tiny", "C1d"])
+@pytest.mark.parametrize("name", ["tiny", "occ"])
 def test_data_costs_without_visibility_test(ref, orc, get_scene, name):
     s = get_scene(name)
     r = ref.data_costs(s, visibility=False)
@@ -42,7 +42,7 @@ def test_data_costs_without_visibility_test(ref, orc, get_scene, name):
     assert np.array_equal(r["cost"].view(np.uint32), o["cost"].view(np.uint32))
     with_test = ref.data_costs(s)
     assert int(r["face_ptr"][-1]) >= int(with_test["face_ptr"][-1])
-    if name == "C1d":                                                    # displaced sphere: bumps occlude
+    if name == "occ":                                                    # floating plates occlude
         assert int(r["face_ptr"][-1]) > int(with_test["face_ptr"][-1])
         o2 = orc.data_costs(s)
         assert np.array_equal(with_test["face_ptr"], o2["face_ptr"]) and np.array_equal(with_test["view"], o2["view"])
