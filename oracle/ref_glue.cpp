@@ -17,6 +17,9 @@
 #include "tex/texturing.h"
 #include "tex/histogram.h"
 #include "tex/tri.h"
+#include "mapmap/full.h"
+
+namespace mapmap { Capture& refshim_capture() { static Capture c; return c; } }
 
 namespace mve { namespace image {
 std::map<std::string, ByteImage::Ptr>& refshim_registry() {
@@ -182,6 +185,93 @@ float ref_histogram_percentile(const float* values, uint64_t n, float vmax, int 
     Histogram h(0.0f, vmax, static_cast<std::size_t>(bins));
     for (uint64_t i = 0; i < n; ++i) h.add_value(values[i]);
     return h.get_approx_percentile(p);
+}
+
+/* mve::MeshInfo from the per-vertex rings (the arrays b2tex_set_vertex_rings takes) */
+static void fill_mesh_info(uint32_t num_verts, const uint32_t* vf_ptr, const uint32_t* vf_idx, const uint32_t* vv_ptr,
+                           const uint32_t* vv_idx, mve::MeshInfo* mi)
+{
+    mi->resize(num_verts);
+    for (uint32_t v = 0; v < num_verts; ++v) {
+        (*mi)[v].vclass = mve::MeshInfo::VERTEX_CLASS_SIMPLE;
+        (*mi)[v].faces.assign(vf_idx + vf_ptr[v], vf_idx + vf_ptr[v + 1]);
+        (*mi)[v].verts.assign(vv_idx + vv_ptr[v], vv_idx + vv_ptr[v + 1]);
+    }
+}
+
+/* tex::build_adjacency_graph (build_adjacency_graph.cpp:16-53): adjacency lists flattened to CSR in
+ * UniGraph order.  adj_idx_out is malloc'd. */
+int ref_build_adjacency(const uint32_t* faces, uint32_t num_faces, uint32_t num_verts, const uint32_t* vf_ptr, const uint32_t* vf_idx,
+                        const uint32_t* vv_ptr, const uint32_t* vv_idx, uint32_t* adj_ptr, uint32_t** adj_idx_out)
+{
+    Quiet q;
+    mve::TriangleMesh::Ptr mesh = mve::TriangleMesh::create();
+    mesh->get_faces().assign(faces, faces + 3 * static_cast<std::size_t>(num_faces));
+    mve::MeshInfo mi;
+    fill_mesh_info(num_verts, vf_ptr, vf_idx, vv_ptr, vv_idx, &mi);
+    tex::Graph graph(num_faces);
+    tex::build_adjacency_graph(mesh, mi, &graph);
+    adj_ptr[0] = 0;
+    for (uint32_t f = 0; f < num_faces; ++f) adj_ptr[f + 1] = adj_ptr[f] + static_cast<uint32_t>(graph.get_adj_nodes(f).size());
+    uint32_t* idx = static_cast<uint32_t*>(std::malloc(sizeof(uint32_t) * (adj_ptr[num_faces] ? adj_ptr[num_faces] : 1)));
+    for (uint32_t f = 0; f < num_faces; ++f) {
+        std::vector<std::size_t> const& a = graph.get_adj_nodes(f);
+        for (std::size_t k = 0; k < a.size(); ++k) idx[adj_ptr[f] + k] = static_cast<uint32_t>(a[k]);
+    }
+    *adj_idx_out = idx;
+    return 0;
+}
+
+/* tex::view_selection (view_selection.cpp:18-133) with the recording mapMAP shim: returns the model it
+ * built and the labels it decoded from the shim's trivial solution.  All out arrays are malloc'd.
+ * params_out: [potts, window, ratio, seed, deterministic, tree_algorithm, use_multilevel, use_spanning_tree,
+ *              use_acyclic, multilevel_after, force_acyclic, min_acyclic_iterations, relax_acyclic_maximal,
+ *              components_updated, compress, all unaries set exactly once] */
+int ref_view_selection_model(uint32_t num_faces, uint32_t num_views, const uint32_t* adj_ptr, const uint32_t* adj_idx,
+                             const uint64_t* face_ptr, const uint16_t* view, const float* cost,
+                             uint64_t* num_edges_out, uint32_t** edges_out, uint64_t* ls_ptr /* F+1 */, int32_t** ls_label_out,
+                             float** ls_cost_out, uint32_t* labels_out /* F */, double* params_out /* 16 */)
+{
+    try {
+        Quiet q;
+        tex::Graph graph(num_faces);
+        for (uint32_t f = 0; f < num_faces; ++f)        // UniGraph::add_edge appends to both lists: replay in list order
+            for (uint32_t k = adj_ptr[f]; k < adj_ptr[f + 1]; ++k) if (f < adj_idx[k]) graph.add_edge(f, adj_idx[k]);
+        tex::DataCosts data_costs(num_faces, static_cast<uint16_t>(num_views));
+        for (uint32_t f = 0; f < num_faces; ++f)
+            for (uint64_t k = face_ptr[f]; k < face_ptr[f + 1]; ++k) data_costs.set_value(f, view[k], cost[k]);
+        tex::Settings settings;
+        tex::view_selection(data_costs, &graph, settings);
+        mapmap::Capture const& c = mapmap::refshim_capture();
+        *num_edges_out = c.edge_weight.size();
+        uint32_t* e = static_cast<uint32_t*>(std::malloc(sizeof(uint32_t) * (c.edges.size() ? c.edges.size() : 1)));
+        std::copy(c.edges.begin(), c.edges.end(), e);
+        *edges_out = e;
+        ls_ptr[0] = 0;
+        for (uint32_t f = 0; f < num_faces; ++f) ls_ptr[f + 1] = ls_ptr[f] + c.labels[f].size();
+        int32_t* ll = static_cast<int32_t*>(std::malloc(sizeof(int32_t) * (ls_ptr[num_faces] ? ls_ptr[num_faces] : 1)));
+        float* lc = static_cast<float*>(std::malloc(sizeof(float) * (ls_ptr[num_faces] ? ls_ptr[num_faces] : 1)));
+        bool unaries_ok = c.unary_set.size() == num_faces;
+        bool weights_ok = true;
+        for (std::size_t i = 0; i < c.edge_weight.size(); ++i) weights_ok = weights_ok && c.edge_weight[i] == 1.0f;
+        for (uint32_t f = 0; f < num_faces; ++f) {
+            if (c.costs[f].size() != c.labels[f].size()) return 2;
+            for (std::size_t k = 0; k < c.labels[f].size(); ++k) { ll[ls_ptr[f] + k] = c.labels[f][k]; lc[ls_ptr[f] + k] = c.costs[f][k]; }
+            unaries_ok = unaries_ok && c.unary_set[f] == 1;
+            labels_out[f] = static_cast<uint32_t>(graph.get_label(f));
+        }
+        *ls_label_out = ll; *ls_cost_out = lc;
+        double p[16] = { c.potts, double(c.window), c.ratio, double(c.ctr.initial_seed), double(c.ctr.sample_deterministic),
+                         double(c.ctr.tree_algorithm), double(c.ctr.use_multilevel), double(c.ctr.use_spanning_tree), double(c.ctr.use_acyclic),
+                         double(c.ctr.spanning_tree_multilevel_after_n_iterations), double(c.ctr.force_acyclic),
+                         double(c.ctr.min_acyclic_iterations), double(c.ctr.relax_acyclic_maximal), double(c.components_updated),
+                         double(c.compress), double(unaries_ok && weights_ok) };
+        std::copy(p, p + 16, params_out);
+        return 0;
+    } catch (std::exception& e) {
+        std::fprintf(stderr, "ref_view_selection_model: %s\n", e.what());
+        return 1;
+    }
 }
 
 }  // extern "C"

@@ -120,3 +120,47 @@ def tri_inside(p1, p2, p3, x, y):
 def histogram_percentile(values, vmax, bins=10000, p=0.995):
     v = np.ascontiguousarray(values, np.float32)
     return float(lib().ref_histogram_percentile(_p(v), C.c_uint64(len(v)), C.c_float(vmax), bins, C.c_float(p)))
+
+
+def _grab(ptr, ctype, n):
+    a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), (max(n, 1),))[:n].copy()
+    lib().ref_free(ptr)
+    return a
+
+
+def build_adjacency(faces, num_verts, rings):
+    """tex::build_adjacency_graph on the reference's UniGraph -> CSR in adjacency-list order"""
+    vf_ptr, vf_idx, vv_ptr, vv_idx = rings
+    F = faces.shape[0]
+    adj_ptr = np.zeros(F + 1, np.uint32)
+    idx = C.c_void_p()
+    rc = lib().ref_build_adjacency(_p(np.ascontiguousarray(faces, np.uint32)), C.c_uint32(F), C.c_uint32(num_verts), _p(vf_ptr), _p(vf_idx),
+                                   _p(vv_ptr), _p(vv_idx), _p(adj_ptr), C.byref(idx))
+    if rc:
+        raise RuntimeError(f"ref_build_adjacency rc={rc}")
+    return adj_ptr, _grab(idx, C.c_uint32, int(adj_ptr[-1]))
+
+
+PARAM_NAMES = ["potts", "window", "ratio", "seed", "deterministic", "tree_algorithm", "use_multilevel", "use_spanning_tree", "use_acyclic",
+               "multilevel_after", "force_acyclic", "min_acyclic_iterations", "relax_acyclic_maximal", "components_updated", "compress",
+               "model_complete"]
+
+
+def view_selection_model(adj, face_ptr, view, cost, num_views):
+    """tex::view_selection with the recording mapMAP shim: the MRF model it builds + the labels it decodes from the
+    shim's trivial solution (cheapest label per node)."""
+    adj_ptr, adj_idx = adj
+    F = len(face_ptr) - 1
+    ne = C.c_uint64()
+    edges, ll, lc = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    ls_ptr = np.zeros(F + 1, np.uint64)
+    labels = np.zeros(F, np.uint32)
+    params = np.zeros(16, np.float64)
+    rc = lib().ref_view_selection_model(C.c_uint32(F), C.c_uint32(num_views), _p(adj_ptr), _p(adj_idx), _p(face_ptr),
+                                        _p(np.ascontiguousarray(view, np.uint16)), _p(np.ascontiguousarray(cost, np.float32)),
+                                        C.byref(ne), C.byref(edges), _p(ls_ptr), C.byref(ll), C.byref(lc), _p(labels), _p(params))
+    if rc:
+        raise RuntimeError(f"ref_view_selection_model rc={rc}")
+    n = int(ls_ptr[-1])
+    return dict(edges=_grab(edges, C.c_uint32, 2 * int(ne.value)).reshape(-1, 2), ls_ptr=ls_ptr, ls_label=_grab(ll, C.c_int32, n),
+                ls_cost=_grab(lc, C.c_float, n), labels=labels, params=dict(zip(PARAM_NAMES, params.tolist())))

@@ -141,3 +141,76 @@ def test_pixel_coords_match_reference_tu(ref, orc, get_scene):
             out = np.empty(2, np.float32)
             L.orc_pixel_coords(C.byref(v), orc._p(x), orc._p(out))
             assert np.array_equal(ref.pixel_coords(s, k, x).view(np.uint32), out.view(np.uint32))
+
+
+# ---- adjacency graph and MRF model (build_adjacency_graph.cpp, view_selection.cpp) ------------------------------
+@pytest.mark.parametrize("name", ["tiny", "small", "occ", "C2s"])
+def test_adjacency_matches_reference_tu(ref, scene_mod, get_scene, name):
+    """tex::build_adjacency_graph (:16-53) on the reference's UniGraph vs scene.face_adjacency (what the oracle and the
+    C ABI are fed): same neighbours in the same adjacency-list order, borders (C2s) and separate components (occ) included."""
+    s = get_scene(name)
+    rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
+    r_ptr, r_idx = ref.build_adjacency(s.faces, s.verts.shape[0], rings)
+    a_ptr, a_idx = scene_mod.face_adjacency(s.faces)
+    assert np.array_equal(r_ptr, a_ptr) and np.array_equal(r_idx, a_idx)
+
+
+@pytest.mark.parametrize("name", ["tiny", "occ"])
+def test_mrf_model_and_label_decoding_match_reference_tu(ref, orc, scene_mod, get_scene, name):
+    """view_selection.cpp:26-82 builds the model, :120-131 decodes the solution.  With the recording mapMAP shim: edges
+    only between seen faces (i < j, weight 1), label set = view id + 1 in DataCosts column order, unary = data cost, unseen
+    faces get the single label 0 with cost 1, Potts weight 1, StopWhenReturnsDiminish(5, 0.01), deterministic seed
+    548923723.  The oracle's energy function must be the energy of exactly this model."""
+    s = get_scene(name)
+    dc = orc.data_costs(s)
+    if name == "tiny":                                           # make a few faces unseen
+        keep = np.ones(len(dc["view"]), bool)
+        ptr = dc["face_ptr"].astype(np.int64)
+        for f in (3, 17, 18, 200):
+            keep[ptr[f]:ptr[f + 1]] = False
+        cnt = np.add.reduceat(keep.astype(np.int64), ptr[:-1]) * (ptr[1:] > ptr[:-1])
+        dc = dict(face_ptr=np.r_[0, np.cumsum(cnt)].astype(np.uint64), view=dc["view"][keep], cost=dc["cost"][keep])
+    adj = scene_mod.face_adjacency(s.faces)
+    m = ref.view_selection_model(adj, dc["face_ptr"], dc["view"], dc["cost"], s.num_views)
+    F = s.num_faces
+    ptr = dc["face_ptr"].astype(np.int64)
+    seen = ptr[1:] > ptr[:-1]
+    assert (~seen).sum() >= (4 if name == "tiny" else 0)
+    # edges
+    exp = [(i, int(j)) for i in range(F) if seen[i] for j in adj[1][adj[0][i]:adj[0][i + 1]] if i < j and seen[j]]
+    assert [tuple(e) for e in m["edges"].tolist()] == exp
+    # label sets and unaries
+    lp = m["ls_ptr"].astype(np.int64)
+    for f in range(F):
+        ll, lc = m["ls_label"][lp[f]:lp[f + 1]], m["ls_cost"][lp[f]:lp[f + 1]]
+        if seen[f]:
+            assert np.array_equal(ll, dc["view"][ptr[f]:ptr[f + 1]].astype(np.int32) + 1)
+            assert np.array_equal(lc.view(np.uint32), dc["cost"][ptr[f]:ptr[f + 1]].view(np.uint32))
+        else:
+            assert ll.tolist() == [0] and lc.tolist() == [1.0]
+    p = m["params"]
+    assert p["potts"] == 1.0 and p["window"] == 5 and abs(p["ratio"] - 0.01) < 1e-12
+    assert p["seed"] == 548923723 and p["deterministic"] == 1 and p["model_complete"] == 1 and p["components_updated"] == 1
+    assert p["use_multilevel"] == 1 and p["use_spanning_tree"] == 1 and p["use_acyclic"] == 1 and p["force_acyclic"] == 1
+    # decoding of the shim's solution (cheapest label per node, first minimum)
+    exp_labels = np.zeros(F, np.uint32)
+    for f in range(F):
+        if seen[f]:
+            c = dc["cost"][ptr[f]:ptr[f + 1]]
+            exp_labels[f] = int(dc["view"][ptr[f] + int(np.argmin(c))]) + 1
+    assert np.array_equal(m["labels"], exp_labels)
+    # the oracle's objective = energy of the recorded model, for the greedy and for the optimised labeling
+    o = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1)
+    def model_energy(labels):
+        e = 0.0
+        for f in range(F):
+            ll = m["ls_label"][lp[f]:lp[f + 1]]
+            k = int(np.flatnonzero(ll == labels[f])[0])
+            e += float(m["ls_cost"][lp[f] + k])
+        e += sum(1.0 for a, b in m["edges"] if labels[a] != labels[b])
+        return e
+    for lab in (exp_labels, o["labels"]):
+        e_model = model_energy(lab)
+        e_orc = orc.mrf_energy(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], lab)
+        assert abs(e_model - e_orc) < 1e-6 * max(1.0, e_model)
+    assert model_energy(o["labels"]) < model_energy(exp_labels)
