@@ -6,6 +6,7 @@
  * oracle/_ref/libtexref.so; never linked or loaded by the product path.
  */
 #include <cstdio>
+#include <omp.h>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -272,6 +273,86 @@ int ref_view_selection_model(uint32_t num_faces, uint32_t num_views, const uint3
         std::fprintf(stderr, "ref_view_selection_model: %s\n", e.what());
         return 1;
     }
+}
+
+/* texrecon.cpp:160-190: generate_texture_patches -> global_seam_leveling (or the zero-adjust pass) ->
+ * local_seam_leveling, on a given labeling.  Results are kept in a static cache and read back with the
+ * ref_patches_* getters (two-call protocol: first the counts, then the copies). */
+namespace {
+struct PatchCache {
+    tex::TexturePatches patches;
+    tex::VertexProjectionInfos vpi;
+    bool has_blending;   /* local_seam_leveling releases the blending masks (:201) */
+};
+PatchCache g_patches;
+}
+
+int ref_seam_leveling(const float* verts, uint32_t num_verts, const uint32_t* faces, uint32_t num_faces,
+                      const uint32_t* vf_ptr, const uint32_t* vf_idx, const uint32_t* vv_ptr, const uint32_t* vv_idx,
+                      const uint32_t* adj_ptr, const uint32_t* adj_idx, const uint32_t* labels,
+                      const orc_view* views, uint32_t num_views, int do_global, int do_local,
+                      uint32_t* num_patches_out)
+{
+    try {
+        Quiet q;
+        /* one thread: patch ids follow the view order (with more they depend on scheduling, :469,514-518) */
+        struct OneThread { int n; OneThread() : n(omp_get_max_threads()) { omp_set_num_threads(1); } ~OneThread() { omp_set_num_threads(n); } } one;
+        mve::TriangleMesh::Ptr mesh = make_mesh(verts, num_verts, faces, NULL, num_faces);
+        mve::MeshInfo mi;
+        fill_mesh_info(num_verts, vf_ptr, vf_idx, vv_ptr, vv_idx, &mi);
+        tex::Graph graph(num_faces);
+        for (uint32_t f = 0; f < num_faces; ++f)
+            for (uint32_t k = adj_ptr[f]; k < adj_ptr[f + 1]; ++k) if (f < adj_idx[k]) graph.add_edge(f, adj_idx[k]);
+        for (uint32_t f = 0; f < num_faces; ++f) graph.set_label(f, labels[f]);
+        tex::TextureViews tvs;
+        make_views(views, num_views, &tvs);
+        tex::Settings settings;
+        g_patches.patches.clear(); g_patches.vpi.clear();
+        tex::generate_texture_patches(graph, mesh, mi, &tvs, settings, &g_patches.vpi, &g_patches.patches);
+        if (do_global) {
+            tex::global_seam_leveling(graph, mesh, mi, g_patches.vpi, &g_patches.patches);
+        } else {                                               /* texrecon.cpp:174-183 */
+            for (std::size_t i = 0; i < g_patches.patches.size(); ++i) {
+                TexturePatch::Ptr tp = g_patches.patches[i];
+                std::vector<math::Vec3f> zero(tp->get_faces().size() * 3, math::Vec3f(0.0f));
+                tp->adjust_colors(zero);
+            }
+        }
+        if (do_local) tex::local_seam_leveling(graph, mesh, g_patches.vpi, &g_patches.patches);
+        g_patches.has_blending = !do_local;
+        *num_patches_out = static_cast<uint32_t>(g_patches.patches.size());
+        return 0;
+    } catch (std::exception& e) {
+        std::fprintf(stderr, "ref_seam_leveling: %s\n", e.what());
+        return 1;
+    }
+}
+
+/* info[4] = label, width, height, number of faces */
+void ref_patch_info(uint32_t id, int32_t* info)
+{
+    TexturePatch::Ptr tp = g_patches.patches[id];
+    info[0] = tp->get_label(); info[1] = tp->get_width(); info[2] = tp->get_height(); info[3] = static_cast<int32_t>(tp->get_faces().size());
+}
+
+/* image: h*w*3 floats, validity / blending: h*w bytes, faces: n, texcoords: n*3*2 floats */
+void ref_patch_data(uint32_t id, float* image, uint8_t* validity, uint8_t* blending, uint32_t* faces, float* texcoords)
+{
+    TexturePatch::Ptr tp = g_patches.patches[id];
+    std::size_t const px = static_cast<std::size_t>(tp->get_width()) * tp->get_height();
+    if (image) std::memcpy(image, tp->get_image()->get_data_pointer(), px * 3 * sizeof(float));
+    if (validity) std::memcpy(validity, tp->get_validity_mask()->get_data_pointer(), px);
+    if (blending && g_patches.has_blending) std::memcpy(blending, tp->get_blending_mask()->get_data_pointer(), px);
+    for (std::size_t i = 0; faces && i < tp->get_faces().size(); ++i) faces[i] = static_cast<uint32_t>(tp->get_faces()[i]);
+    for (std::size_t i = 0; texcoords && i < tp->get_texcoords().size(); ++i) { texcoords[2 * i] = tp->get_texcoords()[i][0]; texcoords[2 * i + 1] = tp->get_texcoords()[i][1]; }
+}
+
+/* vertex projection infos (after merge_vertex_projection_infos): count, then (patch id, x, y) triples */
+uint32_t ref_vertex_projection_count(uint32_t vertex) { return static_cast<uint32_t>(g_patches.vpi[vertex].size()); }
+void ref_vertex_projections(uint32_t vertex, uint32_t* patch_ids, float* xy)
+{
+    std::vector<tex::VertexProjectionInfo> const& v = g_patches.vpi[vertex];
+    for (std::size_t i = 0; i < v.size(); ++i) { patch_ids[i] = static_cast<uint32_t>(v[i].texture_patch_id); xy[2 * i] = v[i].projection[0]; xy[2 * i + 1] = v[i].projection[1]; }
 }
 
 }  // extern "C"

@@ -164,3 +164,46 @@ def view_selection_model(adj, face_ptr, view, cost, num_views):
     n = int(ls_ptr[-1])
     return dict(edges=_grab(edges, C.c_uint32, 2 * int(ne.value)).reshape(-1, 2), ls_ptr=ls_ptr, ls_label=_grab(ll, C.c_int32, n),
                 ls_cost=_grab(lc, C.c_float, n), labels=labels, params=dict(zip(PARAM_NAMES, params.tolist())))
+
+
+class RefPatch:
+    pass
+
+
+def seam_leveling(scene, rings, adj, labels, do_global=True, do_local=False):
+    """texrecon.cpp:160-190 on the reference TUs: texture patches (+ vertex projection infos) after
+    generate_texture_patches -> global_seam_leveling | zero adjust -> local_seam_leveling."""
+    L = lib()
+    views, keep = O.make_views(scene)
+    vf_ptr, vf_idx, vv_ptr, vv_idx = rings
+    n = C.c_uint32()
+    labels = np.ascontiguousarray(labels, np.uint32)
+    rc = L.ref_seam_leveling(_p(scene.verts), C.c_uint32(scene.verts.shape[0]), _p(scene.faces), C.c_uint32(scene.num_faces),
+                             _p(vf_ptr), _p(vf_idx), _p(vv_ptr), _p(vv_idx), _p(adj[0]), _p(adj[1]), _p(labels), views,
+                             C.c_uint32(scene.num_views), 1 if do_global else 0, 1 if do_local else 0, C.byref(n))
+    if rc:
+        raise RuntimeError(f"ref_seam_leveling rc={rc}")
+    patches = []
+    for pid in range(n.value):
+        info = np.zeros(4, np.int32)
+        L.ref_patch_info(C.c_uint32(pid), _p(info))
+        p = RefPatch()
+        p.label, w, h, nf = (int(v) for v in info)
+        p.image = np.zeros((h, w, 3), np.float32)
+        p.validity = np.zeros((h, w), np.uint8)
+        p.blending = np.zeros((h, w), np.uint8)
+        faces = np.zeros(nf, np.uint32)
+        p.texcoords = np.zeros((3 * nf, 2), np.float32)
+        L.ref_patch_data(C.c_uint32(pid), _p(p.image), _p(p.validity), _p(p.blending), _p(faces), _p(p.texcoords))
+        p.faces = faces.tolist()
+        patches.append(p)
+    L.ref_vertex_projection_count.restype = C.c_uint32
+    vpi = []
+    for v in range(scene.verts.shape[0]):
+        k = L.ref_vertex_projection_count(C.c_uint32(v))
+        ids = np.zeros(k, np.uint32)
+        xy = np.zeros((k, 2), np.float32)
+        if k:
+            L.ref_vertex_projections(C.c_uint32(v), _p(ids), _p(xy))
+        vpi.append({int(i): xy[j].copy() for j, i in enumerate(ids)})
+    return patches, vpi

@@ -26,6 +26,10 @@ public:
     template <typename O> Vector(Vector<O, N> const& o) { for (int i = 0; i < N; ++i) v[i] = static_cast<T>(o.v[i]); }
 
     Vector& fill(T const& value) { for (int i = 0; i < N; ++i) v[i] = value; return *this; }
+    T* begin() { return v; }
+    T* end() { return v + N; }
+    T const* begin() const { return v; }
+    T const* end() const { return v + N; }
     T* operator*() { return v; }
     T const* operator*() const { return v; }
     T& operator[](int i) { return v[i]; }

@@ -214,3 +214,86 @@ def test_mrf_model_and_label_decoding_match_reference_tu(ref, orc, scene_mod, ge
         e_orc = orc.mrf_energy(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], lab)
         assert abs(e_model - e_orc) < 1e-6 * max(1.0, e_model)
     assert model_energy(o["labels"]) < model_energy(exp_labels)
+
+
+# ---- texture patches, global and local seam leveling ---------------------------------------------------------------
+@pytest.fixture(scope="module")
+def seam_inputs(orc, scene_mod, get_scene):
+    cache = {}
+    def _get(name):
+        if name not in cache:
+            s = get_scene(name)
+            adj = scene_mod.face_adjacency(s.faces)
+            rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
+            dc = orc.data_costs(s)
+            labels = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1)["labels"]
+            cache[name] = (s, adj, rings, labels)
+        return cache[name]
+    return _get
+
+
+@pytest.mark.parametrize("name", ["tiny", "occ"])
+def test_texture_patches_match_reference_tu(ref, orc, seam_inputs, name):
+    """generate_texture_patches.cpp:453-538 (+ generate_candidate :78-138, merge_vertex_projection_infos :40-65) and the
+    zero-adjust pass texrecon.cpp:174-183 (TexturePatch::adjust_colors, texture_patch.cpp:41-116) vs oracle/patches.py:
+    same patches, faces, bit-identical texcoords, vertex projections, images, validity and blending masks."""
+    import patches as P
+    s, adj, rings, labels = seam_inputs(name)
+    rp, rvpi = ref.seam_leveling(s, rings, adj, labels, do_global=False)
+    pp, pvpi = P.generate_texture_patches(orc, s, adj, labels)
+    rp = [p for p in rp if p.label != 0]                       # label 0 = hole-filling patches (not restated)
+    assert len(rp) == len(pp) >= s.num_views // 2
+    for a, b in zip(rp, pp):
+        assert a.label == b.label and a.faces == b.faces
+        assert np.array_equal(a.texcoords.view(np.uint32), np.asarray(b.texcoords, np.float32).view(np.uint32))
+        img, validity, blending = P.adjust_colors(b, np.zeros((3 * len(b.faces), 3), np.float32))
+        assert np.array_equal(a.validity, validity) and np.array_equal(a.blending, blending)
+        assert np.array_equal(a.image.view(np.uint32), img.view(np.uint32))
+    for v in range(s.verts.shape[0]):
+        mine = {pid: proj for pid, (proj, _f) in pvpi[v].items()}
+        theirs = {pid: xy for pid, xy in rvpi[v].items() if pid < len(pp)}
+        assert set(mine) == set(theirs)
+        for pid in mine:
+            assert np.array_equal(np.asarray(mine[pid], np.float32).view(np.uint32), theirs[pid].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["tiny", "occ"])
+def test_global_seam_leveling_matches_reference_tu(ref, orc, seam_inputs, name):
+    """tex::global_seam_leveling (global_seam_leveling.cpp:140-324: unknown numbering, Gamma, A, b from patch-relative
+    edge samples, Lhs, CG per channel, mean subtraction, adjust_colors per patch) vs orc_global_seam_leveling +
+    oracle/patches.apply_adjust_values.  The CG of both sides is the same restatement of Eigen's (shim / seam.c); the
+    right-hand sides are sampled in patch vs view coordinates, so the adjusted images agree to rounding (2e-5)."""
+    import patches as P
+    s, adj, rings, labels = seam_inputs(name)
+    seam = orc.global_seam_leveling(s, rings, labels)
+    rp, _ = ref.seam_leveling(s, rings, adj, labels, do_global=True)
+    pp, _ = P.generate_texture_patches(orc, s, adj, labels)
+    pa = P.apply_adjust_values(s, pp, seam["row_ptr"], seam["row_label"], seam["x"])
+    rp = [p for p in rp if p.label != 0]
+    assert len(rp) == len(pa)
+    moved = 0.0
+    for a, b, raw in zip(rp, pa, pp):
+        assert np.array_equal(a.validity, b.validity) and np.array_equal(a.blending, b.blending)
+        assert np.abs(a.image - b.image).max() < 2e-5
+        moved = max(moved, float(np.abs(a.image - raw.image)[a.validity != 0].max()))
+    assert moved > 0.02                                        # the leveling really changed the colours
+
+
+def test_local_seam_leveling_matches_reference_tu(ref, orc, seam_inputs):
+    """tex::local_seam_leveling (local_seam_leveling.cpp:105-204, draw_line :39-92, prepare_blending_mask
+    texture_patch.cpp:197-297, poisson_blend poisson_blending.cpp:49-138) vs oracle/patches.local_seam_leveling.
+    Both solve the same fp32 systems with a direct solver in double (shim elimination / scipy splu): 2e-5."""
+    import patches as P
+    s, adj, rings, labels = seam_inputs("tiny")
+    seam = orc.global_seam_leveling(s, rings, labels)
+    rp, _ = ref.seam_leveling(s, rings, adj, labels, do_global=True, do_local=True)
+    pp, pvpi = P.generate_texture_patches(orc, s, adj, labels)
+    pa = P.apply_adjust_values(s, pp, seam["row_ptr"], seam["row_label"], seam["x"])
+    before = [p.image.copy() for p in pa]
+    P.local_seam_leveling(s, adj, labels, pa, pvpi)
+    changed = 0.0
+    for a, b, b0 in zip(rp, pa, before):
+        assert np.array_equal(a.validity, b.validity)
+        assert np.abs(a.image - b.image).max() < 2e-5
+        changed = max(changed, float(np.abs(b.image - b0).max()))
+    assert changed > 0.01
