@@ -29,3 +29,24 @@ def test_data_costs_with_occlusion_bit_exact(b2, get_scene, orc, name):
     g2 = c.data_costs_download(info2.nnz)
     assert np.array_equal(g2["face_ptr"], o_novis["face_ptr"]) and np.array_equal(g2["view"], o_novis["view"])
     c.close()
+
+
+def test_view_selection_and_seam_leveling_with_unseen_faces(b2, get_scene, scene_mod, orc):
+    """`occ` through all three stages: 37 faces no view sees (label 0, excluded from the MRF graph and from the seam
+    system) and ten separate mesh components -- cases the smooth scenes never produce."""
+    s = get_scene("occ")
+    ap, ai = scene_mod.face_adjacency(s.faces)
+    rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
+    dc = orc.data_costs(s)
+    om = orc.view_selection(ap, ai, dc["face_ptr"], dc["view"], dc["cost"], threads=1)
+    assert (om["labels"] == 0).sum() > 10
+    labels, info = b2.view_selection(b2.DataCosts(s.num_faces, s.num_views, dc["face_ptr"], dc["view"], dc["cost"]), ap, ai)
+    assert info.iterations == om["iterations"]
+    assert np.array_equal(labels, om["labels"])
+    assert info.unseen == int((om["labels"] == 0).sum())
+    o = orc.global_seam_leveling(s, rings, om["labels"])
+    g = b2.global_seam_leveling(s, rings, om["labels"])
+    assert np.array_equal(g["row_ptr"], o["row_ptr"]) and np.array_equal(g["row_label"], o["row_label"])
+    assert g["info"].num_a_rows == o["num_a_rows"] and g["info"].num_gamma_rows == o["num_gamma_rows"]
+    rel = np.linalg.norm(g["x"] - o["x"]) / np.linalg.norm(o["x"])
+    assert rel < 5e-3, rel
