@@ -91,6 +91,12 @@ typedef struct {
     float cg_ms;             /* device time of the PCG kernel (CUDA events) */
 } b2tex_seam_info;
 
+typedef struct {
+    uint32_t num_patches;   /* "texture patches." generate_texture_patches.cpp:597 (seen faces only) */
+    uint32_t num_faces;     /* faces with a label != 0 = sum of the patches' face counts */
+    uint64_t num_pixels;    /* sum of width * height over the patches */
+} b2tex_patch_info;
+
 typedef struct b2tex_ctx b2tex_ctx;
 
 /* ---- lifetime ---- */
@@ -147,6 +153,18 @@ int b2tex_seam_download(b2tex_ctx *ctx, uint32_t *row_ptr, uint32_t *row_label, 
                         float *rhs_or_null);
 /* full symmetric CSR of Lhs (for tests / inspection); arrays sized from b2tex_seam_info */
 int b2tex_seam_matrix_download(b2tex_ctx *ctx, uint32_t *csr_ptr, uint32_t *csr_col, float *csr_val);
+/* tex::generate_texture_patches for the seen faces (generate_texture_patches.cpp:78-138,453-538; hole filling
+ * :140-451 is not built: faces with label 0 get no patch) followed by TexturePatch::adjust_colors per patch
+ * (texture_patch.cpp:41-116) with the solved offsets (apply_adjust = 1, global_seam_leveling.cpp:293-323; needs
+ * b2tex_seam_run) or with zeros (apply_adjust = 0, texrecon.cpp:174-183).  Needs mesh, views, adjacency, labels.
+ * Patch ids follow ascending labels (the reference's ids depend on OpenMP scheduling, :469,514-518). */
+int b2tex_texture_patches_run(b2tex_ctx *ctx, int apply_adjust, b2tex_patch_info *info);
+/* desc[num_patches][8] = label, min_x, min_y (view pixel of patch pixel (0,0)), width, height, first face slot,
+ * number of faces, 0; faces[num_faces]; texcoords[num_faces][3][2]; per pixel (patch after patch, row major):
+ * images[num_pixels][3] float, validity[num_pixels], blending[num_pixels] (255 inside, 64 within sqrt(2), 0).
+ * Any pointer may be NULL. */
+int b2tex_texture_patches_download(b2tex_ctx *ctx, int32_t *desc, uint32_t *faces, float *texcoords, float *images,
+                                   uint8_t *validity, uint8_t *blending);
 /* raw device pointers of resident results (torch / NCCL plumbing); 0 if absent */
 uint64_t b2tex_device_ptr(b2tex_ctx *ctx, const char *name, uint64_t *num_elements);
 

@@ -29,6 +29,7 @@ EXPORTS = [
     "b2tex_data_costs_normalize", "b2tex_data_costs_download", "b2tex_view_selection_run",
     "b2tex_labels_download", "b2tex_mrf_init", "b2tex_mrf_iterate", "b2tex_mrf_energy", "b2tex_mrf_sample_forest",
     "b2tex_seam_run", "b2tex_seam_download", "b2tex_seam_matrix_download", "b2tex_device_ptr",
+    "b2tex_texture_patches_run", "b2tex_texture_patches_download",
     "b2tex_calculate_data_costs", "b2tex_calculate_data_costs_into", "b2tex_view_selection",
     "b2tex_global_seam_leveling", "b2tex_texture_hot_path",
 ]
@@ -59,6 +60,10 @@ class B2MrfParams(C.Structure):
 class B2MrfInfo(C.Structure):
     _fields_ = [("iterations", C.c_uint32), ("energy_initial", C.c_double),
                 ("energy_final", C.c_double), ("unseen", C.c_uint64), ("sweep_bytes", C.c_uint64)]
+
+
+class B2PatchInfo(C.Structure):
+    _fields_ = [("num_patches", C.c_uint32), ("num_faces", C.c_uint32), ("num_pixels", C.c_uint64)]
 
 
 class B2SeamInfo(C.Structure):
@@ -285,6 +290,31 @@ class Context:
         r = np.zeros((R, 3), np.float32) if rhs else None
         _check(lib().b2tex_seam_download(self._h, _p(row_ptr), _p(row_label), _p(x), _p(r)))
         return dict(row_ptr=row_ptr, row_label=row_label, x=x, rhs=r)
+
+    def texture_patches_run(self, apply_adjust=True):
+        """tex::generate_texture_patches (seen faces) + TexturePatch::adjust_colors per patch"""
+        info = B2PatchInfo()
+        _check(lib().b2tex_texture_patches_run(self._h, C.c_int(1 if apply_adjust else 0), C.byref(info)))
+        return info
+
+    def texture_patches_download(self, info):
+        """list of dicts: label, min_x, min_y, faces, texcoords (3n x 2), image (h x w x 3), validity, blending"""
+        n, T, P = int(info.num_patches), int(info.num_faces), int(info.num_pixels)
+        desc = np.zeros((max(n, 1), 8), np.int32)
+        faces = np.zeros(max(T, 1), np.uint32)
+        tex = np.zeros((max(T, 1) * 3, 2), np.float32)
+        img = np.zeros((max(P, 1), 3), np.float32)
+        val = np.zeros(max(P, 1), np.uint8)
+        bl = np.zeros(max(P, 1), np.uint8)
+        _check(lib().b2tex_texture_patches_download(self._h, _p(desc), _p(faces), _p(tex), _p(img), _p(val), _p(bl)))
+        out, off = [], 0
+        for q in range(n):
+            label, mx, my, w, h, first, nf, _ = (int(v) for v in desc[q])
+            out.append(dict(label=label, min_x=mx, min_y=my, faces=faces[first:first + nf].tolist(),
+                            texcoords=tex[3 * first:3 * (first + nf)].copy(), image=img[off:off + w * h].reshape(h, w, 3).copy(),
+                            validity=val[off:off + w * h].reshape(h, w).copy(), blending=bl[off:off + w * h].reshape(h, w).copy()))
+            off += w * h
+        return out
 
     def seam_matrix(self, info):
         R, nz = int(info.num_rows), int(info.nnz_full)

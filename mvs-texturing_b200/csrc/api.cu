@@ -63,6 +63,7 @@ void b2tex_destroy(b2tex_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    patches_free(c);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -310,6 +311,20 @@ int b2tex_labels_download(b2tex_ctx *c, uint32_t *labels)
     B2_TRY(c->labels.download(labels, c->F, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     return B2TEX_OK;
+}
+
+int b2tex_texture_patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    b2tex_patch_info local;
+    return patches_run(c, apply_adjust, info ? info : &local);
+}
+
+int b2tex_texture_patches_download(b2tex_ctx *c, int32_t *desc, uint32_t *faces, float *texcoords, float *images,
+                                   uint8_t *validity, uint8_t *blending)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return patches_download(c, desc, faces, texcoords, images, validity, blending);
 }
 
 int b2tex_seam_run(b2tex_ctx *c, b2tex_seam_info *info)

@@ -118,6 +118,8 @@ struct KTimer {
 };
 }  // namespace b2
 
+namespace b2 { struct PatchState; }  // texture patches (patches.cu)
+
 // The opaque C-ABI context.
 struct b2tex_ctx {
     bool profile = false;
@@ -203,6 +205,9 @@ struct b2tex_ctx {
     uint32_t R = 0, A_rows = 0;
     uint64_t nnz_L = 0;
     bool have_seam = false;
+
+    // texture patches (allocated on first use, released by patches_free)
+    b2::PatchState *patches = nullptr;
 };
 
 namespace b2 {
@@ -236,6 +241,10 @@ int mrf_energy_only(b2tex_ctx *c, int64_t *energy_fixed);
 int mrf_sample_only(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t, uint32_t *level_host);
 int mrf_energy_double(b2tex_ctx *c, double *e, uint64_t *unseen);
 int seam_run(b2tex_ctx *c, b2tex_seam_info *info);
+int patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info);
+int patches_download(b2tex_ctx *c, int32_t *desc, uint32_t *faces, float *texcoords, float *images, uint8_t *validity,
+                     uint8_t *blending);
+void patches_free(b2tex_ctx *c);
 int cub_exclusive_sum_u64(b2tex_ctx *c, const uint64_t *in, uint64_t *out, size_t n);
 int cub_exclusive_sum_u32(b2tex_ctx *c, const uint32_t *in, uint32_t *out, size_t n);
 }  // namespace b2

@@ -57,9 +57,11 @@ def emul():
                              "    extern __shared__ uint32_t sm[];  // [rounds+1] level counts\n", close=2))
     with open(os.path.join(OUT, "seam_kernels.inc"), "w") as f:
         f.write(_kernel_part("seam.cu", "int seam_run(b2tex_ctx"))
+    with open(os.path.join(OUT, "patches_kernels.inc"), "w") as f:
+        f.write(_kernel_part("patches.cu", "void patches_free(b2tex_ctx", ("struct PatchState {", "namespace {")))
     libs = {}
     cpp = os.path.join(ROOT, "tests", "cpp")
-    for name in ("emul_bvh", "emul_datacosts", "emul_mrf", "emul_seam"):
+    for name in ("emul_bvh", "emul_datacosts", "emul_mrf", "emul_seam", "emul_patches"):
         so = os.path.join(OUT, name + ".so")
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w",
                                "-I" + os.path.join(cpp, "emul_include"), "-I" + cpp, "-I" + CUDA_INC, "-I" + CSRC,
@@ -194,3 +196,174 @@ def test_device_seam_leveling_kernels(emul, orc, scene_mod, get_scene, name):
     assert np.array_equal(rhs.view(np.uint32), o["rhs"].view(np.uint32))
     assert status[:3].tolist() == list(o["iterations"])
     assert np.linalg.norm(x - o["x"]) / np.linalg.norm(o["x"]) < 1e-4
+
+
+# ---- texture patches + adjust_colors (csrc/patches.cu, csrc/patches_host.h) -----------------------------------------
+def _emul_patches(emul, orc, s, adj, labels, seam=None):
+    L = emul["emul_patches"]
+    views, keep = orc.make_views(s)
+    ptrs = [C.c_void_p() for _ in range(6)]
+    sizes = np.zeros(3, np.uint64)
+    labels = np.ascontiguousarray(labels, np.uint32)
+    if seam is not None:
+        x = np.ascontiguousarray(seam["x"], np.float32)
+        args = (orc._p(seam["row_ptr"]), orc._p(seam["row_label"]), orc._p(x), C.c_uint32(len(seam["row_label"])))
+    else:
+        args = (None, None, None, C.c_uint32(0))
+    rc = L.emul_texture_patches(orc._p(s.verts), C.c_uint32(s.verts.shape[0]), orc._p(s.faces), C.c_uint32(s.num_faces), orc._p(adj[0]),
+                                orc._p(adj[1]), orc._p(labels), views, C.c_uint32(s.num_views), *args, *[C.byref(p) for p in ptrs],
+                                orc._p(sizes))
+    assert rc == 0
+    n, T, Pn = (int(v) for v in sizes)
+    def grab(p, ct, k):
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), (max(k, 1),))[:k].copy()
+        L.emul_patches_free(p)
+        return a
+    desc = grab(ptrs[0], C.c_int32, 8 * n).reshape(n, 8)
+    faces, tex = grab(ptrs[1], C.c_uint32, T), grab(ptrs[2], C.c_float, 6 * T).reshape(-1, 2)
+    img, val, bl = grab(ptrs[3], C.c_float, 3 * Pn).reshape(-1, 3), grab(ptrs[4], C.c_uint8, Pn), grab(ptrs[5], C.c_uint8, Pn)
+    out, off = [], 0
+    for q in range(n):
+        label, mx, my, w, h, first, nf, _ = (int(v) for v in desc[q])
+        out.append(dict(label=label, min_x=mx, min_y=my, faces=faces[first:first + nf].tolist(), texcoords=tex[3 * first:3 * (first + nf)],
+                        image=img[off:off + w * h].reshape(h, w, 3), validity=val[off:off + w * h].reshape(h, w),
+                        blending=bl[off:off + w * h].reshape(h, w)))
+        off += w * h
+    return out
+
+
+def _same_patch(a, label, faces, texcoords, image, validity, blending):
+    return (a["label"] == label and a["faces"] == list(faces)
+            and np.array_equal(a["texcoords"].view(np.uint32), np.asarray(texcoords, np.float32).view(np.uint32))
+            and a["image"].shape == image.shape and np.array_equal(a["image"].view(np.uint32), image.view(np.uint32))
+            and np.array_equal(a["validity"], validity) and np.array_equal(a["blending"], blending))
+
+
+@pytest.mark.parametrize("name,adjust", [("tiny", False), ("tiny", True), ("occ", True)])
+def test_device_texture_patch_kernels(emul, orc, scene_mod, get_scene, name, adjust):
+    """csrc/patches.cu vs oracle/patches.py (itself pinned to the reference TUs): same patches, face order, bit-identical
+    texcoords, images after adjust_colors (zero and solved offsets), validity and blending masks."""
+    import patches as P
+    s = get_scene(name)
+    adj = scene_mod.face_adjacency(s.faces)
+    rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
+    dc = orc.data_costs(s)
+    labels = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1)["labels"]
+    seam = orc.global_seam_leveling(s, rings, labels) if adjust else None
+    ep = _emul_patches(emul, orc, s, adj, labels, seam)
+    pp, _ = P.generate_texture_patches(orc, s, adj, labels)
+    assert len(ep) == len(pp) > 0
+    if adjust:
+        pa = P.apply_adjust_values(s, pp, seam["row_ptr"], seam["row_label"], seam["x"])
+        exp = [(q.label, q.faces, q.texcoords, q.image, q.validity, q.blending) for q in pa]
+    else:
+        exp = [(q.label, q.faces, q.texcoords) + P.adjust_colors(q, np.zeros((3 * len(q.faces), 3), np.float32)) for q in pp]
+    for a, e, q in zip(ep, exp, pp):
+        assert _same_patch(a, *e)
+        assert [a["min_x"], a["min_y"]] == list(q.bbox[:2])
+
+
+def test_device_texture_patches_merge_like_reference_tu(emul, orc, scene_mod, get_scene):
+    """Candidate merging (generate_texture_patches.cpp:484-508): label islands whose bounding box lies inside the box of
+    another component of the same label are absorbed.  Crafted on `small` (six one-face islands); compared with the
+    reference's own translation units when libtexref.so is available, else with oracle/patches.py."""
+    import patches as P
+    s = get_scene("small")
+    adj = scene_mod.face_adjacency(s.faces)
+    rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
+    dc = orc.data_costs(s)
+    labels = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1)["labels"].copy()
+    ptr = dc["face_ptr"].astype(np.int64)
+    vis = [set((dc["view"][ptr[f]:ptr[f + 1]] + 1).tolist()) for f in range(s.num_faces)]
+    nb = lambda f: [int(a) for a in adj[1][adj[0][f]:adj[0][f + 1]]]
+    islands, used = 0, set()
+    for f in range(s.num_faces):
+        L = labels[f]
+        ring1 = nb(f)
+        if len(ring1) != 3 or any(labels[a] != L for a in ring1):
+            continue
+        ring2 = set(b for a in ring1 for b in nb(a)) - {f} - set(ring1)
+        if any(labels[b] != L for b in ring2) or used & ({f} | set(ring1) | ring2):
+            continue
+        common = set.intersection(*[vis[a] for a in ring1]) - {int(L)}
+        if not common:
+            continue
+        for a in ring1:
+            labels[a] = min(common)          # cut face f off from its component
+        used |= {f} | set(ring1) | ring2
+        islands += 1
+        if islands >= 6:
+            break
+    assert islands >= 3
+    ncomp = sum(len(P.get_subgraphs(adj[0], adj[1], labels, lab)) for lab in range(1, s.num_views + 1))
+    ep = _emul_patches(emul, orc, s, adj, labels, None)
+    assert len(ep) <= ncomp - islands                          # the islands (at least) were absorbed
+    try:
+        import refpin
+        have_ref = refpin.available()
+    except Exception:
+        have_ref = False
+    if have_ref:
+        rp, _ = refpin.seam_leveling(s, rings, adj, labels, do_global=False)
+        assert len(rp) == len(ep)
+        for a, b in zip(ep, rp):
+            assert _same_patch(a, b.label, b.faces, b.texcoords, b.image, b.validity, b.blending)
+    else:
+        pp, _ = P.generate_texture_patches(orc, s, adj, labels)
+        assert len(pp) == len(ep)
+        for a, q in zip(ep, pp):
+            assert _same_patch(a, q.label, q.faces, q.texcoords, *P.adjust_colors(q, np.zeros((3 * len(q.faces), 3), np.float32)))
+
+
+def test_patch_plan_merge_chains(emul):
+    """plan_patches() on random rectangles vs a literal transcription of the reference's std::list loop (:484-508),
+    including chains (a candidate that absorbed others is absorbed itself later: offsets accumulate in order)."""
+    L = emul["emul_patches"]
+    rng = np.random.RandomState(4)
+    chains_seen = 0
+    for trial in range(60):
+        Cn = int(rng.randint(2, 14))
+        labels = np.sort(rng.randint(1, 4, size=Cn)).astype(np.uint32)
+        x0, y0 = rng.randint(0, 40, size=Cn), rng.randint(0, 40, size=Cn)
+        w, h = rng.randint(1, 45, size=Cn), rng.randint(1, 45, size=Cn)
+        if trial % 3 == 0:                                     # nested boxes, small first -> chains (the harness reports <= 8 offsets)
+            Cn = min(Cn, 8); labels = labels[:Cn]
+            x0, y0, w, h = 20 - np.arange(Cn), 20 - np.arange(Cn), 2 + 2 * np.arange(Cn), 2 + 2 * np.arange(Cn)
+            labels[:] = 1
+        bbox = np.stack([x0, y0, x0 + w, y0 + h], 1).astype(np.int32)
+        # transcription: candidates in order, Rect(min - border, max), list erase semantics
+        cands = [dict(r=[int(b[0]) - 1, int(b[1]) - 1, int(b[2]), int(b[3])], members=[(c, [])], label=int(labels[c])) for c, b in enumerate(bbox)]
+        out = []
+        for lab in sorted(set(labels.tolist())):
+            lst = [c for c in cands if c["label"] == lab]
+            i = 0
+            while i < len(lst):
+                it = lst[i]
+                j = 0
+                while j < len(lst):
+                    sit = lst[j]
+                    if sit is not it and sit["r"][0] >= it["r"][0] and sit["r"][2] <= it["r"][2] and sit["r"][1] >= it["r"][1] and sit["r"][3] <= it["r"][3]:
+                        off = (float(sit["r"][0] - it["r"][0]), float(sit["r"][1] - it["r"][1]))
+                        it["members"] += [(c, ch + [off]) for c, ch in sit["members"]]
+                        del lst[j]
+                        if j < i:
+                            i -= 1
+                    else:
+                        j += 1
+                i += 1
+            out += lst
+        comp_patch, comp_pos, cnt = np.zeros(Cn, np.uint32), np.zeros(Cn, np.uint32), np.zeros(Cn, np.uint32)
+        chain = np.zeros((Cn, 16), np.float32)
+        desc = np.zeros((Cn, 8), np.int32)
+        n = L.emul_plan_patches(C.c_uint32(Cn), labels.ctypes.data_as(C.c_void_p), bbox.ctypes.data_as(C.c_void_p),
+                                comp_patch.ctypes.data_as(C.c_void_p), comp_pos.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p),
+                                chain.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p))
+        assert n == len(out)
+        for q, cand in enumerate(out):
+            assert desc[q, 0] == cand["label"] and desc[q, 1] == cand["r"][0] and desc[q, 2] == cand["r"][1]
+            assert desc[q, 3] == cand["r"][2] - cand["r"][0] + 2 and desc[q, 4] == cand["r"][3] - cand["r"][1] + 2
+            for pos, (c, ch) in enumerate(cand["members"]):
+                assert comp_patch[c] == q and comp_pos[c] == pos and cnt[c] == len(ch)
+                assert chain[c, :2 * len(ch)].tolist() == [v for o in ch for v in o]
+                chains_seen += len(ch) >= 2
+    assert chains_seen > 10

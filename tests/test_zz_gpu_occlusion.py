@@ -50,3 +50,42 @@ def test_view_selection_and_seam_leveling_with_unseen_faces(b2, get_scene, scene
     assert g["info"].num_a_rows == o["num_a_rows"] and g["info"].num_gamma_rows == o["num_gamma_rows"]
     rel = np.linalg.norm(g["x"] - o["x"]) / np.linalg.norm(o["x"])
     assert rel < 5e-3, rel
+
+
+@pytest.mark.parametrize("name", ["tiny", "occ"])
+def test_texture_patches_and_adjust_colors(b2, get_scene, scene_mod, orc, name):
+    """b2tex_texture_patches_run (csrc/patches.cu: generate_texture_patches for seen faces + TexturePatch::adjust_colors)
+    against oracle/patches.py, which tests/test_ref_pinning.py holds bit for bit to the reference's own translation units:
+    same patches and face order, bit-identical texcoords, images and masks -- with zero offsets (texrecon.cpp:174-183) and
+    with the offsets the device PCG just solved (global_seam_leveling.cpp:293-323)."""
+    import patches as P
+    s = get_scene(name)
+    ap, ai = scene_mod.face_adjacency(s.faces)
+    rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
+    dc = orc.data_costs(s)
+    labels = orc.view_selection(ap, ai, dc["face_ptr"], dc["view"], dc["cost"], threads=1)["labels"]
+    pp, _ = P.generate_texture_patches(orc, s, (ap, ai), labels)
+    c = b2.Context(0)
+    c.set_scene(s)
+    c.set_adjacency(ap, ai)
+    c.set_vertex_rings(*rings)
+    c.set_labels(labels)
+
+    def check(got, exp):
+        assert len(got) == len(exp) > 0
+        for a, (label, faces, tex, img, val, bl), q in zip(got, exp, pp):
+            assert a["label"] == label and a["faces"] == list(faces) and [a["min_x"], a["min_y"]] == list(q.bbox[:2])
+            assert np.array_equal(a["texcoords"].view(np.uint32), np.asarray(tex, np.float32).view(np.uint32))
+            assert np.array_equal(a["validity"], val) and np.array_equal(a["blending"], bl)
+            assert np.array_equal(a["image"].view(np.uint32), img.view(np.uint32))
+
+    info = c.texture_patches_run(apply_adjust=False)
+    assert info.num_faces == int((labels != 0).sum())
+    check(c.texture_patches_download(info),
+          [(q.label, q.faces, q.texcoords) + P.adjust_colors(q, np.zeros((3 * len(q.faces), 3), np.float32)) for q in pp])
+    sinfo = c.seam_run()
+    d = c.seam_download(sinfo)
+    info = c.texture_patches_run(apply_adjust=True)
+    pa = P.apply_adjust_values(s, pp, d["row_ptr"], d["row_label"], d["x"])
+    check(c.texture_patches_download(info), [(q.label, q.faces, q.texcoords, q.image, q.validity, q.blending) for q in pa])
+    c.close()
