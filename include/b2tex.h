@@ -97,6 +97,15 @@ typedef struct {
     uint64_t num_pixels;    /* sum of width * height over the patches */
 } b2tex_patch_info;
 
+typedef struct {
+    uint32_t num_seam_edges;    /* find_seam_edges, seam_leveling.cpp:16-59 */
+    uint32_t num_edge_samples;  /* sum of ceil(2 * max projected length), local_seam_leveling.cpp:139 */
+    uint32_t num_vertices;      /* vertices projected into more than one patch, :157 */
+    uint32_t num_unknowns;      /* blending mask == 255 pixels of all patches (interior of the 20 px strips) */
+    uint32_t iterations[3];     /* CG iterations per colour channel (one batched solve for all patches) */
+    float residual[3];          /* |r| / |b| per colour channel at exit */
+} b2tex_local_seam_info;
+
 typedef struct b2tex_ctx b2tex_ctx;
 
 /* ---- lifetime ---- */
@@ -165,6 +174,14 @@ int b2tex_texture_patches_run(b2tex_ctx *ctx, int apply_adjust, b2tex_patch_info
  * Any pointer may be NULL. */
 int b2tex_texture_patches_download(b2tex_ctx *ctx, int32_t *desc, uint32_t *faces, float *texcoords, float *images,
                                    uint8_t *validity, uint8_t *blending);
+/* tex::local_seam_leveling (local_seam_leveling.cpp:105-204) on the patches b2tex_texture_patches_run left on the device:
+ * mean colours along the seam edges and at shared vertices are stamped into every adjacent patch, the blending mask keeps
+ * a 20 pixel strip (TexturePatch::prepare_blending_mask), the strip is Poisson-blended towards the stamped colours
+ * (poisson_blend, alpha = 1; one batched CG over all patches instead of one SparseLU per patch: same linear systems,
+ * agreement to the CG tolerance) and pixels outside the patch boundary are invalidated (TexturePatch::blend).
+ * Download the result with b2tex_texture_patches_download (the blending mask is the one used for blending; the
+ * reference releases it at :201). */
+int b2tex_local_seam_leveling_run(b2tex_ctx *ctx, b2tex_local_seam_info *info);
 /* raw device pointers of resident results (torch / NCCL plumbing); 0 if absent */
 uint64_t b2tex_device_ptr(b2tex_ctx *ctx, const char *name, uint64_t *num_elements);
 

@@ -29,7 +29,7 @@ EXPORTS = [
     "b2tex_data_costs_normalize", "b2tex_data_costs_download", "b2tex_view_selection_run",
     "b2tex_labels_download", "b2tex_mrf_init", "b2tex_mrf_iterate", "b2tex_mrf_energy", "b2tex_mrf_sample_forest",
     "b2tex_seam_run", "b2tex_seam_download", "b2tex_seam_matrix_download", "b2tex_device_ptr",
-    "b2tex_texture_patches_run", "b2tex_texture_patches_download",
+    "b2tex_texture_patches_run", "b2tex_texture_patches_download", "b2tex_local_seam_leveling_run",
     "b2tex_calculate_data_costs", "b2tex_calculate_data_costs_into", "b2tex_view_selection",
     "b2tex_global_seam_leveling", "b2tex_texture_hot_path",
 ]
@@ -64,6 +64,11 @@ class B2MrfInfo(C.Structure):
 
 class B2PatchInfo(C.Structure):
     _fields_ = [("num_patches", C.c_uint32), ("num_faces", C.c_uint32), ("num_pixels", C.c_uint64)]
+
+
+class B2LocalSeamInfo(C.Structure):
+    _fields_ = [("num_seam_edges", C.c_uint32), ("num_edge_samples", C.c_uint32), ("num_vertices", C.c_uint32),
+                ("num_unknowns", C.c_uint32), ("iterations", C.c_uint32 * 3), ("residual", C.c_float * 3)]
 
 
 class B2SeamInfo(C.Structure):
@@ -295,6 +300,12 @@ class Context:
         """tex::generate_texture_patches (seen faces) + TexturePatch::adjust_colors per patch"""
         info = B2PatchInfo()
         _check(lib().b2tex_texture_patches_run(self._h, C.c_int(1 if apply_adjust else 0), C.byref(info)))
+        return info
+
+    def local_seam_leveling_run(self):
+        """tex::local_seam_leveling on the resident texture patches"""
+        info = B2LocalSeamInfo()
+        _check(lib().b2tex_local_seam_leveling_run(self._h, C.byref(info)))
         return info
 
     def texture_patches_download(self, info):

@@ -320,6 +320,13 @@ int b2tex_texture_patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *
     return patches_run(c, apply_adjust, info ? info : &local);
 }
 
+int b2tex_local_seam_leveling_run(b2tex_ctx *c, b2tex_local_seam_info *info)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    b2tex_local_seam_info local;
+    return local_seam_run(c, info ? info : &local);
+}
+
 int b2tex_texture_patches_download(b2tex_ctx *c, int32_t *desc, uint32_t *faces, float *texcoords, float *images,
                                    uint8_t *validity, uint8_t *blending)
 {

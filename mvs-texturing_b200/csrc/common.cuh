@@ -245,6 +245,7 @@ int patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info);
 int patches_download(b2tex_ctx *c, int32_t *desc, uint32_t *faces, float *texcoords, float *images, uint8_t *validity,
                      uint8_t *blending);
 void patches_free(b2tex_ctx *c);
+int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info);
 int cub_exclusive_sum_u64(b2tex_ctx *c, const uint64_t *in, uint64_t *out, size_t n);
 int cub_exclusive_sum_u32(b2tex_ctx *c, const uint32_t *in, uint32_t *out, size_t n);
 }  // namespace b2

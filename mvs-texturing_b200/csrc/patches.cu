@@ -19,22 +19,9 @@
 // result is independent of the execution order and identical to the sequential loop.
 #include <math.h>
 
-#include "common.cuh"
-#include "patches_host.h"
+#include "patches.cuh"
 
 namespace b2 {
-
-struct PatchState {
-    PatchPlan plan;
-    std::vector<uint32_t> faces;          // face id per final slot
-    DevBuf<uint32_t> comp_faces, slot_comp0, slot_src, slot_comp, slot_patch, slot_face, comp_chain, comp_wh, key;
-    DevBuf<int32_t> comp_bbox, comp_min, desc;
-    DevBuf<uint64_t> pix_off;
-    DevBuf<float> px, tex, chain, adj, img;
-    DevBuf<uint8_t> valid, blend;
-    uint64_t total_pixels = 0;
-    bool ready = false;
-};
 
 namespace {
 
@@ -280,6 +267,7 @@ int patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info)
     if (!c->patches) c->patches = new PatchState();
     PatchState &ps = *c->patches;
     ps.ready = false;
+    ps.leveled = false;
     ScopedTimer tm(c, "texture_patches");
 
     // ---- components on the host (graph traversal, order defining) ----

@@ -6,7 +6,10 @@
 #pragma once
 #include <stdint.h>
 
+#include <math.h>
+
 #include <algorithm>
+#include <cmath>
 #include <deque>
 #include <vector>
 
@@ -139,6 +142,94 @@ inline void plan_patches(const std::vector<PatchComponent> &comps, const int32_t
         plan.comp_chain[2 * c] = (uint32_t)(plan.chain.size() / 2);
         plan.comp_chain[2 * c + 1] = (uint32_t)(chains[c].size() / 2);
         plan.chain.insert(plan.chain.end(), chains[c].begin(), chains[c].end());
+    }
+}
+
+// ---- local seam leveling bookkeeping (libs/tex/seam_leveling.cpp, local_seam_leveling.cpp:113-176) -------------
+struct VertexProj {          // VertexProjectionInfo after merge_vertex_projection_infos (:40-65)
+    uint32_t patch;
+    float x, y;              // the FIRST projection of the vertex met in the patch
+    std::vector<uint32_t> faces;
+};
+
+// generate_texture_patches.cpp:520-535 + merge: per vertex one entry per patch (ascending patch id), first projection
+// wins, faces appended.  slot order is patch major, so entries arrive in ascending patch order.
+inline void vertex_projections(uint32_t num_verts, const uint32_t *mesh_faces, const PatchPlan &plan, const uint32_t *slot_face,
+                               const float *tex /* [slots][3][2] */, std::vector<std::vector<VertexProj> > &vpi)
+{
+    vpi.assign(num_verts, std::vector<VertexProj>());
+    const uint32_t T = plan.num_slots();
+    for (uint32_t t = 0; t < T; ++t) {
+        const uint32_t f = slot_face[t], q = plan.slot_patch[t];
+        for (int j = 0; j < 3; ++j) {
+            std::vector<VertexProj> &e = vpi[mesh_faces[3 * (size_t)f + j]];
+            if (e.empty() || e.back().patch != q) {
+                VertexProj p; p.patch = q; p.x = tex[6 * (size_t)t + 2 * j]; p.y = tex[6 * (size_t)t + 2 * j + 1];
+                e.push_back(p);
+            }
+            e.back().faces.push_back(f);
+        }
+    }
+}
+
+struct SeamLines {
+    // per seam edge: [proj_begin, proj_count, sample_begin, sample_count]
+    std::vector<uint32_t> edge_info;
+    std::vector<float> edge_proj;        // per projection: p1.x, p1.y, p2.x, p2.y
+    std::vector<uint32_t> proj_patch;    // per projection
+    std::vector<uint32_t> sample_edge;   // per colour sample: its edge
+    // per multi-patch vertex: [proj_begin, proj_count]; projections share the layout of edge projections (x, y only)
+    std::vector<uint32_t> vert_info;
+    std::vector<float> vert_proj;        // per vertex projection: x, y
+    std::vector<uint32_t> vert_proj_patch;
+    uint32_t num_edges() const { return (uint32_t)(edge_info.size() / 4); }
+    uint32_t num_samples() const { return (uint32_t)sample_edge.size(); }
+    uint32_t num_verts() const { return (uint32_t)(vert_info.size() / 2); }
+};
+
+// find_seam_edges (seam_leveling.cpp:16-59), find_mesh_edge_projections (:61-91), the sampling density of
+// local_seam_leveling.cpp:131-140 and the vertex list of :155-176
+inline void plan_seam_lines(uint32_t F, const uint32_t *adj_ptr, const uint32_t *adj_idx, const uint32_t *labels,
+                            const uint32_t *mesh_faces, const std::vector<std::vector<VertexProj> > &vpi, SeamLines &out)
+{
+    out = SeamLines();
+    for (uint32_t node = 0; node < F; ++node)
+        for (uint32_t a = adj_ptr[node]; a < adj_ptr[node + 1]; ++a) {
+            const uint32_t adj = adj_idx[a];
+            if (node > adj || labels[node] == labels[adj]) continue;
+            uint32_t shared[4]; int ns = 0;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    if (mesh_faces[3 * (size_t)node + i] == mesh_faces[3 * (size_t)adj + j] && ns < 4) shared[ns++] = mesh_faces[3 * (size_t)node + i];
+            if (ns != 2 || shared[0] == shared[1]) continue;   // the reference asserts this
+            uint32_t v1 = shared[0], v2 = shared[1];
+            if (v1 > v2) std::swap(v1, v2);
+            const uint32_t pb = (uint32_t)out.proj_patch.size();
+            float max_length = 1.0f;
+            for (const VertexProj &p1 : vpi[v1])
+                for (const VertexProj &p2 : vpi[v2]) {
+                    if (p1.patch != p2.patch) continue;
+                    bool common = false;
+                    for (uint32_t f1 : p1.faces) { for (uint32_t f2 : p2.faces) if (f1 == f2) { common = true; break; } if (common) break; }
+                    if (!common) continue;
+                    out.proj_patch.push_back(p1.patch);
+                    out.edge_proj.push_back(p1.x); out.edge_proj.push_back(p1.y); out.edge_proj.push_back(p2.x); out.edge_proj.push_back(p2.y);
+                    const float dx = p1.x - p2.x, dy = p1.y - p2.y;
+                    const float length = sqrtf((0.0f + dx * dx) + dy * dy);
+                    max_length = std::max(max_length, length);
+                }
+            const uint32_t n = (uint32_t)std::ceil(max_length * 2.0f);   // :139
+            const uint32_t sb = (uint32_t)out.sample_edge.size();
+            const uint32_t e = out.num_edges();
+            for (uint32_t j = 0; j < n; ++j) out.sample_edge.push_back(e);
+            const uint32_t info[4] = {pb, (uint32_t)out.proj_patch.size() - pb, sb, n};
+            out.edge_info.insert(out.edge_info.end(), info, info + 4);
+        }
+    for (uint32_t v = 0; v < (uint32_t)vpi.size(); ++v) {
+        if (vpi[v].size() <= 1) continue;                            // :157
+        const uint32_t info[2] = {(uint32_t)out.vert_proj_patch.size(), (uint32_t)vpi[v].size()};
+        out.vert_info.insert(out.vert_info.end(), info, info + 2);
+        for (const VertexProj &p : vpi[v]) { out.vert_proj_patch.push_back(p.patch); out.vert_proj.push_back(p.x); out.vert_proj.push_back(p.y); }
     }
 }
 

@@ -106,6 +106,17 @@ static bool launch(unsigned grid, unsigned block, F body, unsigned long long max
     return true;
 }
 
+// kernels WITHOUT any synchronisation: every (block, thread) index runs to completion in order, no fibers (fast).
+// A kernel that does reach a barrier / shuffle here dereferences g_cur == nullptr and crashes -- by design.
+template <typename F>
+static void launch_serial(unsigned grid, unsigned block, F body)
+{
+    gridDim.x = grid; blockDim.x = block;
+    g_cur = nullptr;
+    for (unsigned b = 0; b < grid; ++b)
+        for (unsigned t = 0; t < block; ++t) { blockIdx.x = b; threadIdx.x = t; body(); }
+}
+
 template <typename T> static inline unsigned long long to_bits(T v) { unsigned long long b = 0; memcpy(&b, &v, sizeof(T)); return b; }
 template <typename T> static inline T from_bits(unsigned long long b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
 

@@ -58,10 +58,12 @@ def emul():
     with open(os.path.join(OUT, "seam_kernels.inc"), "w") as f:
         f.write(_kernel_part("seam.cu", "int seam_run(b2tex_ctx"))
     with open(os.path.join(OUT, "patches_kernels.inc"), "w") as f:
-        f.write(_kernel_part("patches.cu", "void patches_free(b2tex_ctx", ("struct PatchState {", "namespace {")))
+        f.write(_kernel_part("patches.cu", "void patches_free(b2tex_ctx"))
+    with open(os.path.join(OUT, "localseam_kernels.inc"), "w") as f:
+        f.write(_kernel_part("localseam.cu", "int local_seam_run(b2tex_ctx"))
     libs = {}
     cpp = os.path.join(ROOT, "tests", "cpp")
-    for name in ("emul_bvh", "emul_datacosts", "emul_mrf", "emul_seam", "emul_patches"):
+    for name in ("emul_bvh", "emul_datacosts", "emul_mrf", "emul_seam", "emul_patches", "emul_localseam"):
         so = os.path.join(OUT, name + ".so")
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w",
                                "-I" + os.path.join(cpp, "emul_include"), "-I" + cpp, "-I" + CUDA_INC, "-I" + CSRC,
@@ -367,3 +369,96 @@ def test_patch_plan_merge_chains(emul):
                 assert chain[c, :2 * len(ch)].tolist() == [v for o in ch for v in o]
                 chains_seen += len(ch) >= 2
     assert chains_seen > 10
+
+
+# ---- local seam leveling (csrc/localseam.cu) ---------------------------------------------------------------------------
+def _emul_pipeline(emul, orc, s, adj, labels, seam, stage):
+    L = emul["emul_localseam"]
+    views, keep = orc.make_views(s)
+    ptrs = [C.c_void_p() for _ in range(6)]
+    sizes = np.zeros(8, np.uint64)
+    labels = np.ascontiguousarray(labels, np.uint32)
+    x = np.ascontiguousarray(seam["x"], np.float32)
+    rc = L.emul_texture_pipeline(orc._p(s.verts), C.c_uint32(s.verts.shape[0]), orc._p(s.faces), C.c_uint32(s.num_faces), orc._p(adj[0]),
+                                 orc._p(adj[1]), orc._p(labels), views, C.c_uint32(s.num_views), orc._p(seam["row_ptr"]),
+                                 orc._p(seam["row_label"]), orc._p(x), C.c_uint32(len(seam["row_label"])), stage,
+                                 *[C.byref(p) for p in ptrs], orc._p(sizes))
+    assert rc == 0, "the Poisson CG launch did not terminate" if rc == -1 else rc
+    n, T, Pn = (int(v) for v in sizes[:3])
+    def grab(p, ct, k):
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), (max(k, 1),))[:k].copy()
+        L.emul_local_free(p)
+        return a
+    desc = grab(ptrs[0], C.c_int32, 8 * n).reshape(n, 8)
+    faces, tex = grab(ptrs[1], C.c_uint32, T), grab(ptrs[2], C.c_float, 6 * T).reshape(-1, 2)
+    img, val, bl = grab(ptrs[3], C.c_float, 3 * Pn).reshape(-1, 3), grab(ptrs[4], C.c_uint8, Pn), grab(ptrs[5], C.c_uint8, Pn)
+    out, off = [], 0
+    for q in range(n):
+        label, mx, my, w, h, first, nf, _ = (int(v) for v in desc[q])
+        out.append(dict(label=label, faces=faces[first:first + nf].tolist(), image=img[off:off + w * h].reshape(h, w, 3),
+                        validity=val[off:off + w * h].reshape(h, w), blending=bl[off:off + w * h].reshape(h, w)))
+        off += w * h
+    return out, sizes
+
+
+@pytest.fixture(scope="module")
+def local_inputs(orc, scene_mod, get_scene):
+    cache = {}
+    def _get(name):
+        if name not in cache:
+            import patches as P
+            s = get_scene(name)
+            adj = scene_mod.face_adjacency(s.faces)
+            rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
+            dc = orc.data_costs(s)
+            labels = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1)["labels"]
+            seam = orc.global_seam_leveling(s, rings, labels)
+            pp, pvpi = P.generate_texture_patches(orc, s, adj, labels)
+            cache[name] = (s, adj, rings, labels, seam, pp, pvpi)
+        return cache[name]
+    return _get
+
+
+@pytest.mark.parametrize("name", ["tiny", "occ"])
+def test_device_seam_colours_stamping_and_blending_mask(emul, orc, local_inputs, name, monkeypatch):
+    """csrc/localseam.cu up to the Poisson solve vs oracle/patches.local_seam_leveling with the solve switched off: the
+    images with the mean seam / vertex colours stamped in ("last writer wins" by atomicMax on the write order) and the
+    blending masks after prepare_blending_mask (breadth-first layering, 20 px strip) are bit-identical."""
+    import patches as P
+    s, adj, rings, labels, seam, pp, pvpi = local_inputs(name)
+    pa = P.apply_adjust_values(s, pp, seam["row_ptr"], seam["row_label"], seam["x"])
+    monkeypatch.setattr(P, "poisson_blend", lambda *a, **k: None)
+    P.local_seam_leveling(s, adj, labels, pa, pvpi)
+    ep, sizes = _emul_pipeline(emul, orc, s, adj, labels, seam, 1)
+    assert len(ep) == len(pa) and sizes[3] > 20 and sizes[5] > 20
+    for a, b in zip(ep, pa):
+        assert np.array_equal(a["blending"], b.blending)
+        assert np.array_equal(a["image"].view(np.uint32), b.image.view(np.uint32))
+        assert (a["blending"] == 128).any() and (a["blending"] == 255).any()
+
+
+def test_device_local_seam_leveling(emul, orc, local_inputs):
+    """Full tex::local_seam_leveling on the device kernels (one batched CG over all patches, on fibers) vs the oracle
+    (scipy splu per patch) and, when libtexref.so is there, vs the reference's own translation units (SparseLU shim):
+    same validity masks, images within 5e-5 (CG tolerance 1e-5 relative residual; 8-bit quantisation is 4e-3)."""
+    import patches as P
+    s, adj, rings, labels, seam, pp, pvpi = local_inputs("tiny")
+    pa = P.apply_adjust_values(s, pp, seam["row_ptr"], seam["row_label"], seam["x"])
+    before = [q.image.copy() for q in pa]
+    P.local_seam_leveling(s, adj, labels, pa, pvpi)
+    ep, sizes = _emul_pipeline(emul, orc, s, adj, labels, seam, 2)
+    assert sizes[6] > 1000 and 10 < sizes[7] < 1000               # unknowns, CG iterations
+    for a, b, b0 in zip(ep, pa, before):
+        assert np.array_equal(a["validity"], b.validity)
+        assert np.abs(a["image"] - b.image).max() < 5e-5
+    assert max(float(np.abs(b.image - b0).max()) for b, b0 in zip(pa, before)) > 0.01
+    try:
+        import refpin
+        have_ref = refpin.available()
+    except Exception:
+        have_ref = False
+    if have_ref:
+        rp, _ = refpin.seam_leveling(s, rings, adj, labels, do_global=True, do_local=True)
+        for a, r in zip(ep, [q for q in rp if q.label != 0]):
+            assert np.array_equal(a["validity"], r.validity)
+            assert np.abs(a["image"] - r.image).max() < 5e-5

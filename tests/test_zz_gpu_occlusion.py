@@ -89,3 +89,35 @@ def test_texture_patches_and_adjust_colors(b2, get_scene, scene_mod, orc, name):
     pa = P.apply_adjust_values(s, pp, d["row_ptr"], d["row_label"], d["x"])
     check(c.texture_patches_download(info), [(q.label, q.faces, q.texcoords, q.image, q.validity, q.blending) for q in pa])
     c.close()
+
+
+def test_local_seam_leveling(b2, get_scene, scene_mod, orc):
+    """b2tex_local_seam_leveling_run (csrc/localseam.cu) after the global leveling, against oracle/patches.local_seam_leveling
+    (pinned to the reference's own translation units to 2e-5): same validity masks, images within 1e-4 -- the device
+    solves all patches with one batched CG (tolerance 1e-5) where the reference factorises each patch with SparseLU."""
+    import patches as P
+    s = get_scene("tiny")
+    ap, ai = scene_mod.face_adjacency(s.faces)
+    rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
+    dc = orc.data_costs(s)
+    labels = orc.view_selection(ap, ai, dc["face_ptr"], dc["view"], dc["cost"], threads=1)["labels"]
+    c = b2.Context(0)
+    c.set_scene(s)
+    c.set_adjacency(ap, ai)
+    c.set_vertex_rings(*rings)
+    c.set_labels(labels)
+    sinfo = c.seam_run()
+    d = c.seam_download(sinfo)
+    pinfo = c.texture_patches_run(apply_adjust=True)
+    linfo = c.local_seam_leveling_run()
+    got = c.texture_patches_download(pinfo)
+    c.close()
+    pp, pvpi = P.generate_texture_patches(orc, s, (ap, ai), labels)
+    pa = P.apply_adjust_values(s, pp, d["row_ptr"], d["row_label"], d["x"])
+    P.local_seam_leveling(s, (ap, ai), labels, pa, pvpi)
+    assert linfo.num_seam_edges == len(P.find_seam_edges(s, (ap, ai), labels)) and linfo.num_unknowns > 1000
+    assert all(r < 2e-5 for r in linfo.residual) and max(linfo.iterations) < 2000
+    assert len(got) == len(pa)
+    for a, b in zip(got, pa):
+        assert np.array_equal(a["validity"], b.validity)
+        assert np.abs(a["image"] - b.image).max() < 1e-4
