@@ -68,3 +68,55 @@ def test_labeling_vec_format(ic, tmp_path):
         ic.load_labeling(p, 5, 3)                          # wrong face count
     with pytest.raises(ic.FileException):
         ic.load_labeling(p, 4, 2)                          # label 3 > 2 views
+
+
+def test_timings_csv_format(tmp_path):
+    """Timer::write_to_file (libs/tex/timer.cpp:42-61) with texrecon's event names (texrecon.cpp:86-211)"""
+    ic = importlib.import_module("mvs-texturing_b200.interchange")
+    log = ic.TimingLog(header="b200")
+    for i, name in enumerate(ic.TIMING_EVENTS):
+        log.measure(name, abs_ms=10 * (i + 1) ** 2, abs_clocks=1000 * (i + 1))
+    p = str(tmp_path / "OUT_timings.csv")
+    log.write_to_file(p)
+    lines = open(p).read().splitlines()
+    assert lines[0] == "#b200"
+    assert lines[1] == "Event, Absolute clocks, Absolute milliseconds, Relative clocks, Relative milliseconds"
+    assert lines[2] == "Loading, 1000, 10, 1000, 10"
+    assert lines[3] == "Calculating data costs, 2000, 40, 1000, 30"
+    assert len(lines) == 2 + len(ic.TIMING_EVENTS) and lines[-1].startswith("Total, ")
+    assert [r[0] for r in ic.load_timings(p)] == list(ic.TIMING_EVENTS)
+
+
+def test_cam_file_round_trip(tmp_path, scene_mod):
+    """.cam as generate_texture_views.cpp:118-151 reads it; a synthetic camera survives save -> load and projects a point
+    to the same pixel as the scene's own TextureView record."""
+    ic = importlib.import_module("mvs-texturing_b200.interchange")
+    s = scene_mod.config("tiny", with_images=False)
+    k = 2
+    w2c = s.w2c[k].reshape(4, 4)
+    proj = s.proj[k].reshape(3, 3)
+    flen = float(proj[0, 0]) / max(s.width, s.height)          # MVE normalises by the larger side
+    p = str(tmp_path / "view.cam")
+    ic.save_cam(p, w2c, flen)
+    cam = ic.load_cam(p, s.width, s.height)
+    assert np.allclose(cam["w2c"], s.w2c[k], atol=1e-6) and np.allclose(cam["pos"], s.pos[k], atol=1e-5)
+    assert np.allclose(cam["viewdir"], s.viewdir[k], atol=1e-6) and np.allclose(cam["proj"], s.proj[k], rtol=1e-5)
+    with open(p, "w") as f:
+        f.write("1 2 3\n0.9\n")
+    with pytest.raises(ic.FileException):
+        ic.load_cam(p, 640, 480)
+
+
+@pytest.mark.parametrize("binary", [True, False])
+def test_ply_round_trip(tmp_path, scene_mod, binary):
+    ic = importlib.import_module("mvs-texturing_b200.interchange")
+    s = scene_mod.config("tiny", with_images=False)
+    p = str(tmp_path / "mesh.ply")
+    ic.save_ply(p, s.verts, s.faces, binary=binary)
+    v, f = ic.load_ply(p)
+    assert np.array_equal(f, s.faces)
+    assert np.array_equal(v, s.verts) if binary else np.allclose(v, s.verts, atol=1e-7)
+    with open(p, "wb") as fh:
+        fh.write(b"plx\n")
+    with pytest.raises(ic.FileException):
+        ic.load_ply(p)
