@@ -478,10 +478,12 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
     std::vector<uint32_t> adj_idx(adj_ptr[F] ? adj_ptr[F] : 1);
     B2_TRY(c->adj_idx.download(adj_idx.data(), adj_ptr[F], s));
     B2_CUDA(cudaStreamSynchronize(s));
+    std::vector<uint32_t> seam_edges;
+    find_seam_edges(F, adj_ptr.data(), adj_idx.data(), labels.data(), mesh_faces.data(), seam_edges);
     std::vector<std::vector<VertexProj> > vpi;
-    vertex_projections(c->Vn, mesh_faces.data(), pl, ps.faces.data(), tex.data(), vpi);
+    vertex_projections(c->Vn, mesh_faces.data(), pl, ps.faces.data(), tex.data(), seam_edges, vpi);
     SeamLines sl;
-    plan_seam_lines(F, adj_ptr.data(), adj_idx.data(), labels.data(), mesh_faces.data(), vpi, sl);
+    plan_seam_lines(seam_edges, vpi, sl);
     const uint32_t NE = sl.num_edges(), S = sl.num_samples(), NV = sl.num_verts();
     const uint32_t NL = (uint32_t)sl.proj_patch.size(), NVP = (uint32_t)sl.vert_proj_patch.size();
     std::vector<uint32_t> proj_edge(NL ? NL : 1), vproj_vert(NVP ? NVP : 1);
