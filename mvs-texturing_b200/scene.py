@@ -364,7 +364,8 @@ def face_adjacency(faces: np.ndarray):
     # UniGraph::add_edge (uni_graph.h:80-88) appends to BOTH lists when the lower face is
     # visited, so a row holds lower-id neighbours first (ascending), then higher ones by slot.
     hi_side = (b > a).astype(np.int64)
-    o = np.lexsort((np.where(b < a, b, s), hi_side, a))
+    # several higher faces on one (non-manifold) edge: MeshInfo::get_faces_for_edge order = ascending face id here
+    o = np.lexsort((b, np.where(b < a, b, s), hi_side, a))
     a, b, s = a[o], b[o], s[o]
     # drop duplicate (a,b) keeping first occurrence in (slot) order
     ab = a * F + b

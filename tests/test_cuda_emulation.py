@@ -462,3 +462,47 @@ def test_device_local_seam_leveling(emul, orc, local_inputs):
         for a, r in zip(ep, [q for q in rp if q.label != 0]):
             assert np.array_equal(a["validity"], r.validity)
             assert np.abs(a["image"] - r.image).max() < 5e-5
+
+
+def _random_mrf_problem(rng, n, extra_edges, K, max_labels, unseen_frac=0.03):
+    """ring + random chords: node degrees up to ~8 (face graphs of non-manifold meshes exceed 3)"""
+    edges = set((i, (i + 1) % n) for i in range(n))
+    while len(edges) < n + extra_edges:
+        a, b = rng.randint(n, size=2)
+        if a != b:
+            edges.add((min(a, b), max(a, b)))
+    adj = [[] for _ in range(n)]
+    for a, b in sorted(edges):
+        adj[a].append(b); adj[b].append(a)
+    ap = np.zeros(n + 1, np.uint32)
+    ap[1:] = np.cumsum([len(x) for x in adj])
+    ai = np.array([w for x in adj for w in x], np.uint32)
+    ptr, view, cost = [0], [], []
+    for i in range(n):
+        k = 0 if rng.rand() < unseen_frac else rng.randint(1, max_labels + 1)
+        view += np.sort(rng.choice(K, size=k, replace=False)).tolist()
+        cost += rng.uniform(0, 1, size=k).astype(np.float32).tolist()
+        ptr.append(len(view))
+    return ap, ai, np.array(ptr, np.uint64), np.array(view, np.uint16), np.array(cost, np.float32)
+
+
+@pytest.mark.parametrize("case", ["degree>3", "degree>3, no label masks", "3000 views, binary search", "64 labels per node"])
+def test_device_view_selection_generic_paths(emul, orc, case):
+    """Code paths of k_up / k_down / k_energy no mesh-derived test reaches: neighbour lists longer than 3 (CSR fallback
+    instead of the packed adjacency), more than 2047 views (no label bitmasks: binary search in the sorted label lists),
+    long label lists (several strides of the lane loop)."""
+    rng = np.random.RandomState(7)
+    n, extra, K, maxl, Kdev, group = {"degree>3": (600, 500, 12, 6, 12, 0), "degree>3, no label masks": (600, 500, 12, 6, 5000, 0),
+                                      "3000 views, binary search": (500, 0, 3000, 40, 3000, 32),
+                                      "64 labels per node": (400, 300, 70, 64, 70, 0)}[case]
+    ap, ai, ptr, view, cost = _random_mrf_problem(rng, n, extra, K, maxl)
+    o = orc.view_selection(ap, ai, ptr, view, cost, threads=1)
+    P = dict(orc.DEFAULT_MRF)
+    params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], P["num_parts"], group, 2, 2], np.uint32)
+    labels = np.zeros(n, np.uint32)
+    trace = np.full(P["max_iterations"] + 1, np.nan)
+    it = emul["emul_mrf"].emul_view_selection(C.c_uint32(n), C.c_uint32(Kdev), orc._p(ap), orc._p(ai), orc._p(ptr), orc._p(view), orc._p(cost),
+                                              orc._p(params), C.c_float(P["ratio"]), orc._p(labels), orc._p(trace), None)
+    assert it == o["iterations"] and np.array_equal(labels, o["labels"])
+    if extra:
+        assert int(np.diff(ap).max()) > 3

@@ -297,3 +297,21 @@ def test_local_seam_leveling_matches_reference_tu(ref, orc, seam_inputs):
         assert np.abs(a.image - b.image).max() < 2e-5
         changed = max(changed, float(np.abs(b.image - b0).max()))
     assert changed > 0.01
+
+
+def test_adjacency_of_non_manifold_mesh_matches_reference_tu(ref, scene_mod, get_scene):
+    """An edge shared by three faces (a fin glued onto `tiny`): tex::build_adjacency_graph links all of them; the order of
+    the adjacency lists is what scene.face_adjacency has to reproduce (face graphs with degree > 3 take the generic paths of
+    the MRF kernels)."""
+    s = get_scene("tiny")
+    verts = np.concatenate([s.verts, (s.verts[s.faces[5]].mean(0) * 1.3)[None].astype(np.float32),
+                            (s.verts[s.faces[40]].mean(0) * 1.3)[None].astype(np.float32)], 0)
+    nv = verts.shape[0]
+    fins = np.array([[s.faces[5][0], s.faces[5][1], nv - 2], [s.faces[5][1], s.faces[5][2], nv - 2],
+                     [s.faces[40][2], s.faces[40][0], nv - 1]], np.uint32)
+    faces = np.ascontiguousarray(np.concatenate([s.faces, fins], 0))
+    rings = scene_mod.vertex_rings(faces, nv)
+    r_ptr, r_idx = ref.build_adjacency(faces, nv, rings)
+    a_ptr, a_idx = scene_mod.face_adjacency(faces)
+    assert int(np.diff(r_ptr).max()) > 3
+    assert np.array_equal(r_ptr, a_ptr) and np.array_equal(r_idx, a_idx)
