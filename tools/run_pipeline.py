@@ -8,6 +8,7 @@ scene = importlib.import_module("mvs-texturing_b200.scene")
 
 name = sys.argv[1] if len(sys.argv) > 1 else "C2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+with_patches = "--patches" in sys.argv   # also run texture patches + adjust_colors + local seam leveling
 t = time.time(); s = scene.config(name); print(f"scene {name}: F={s.num_faces} K={s.num_views} gen {time.time()-t:.1f}s", flush=True)
 t = time.time(); ap, ai = scene.face_adjacency(s.faces); rings = scene.vertex_rings(s.faces, s.verts.shape[0]); print(f"graph {time.time()-t:.1f}s", flush=True)
 c = b2.Context(0)
@@ -21,6 +22,11 @@ for rep in range(reps):
           f"mrf {1e3*(t2-t1):.1f} ms (it={minfo.iterations} E0={minfo.energy_initial:.1f} E={minfo.energy_final:.1f})  "
           f"seam {1e3*(t3-t2):.1f} ms (R={sinfo.num_rows} nnzL={sinfo.nnz_full} A={sinfo.num_a_rows} it={list(sinfo.iterations)} cg_ms={sinfo.cg_ms:.2f})  "
           f"total {1e3*(t3-t0):.1f} ms -> {s.num_faces/(t3-t0):.0f} faces/s", flush=True)
+    if with_patches:
+        t4 = time.time(); pinfo = c.texture_patches_run(apply_adjust=True); t5 = time.time()
+        linfo = c.local_seam_leveling_run(); t6 = time.time()
+        print(f"        patches {1e3*(t5-t4):.1f} ms (n={pinfo.num_patches} px={pinfo.num_pixels})  local seam {1e3*(t6-t5):.1f} ms "
+              f"(edges={linfo.num_seam_edges} unknowns={linfo.num_unknowns} it={list(linfo.iterations)} res={[f'{r:.1e}' for r in linfo.residual]})", flush=True)
     rep_ = c.profile_report()
     agg = {}
     for n_, ms, by in rep_:
