@@ -158,6 +158,16 @@ int b2tex_mrf_sample_forest(b2tex_ctx *ctx, const b2tex_mrf_params *params, uint
                             uint32_t *level_out_host);
 
 int b2tex_seam_run(b2tex_ctx *ctx, b2tex_seam_info *info);
+/* Multi-GPU solve of the same system (one process per GPU): every rank assembles (b2tex_seam_assemble = b2tex_seam_run
+ * without the PCG), allocates a peer-visible exchange block and exports its 64-byte cudaIpc handle, imports the handles
+ * of all peers (exchanged by the caller, e.g. an all-gather over torch.distributed), then every rank calls
+ * b2tex_seam_mg_solve: one persistent cooperative kernel per GPU that runs the PCG on its slice of the rows and exchanges
+ * the search direction and the dot products with its peers through NVLink peer memory inside the kernel.  Every rank ends
+ * with the complete solution (b2tex_seam_download).  At most 8 ranks.  Not yet run on hardware (emulation only). */
+int b2tex_seam_assemble(b2tex_ctx *ctx, b2tex_seam_info *info);
+int b2tex_seam_mg_export(b2tex_ctx *ctx, uint32_t rank, uint32_t num_ranks, void *ipc_handle_64_bytes);
+int b2tex_seam_mg_import(b2tex_ctx *ctx, uint32_t peer_rank, const void *ipc_handle_64_bytes);
+int b2tex_seam_mg_solve(b2tex_ctx *ctx, b2tex_seam_info *info);
 int b2tex_seam_download(b2tex_ctx *ctx, uint32_t *row_ptr, uint32_t *row_label, float *x,
                         float *rhs_or_null);
 /* full symmetric CSR of Lhs (for tests / inspection); arrays sized from b2tex_seam_info */

@@ -29,7 +29,8 @@ EXPORTS = [
     "b2tex_data_costs_normalize", "b2tex_data_costs_download", "b2tex_view_selection_run",
     "b2tex_labels_download", "b2tex_mrf_init", "b2tex_mrf_iterate", "b2tex_mrf_energy", "b2tex_mrf_sample_forest",
     "b2tex_seam_run", "b2tex_seam_download", "b2tex_seam_matrix_download", "b2tex_device_ptr",
-    "b2tex_texture_patches_run", "b2tex_texture_patches_download", "b2tex_local_seam_leveling_run",
+    "b2tex_texture_patches_run", "b2tex_texture_patches_download", "b2tex_local_seam_leveling_run", "b2tex_seam_assemble", "b2tex_seam_mg_export", "b2tex_seam_mg_import",
+    "b2tex_seam_mg_solve",
     "b2tex_calculate_data_costs", "b2tex_calculate_data_costs_into", "b2tex_view_selection",
     "b2tex_global_seam_leveling", "b2tex_texture_hot_path",
 ]
@@ -285,6 +286,24 @@ class Context:
     def seam_run(self):
         info = B2SeamInfo()
         _check(lib().b2tex_seam_run(self._h, C.byref(info)))
+        return info
+
+    # multi-GPU seam solve (csrc/seam_mg.cu): assemble, exchange the IPC handles of the peer blocks, solve
+    def seam_assemble(self):
+        info = B2SeamInfo()
+        _check(lib().b2tex_seam_assemble(self._h, C.byref(info)))
+        return info
+
+    def seam_mg_export(self, rank, num_ranks) -> bytes:
+        h = C.create_string_buffer(64)
+        _check(lib().b2tex_seam_mg_export(self._h, C.c_uint32(rank), C.c_uint32(num_ranks), h))
+        return h.raw
+
+    def seam_mg_import(self, peer_rank, handle: bytes):
+        _check(lib().b2tex_seam_mg_import(self._h, C.c_uint32(peer_rank), C.c_char_p(handle)))
+
+    def seam_mg_solve(self, info):
+        _check(lib().b2tex_seam_mg_solve(self._h, C.byref(info)))
         return info
 
     def seam_download(self, info, rhs=False):

@@ -64,6 +64,7 @@ void b2tex_destroy(b2tex_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     patches_free(c);
+    seam_mg_free(c);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -338,6 +339,31 @@ int b2tex_seam_run(b2tex_ctx *c, b2tex_seam_info *info)
 {
     B2_CUDA(cudaSetDevice(c->device));
     return seam_run(c, info);
+}
+
+// ---- multi-GPU seam solve: assembly on every rank, then one fused compute + exchange kernel per GPU (seam_mg.cu) ----
+int b2tex_seam_assemble(b2tex_ctx *c, b2tex_seam_info *info)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return seam_run(c, info, false);
+}
+
+int b2tex_seam_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t num_ranks, void *ipc_handle_64_bytes)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return seam_mg_export(c, rank, num_ranks, ipc_handle_64_bytes);
+}
+
+int b2tex_seam_mg_import(b2tex_ctx *c, uint32_t peer_rank, const void *ipc_handle_64_bytes)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return seam_mg_import(c, peer_rank, ipc_handle_64_bytes);
+}
+
+int b2tex_seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return seam_mg_solve(c, info);
 }
 
 int b2tex_seam_download(b2tex_ctx *c, uint32_t *row_ptr, uint32_t *row_label, float *x, float *rhs)

@@ -119,6 +119,7 @@ struct KTimer {
 }  // namespace b2
 
 namespace b2 { struct PatchState; }  // texture patches (patches.cu)
+namespace b2 { struct MgState; }     // multi-GPU seam solve (seam_mg.cu)
 
 // The opaque C-ABI context.
 struct b2tex_ctx {
@@ -208,6 +209,8 @@ struct b2tex_ctx {
 
     // texture patches (allocated on first use, released by patches_free)
     b2::PatchState *patches = nullptr;
+    // peer-memory blocks of the multi-GPU seam solve (seam_mg.cu)
+    b2::MgState *seam_mg = nullptr;
 };
 
 namespace b2 {
@@ -240,7 +243,11 @@ int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *energy_fixed);
 int mrf_energy_only(b2tex_ctx *c, int64_t *energy_fixed);
 int mrf_sample_only(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t, uint32_t *level_host);
 int mrf_energy_double(b2tex_ctx *c, double *e, uint64_t *unseen);
-int seam_run(b2tex_ctx *c, b2tex_seam_info *info);
+int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve = true);
+int seam_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t nranks, void *handle64);
+int seam_mg_import(b2tex_ctx *c, uint32_t peer_rank, const void *handle64);
+int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info);
+void seam_mg_free(b2tex_ctx *c);
 int patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info);
 int patches_download(b2tex_ctx *c, int32_t *desc, uint32_t *faces, float *texcoords, float *images, uint8_t *validity,
                      uint8_t *blending);

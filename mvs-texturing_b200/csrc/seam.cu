@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg(Pcg q)
 
 }  // namespace
 
-int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
+int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
 {
     if (!c->Vn || !c->have_rings || !c->have_labels || !c->K) {
         set_error("seam leveling: mesh, vertex rings, labels and views must be set");
@@ -496,7 +496,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
     tm_asm.reset();
     B2_TRY(c->seam_status.alloc(16));
     B2_TRY(c->seam_status.zero(s));
-    if (R) {
+    if (R && solve) {   // solve == false: assembly only, the multi-GPU solver (seam_mg.cu) takes over
         int per_sm = 0;
         B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, PCG_THREADS, 0));
         if (per_sm < 1) { set_error("k_pcg cannot be resident"); return B2TEX_ERR_CUDA; }
@@ -527,7 +527,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info)
         info->cg_launch_iterations = st[6];
         info->cg_ms = ms;
     }
-    c->have_seam = true;
+    c->have_seam = solve;
     return B2TEX_OK;
 }
 

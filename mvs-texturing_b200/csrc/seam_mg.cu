@@ -1,0 +1,384 @@
+// seam_mg.cu -- K9': the global seam leveling solve across GPUs, ONE kernel per GPU doing compute + exchange.
+//
+// Replaces the replicated k_pcg (seam.cu) when the job runs on several GPUs (one process per GPU): the rows of
+// Lhs x = Rhs (global_seam_leveling.cpp:245-277) are split into contiguous ranges, one per rank.  Every rank runs the
+// same persistent cooperative Jacobi-PCG as k_pcg on ITS rows and, inside the kernel, exchanges with its peers through
+// peer-mapped memory (cudaIpc handles, NVLink / NVSwitch loads and stores) instead of returning to the host for NCCL:
+//   * search direction p: after "p = z + beta p" every rank STORES its slice into every peer's full-length copy of p,
+//     so the SpMV of the next iteration reads only local memory (an all-gather by stores, overlapped with the update);
+//   * dot products: every rank stores its fp64 partial sums into every peer's slot table; after the barrier all ranks
+//     add the P slots in rank order -> bit-identical scalars everywhere, no divergence of the iteration;
+//   * barrier: one epoch counter per (rank, peer) in peer memory, store-release at system scope after a system fence,
+//     polled with load-acquire; three per iteration (p.t, |r|^2 & r.z, p exchange), each bracketed by grid.sync().
+// Results are deterministic for a given rank count; they differ from the single-GPU kernel only by the summation
+// order of the reductions (per rank, then across ranks).
+//
+// STATUS (end of round 1): the kernel logic runs in the multi-rank fiber emulation (tests/cpp/emul_seam_mg.cpp) and
+// matches the oracle; it has NOT run on hardware.  mvs-texturing_b200/sharded.py keeps the replicated solve as default.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace b2 {
+
+constexpr int MG_MAX_RANKS = 8;
+
+// Layout of the peer-visible block every rank allocates (and exports through one cudaIpc handle):
+//   float4 p[R] | float x[3][R] | double part[2][MG_MAX_RANKS][8] | uint32 flag[MG_MAX_RANKS] (padded to 64 B)
+struct MgBlock {
+    float4 *p;
+    float *x;
+    double *part;
+    uint32_t *flag;
+};
+__host__ __device__ inline size_t mg_block_bytes(uint32_t R)
+{
+    return (size_t)R * 16 + (size_t)R * 12 + 2 * MG_MAX_RANKS * 8 * sizeof(double) + 64;
+}
+__host__ __device__ inline MgBlock mg_carve(void *base, uint32_t R)
+{
+    MgBlock b;
+    char *c = (char *)base;
+    b.p = (float4 *)c; c += (size_t)R * 16;
+    b.x = (float *)c; c += (size_t)R * 12;
+    b.part = (double *)c; c += 2 * MG_MAX_RANKS * 8 * sizeof(double);
+    b.flag = (uint32_t *)c;
+    return b;
+}
+
+struct PcgMg {
+    uint32_t R, r0, r1;          // system size, own row range [r0, r1)
+    uint32_t rank, nranks;
+    const uint32_t *csr_ptr, *csr_enc;
+    const float *diag_val, *inv_diag, *rhs;   // replicated assembly (k_matrix), indexed by global row
+    float *r, *t;                // [3][R] local scratch (own rows used)
+    double *blockpart;           // [grid][8] per-block partials of this rank
+    uint32_t *status;            // [0..2] iterations, [3..5] residual bits, [6] loops, [7] barrier timeouts
+    void *peer[MG_MAX_RANKS];    // base pointers of every rank's MgBlock (peer[rank] = own)
+    uint32_t max_iters;
+    float tol;
+    uint32_t epoch0;             // barrier epochs used so far (blocks are reused across solves)
+    unsigned long long spin_limit;
+};
+
+namespace {
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void mg_block_reduce6(double v[6], double *smem)
+{
+    for (int k = 0; k < 6; ++k)
+        for (int s = 16; s; s >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], s);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0)
+        for (int k = 0; k < 6; ++k) smem[warp * 6 + k] = v[k];
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int k = 0; k < 6; ++k) {
+        double s = 0.0;
+        for (int w = 0; w < nw; ++w) s += smem[w * 6 + k];
+        v[k] = s;
+    }
+}
+
+// Cross-GPU barrier, called by ALL threads of the grid.  Everything every thread of this rank stored to peer memory
+// before the call is visible to every thread of every rank after it.
+__device__ __forceinline__ bool mg_barrier(cg::grid_group &grid, const PcgMg &q, uint32_t epoch)
+{
+    __threadfence_system();   // this thread's peer stores before the rank-wide barrier
+    grid.sync();
+    bool ok = true;
+    if (blockIdx.x == 0 && threadIdx.x < q.nranks) {
+        const uint32_t k = threadIdx.x;
+        st_release_sys(mg_carve(q.peer[k], q.R).flag + q.rank, epoch);          // tell peer k: rank `rank` reached `epoch`
+        const uint32_t *mine = mg_carve(q.peer[q.rank], q.R).flag + k;          // wait until peer k reached it too
+        unsigned long long spins = 0;
+        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+            __nanosleep(64);
+            if (++spins > q.spin_limit) { ok = false; atomicAdd(q.status + 7, 1u); break; }
+        }
+    }
+    grid.sync();
+    return ok;
+}
+
+// sum of the per-block partials of this rank (every thread computes the same value), pushed to all peers by block 0
+__device__ __forceinline__ void mg_push_partials(cg::grid_group &grid, const PcgMg &q, double acc[6], double *smem, int parity)
+{
+    mg_block_reduce6(acc, smem);
+    if (threadIdx.x == 0) for (int k = 0; k < 6; ++k) q.blockpart[(size_t)blockIdx.x * 8 + k] = acc[k];
+    grid.sync();
+    if (blockIdx.x == 0) {
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+            for (int k = 0; k < 6; ++k) v[k] += q.blockpart[(size_t)b * 8 + k];
+        mg_block_reduce6(v, smem);
+        if (threadIdx.x < q.nranks)
+            for (int k = 0; k < 6; ++k)
+                mg_carve(q.peer[threadIdx.x], q.R).part[((size_t)parity * MG_MAX_RANKS + q.rank) * 8 + k] = v[k];
+    }
+}
+__device__ __forceinline__ void mg_totals(const PcgMg &q, int parity, double tot[6])
+{
+    const double *part = mg_carve(q.peer[q.rank], q.R).part + (size_t)parity * MG_MAX_RANKS * 8;
+    for (int k = 0; k < 6; ++k) {
+        double s = 0.0;
+        for (uint32_t r = 0; r < q.nranks; ++r) s += __ldcg(part + (size_t)r * 8 + k);   // rank order: identical on every GPU
+        tot[k] = s;
+    }
+}
+
+}  // namespace
+
+constexpr int MG_THREADS = 1024;
+__global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double smem[(MG_THREADS / 32) * 6];
+    const uint32_t R = q.R;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const MgBlock own = mg_carve(q.peer[q.rank], R);
+    double acc[6], tot[6];
+    uint32_t epoch = q.epoch0;
+    bool alive = true;
+
+    // r = rhs, p = M^-1 r on the own rows; p goes to every rank's copy
+    for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+    for (uint32_t i = q.r0 + tid; i < q.r1; i += nth) {
+        const float id = q.inv_diag[i];
+        float pv[3];
+        for (int c = 0; c < 3; ++c) {
+            const float rv = q.rhs[(size_t)c * R + i];
+            q.r[(size_t)c * R + i] = rv;
+            own.x[(size_t)c * R + i] = 0.0f;
+            pv[c] = id * rv;
+            acc[c] += (double)rv * rv;
+            acc[3 + c] += (double)rv * pv[c];
+        }
+        const float4 p4 = make_float4(pv[0], pv[1], pv[2], 0.0f);
+        for (uint32_t k = 0; k < q.nranks; ++k) mg_carve(q.peer[k], R).p[i] = p4;
+    }
+    mg_push_partials(grid, q, acc, smem, 0);
+    alive = mg_barrier(grid, q, ++epoch) && alive;
+    mg_totals(q, 0, tot);
+    float rhsNorm2[3], threshold[3], absNew[3], resNorm2[3];
+    bool active[3];
+    uint32_t iters[3] = {0, 0, 0};
+    for (int c = 0; c < 3; ++c) {
+        rhsNorm2[c] = (float)tot[c];
+        threshold[c] = q.tol * q.tol * rhsNorm2[c];
+        resNorm2[c] = rhsNorm2[c];
+        absNew[c] = (float)tot[3 + c];
+        active[c] = rhsNorm2[c] != 0.0f && !(resNorm2[c] < threshold[c]);
+    }
+    uint32_t loops = 0;
+    while (alive && (active[0] || active[1] || active[2])) {
+        // phase 1: t = A p on the own rows (p is complete locally), p.t
+        for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+        for (uint32_t i = q.r0 + tid; i < q.r1; i += nth) {
+            const uint32_t e1 = q.csr_ptr[i + 1];
+            const float4 pi = own.p[i];
+            const float dv = q.diag_val[i];
+            float s0 = 0.0f + dv * pi.x, s1 = 0.0f + dv * pi.y, s2 = 0.0f + dv * pi.z;
+            const float lam2 = 0.1f * 0.1f;
+            for (uint32_t e = q.csr_ptr[i] + 1; e < e1; ++e) {
+                const uint32_t enc = q.csr_enc[e];
+                const float a = (enc >> 31) ? -1.0f : -lam2;
+                const float4 pv = own.p[enc & 0x7FFFFFFFu];
+                s0 += a * pv.x; s1 += a * pv.y; s2 += a * pv.z;
+            }
+            q.t[i] = s0; q.t[(size_t)R + i] = s1; q.t[2 * (size_t)R + i] = s2;
+            acc[0] += (double)pi.x * s0; acc[1] += (double)pi.y * s1; acc[2] += (double)pi.z * s2;
+        }
+        mg_push_partials(grid, q, acc, smem, 1);
+        alive = mg_barrier(grid, q, ++epoch) && alive;
+        mg_totals(q, 1, tot);
+        float alpha[3];
+        for (int c = 0; c < 3; ++c) alpha[c] = active[c] ? absNew[c] / (float)tot[c] : 0.0f;
+
+        // phase 2: x += a p, r -= a t, |r|^2, r.z
+        for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+        for (uint32_t i = q.r0 + tid; i < q.r1; i += nth) {
+            const float4 pi = own.p[i];
+            const float pv[3] = {pi.x, pi.y, pi.z};
+            const float id = q.inv_diag[i];
+            for (int c = 0; c < 3; ++c) {
+                if (!active[c]) continue;
+                const size_t o = (size_t)c * R + i;
+                own.x[o] += alpha[c] * pv[c];
+                const float rv = q.r[o] - alpha[c] * q.t[o];
+                q.r[o] = rv;
+                acc[c] += (double)rv * rv;
+                acc[3 + c] += (double)rv * (id * rv);
+            }
+        }
+        mg_push_partials(grid, q, acc, smem, 0);
+        alive = mg_barrier(grid, q, ++epoch) && alive;
+        mg_totals(q, 0, tot);
+        float beta[3] = {0.0f, 0.0f, 0.0f};
+        bool upd[3];
+        for (int c = 0; c < 3; ++c) {
+            upd[c] = false;
+            if (!active[c]) continue;
+            resNorm2[c] = (float)tot[c];
+            if (resNorm2[c] < threshold[c]) { active[c] = false; continue; }
+            const float absOld = absNew[c];
+            absNew[c] = (float)tot[3 + c];
+            beta[c] = absNew[c] / absOld;
+            upd[c] = true;
+            if (++iters[c] >= q.max_iters) active[c] = false;
+        }
+        // phase 3: p = z + beta p on the own rows, stored into every rank's copy (the all-gather)
+        if (upd[0] || upd[1] || upd[2])
+            for (uint32_t i = q.r0 + tid; i < q.r1; i += nth) {
+                float4 pi = own.p[i];
+                const float id = q.inv_diag[i];
+                if (upd[0]) pi.x = id * q.r[i] + beta[0] * pi.x;
+                if (upd[1]) pi.y = id * q.r[(size_t)R + i] + beta[1] * pi.y;
+                if (upd[2]) pi.z = id * q.r[2 * (size_t)R + i] + beta[2] * pi.z;
+                for (uint32_t k = 0; k < q.nranks; ++k) mg_carve(q.peer[k], R).p[i] = pi;
+            }
+        ++loops;
+        alive = mg_barrier(grid, q, ++epoch) && alive;
+    }
+    // x -= mean(x) (:277), then every rank gets the complete solution
+    for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+    for (uint32_t i = q.r0 + tid; i < q.r1; i += nth)
+        for (int c = 0; c < 3; ++c) acc[c] += (double)own.x[(size_t)c * R + i];
+    mg_push_partials(grid, q, acc, smem, 1);
+    alive = mg_barrier(grid, q, ++epoch) && alive;
+    mg_totals(q, 1, tot);
+    float mean[3];
+    for (int c = 0; c < 3; ++c) mean[c] = R ? (float)(tot[c] / (double)R) : 0.0f;
+    for (uint32_t i = q.r0 + tid; i < q.r1; i += nth)
+        for (int c = 0; c < 3; ++c) {
+            const float v = own.x[(size_t)c * R + i] - mean[c];
+            for (uint32_t k = 0; k < q.nranks; ++k) mg_carve(q.peer[k], R).x[(size_t)c * R + i] = v;
+        }
+    alive = mg_barrier(grid, q, ++epoch) && alive;
+    if (tid == 0) {
+        for (int c = 0; c < 3; ++c) {
+            q.status[c] = iters[c];
+            const float err = rhsNorm2[c] != 0.0f ? sqrtf(resNorm2[c] / rhsNorm2[c]) : 0.0f;
+            q.status[3 + c] = __float_as_uint(err);
+        }
+        q.status[6] = loops;
+        q.status[8] = epoch;
+    }
+}
+
+// ---- host side: peer block management and launch -----------------------------------------------------------------
+struct MgState {
+    void *block = nullptr;                 // own MgBlock (cudaMalloc)
+    void *peer[MG_MAX_RANKS] = {nullptr};  // opened peers (peer[rank] = block)
+    bool opened[MG_MAX_RANKS] = {false};
+    uint32_t R = 0, rank = 0, nranks = 1, epoch = 0;
+    DevBuf<double> blockpart;
+    DevBuf<uint32_t> status;
+};
+
+void seam_mg_free(b2tex_ctx *c)
+{
+    MgState *m = c->seam_mg;
+    if (!m) return;
+    for (uint32_t k = 0; k < MG_MAX_RANKS; ++k)
+        if (m->opened[k] && m->peer[k]) cudaIpcCloseMemHandle(m->peer[k]);
+    if (m->block) cudaFree(m->block);
+    delete m;
+    c->seam_mg = nullptr;
+}
+
+// assembly must have run (b2tex_seam_assemble); allocates the peer block for R rows and returns its IPC handle
+int seam_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t nranks, void *handle64)
+{
+    if (!c->R) { set_error("seam_mg_export: assemble the seam system first"); return B2TEX_ERR_ARG; }
+    if (nranks < 1 || nranks > (uint32_t)MG_MAX_RANKS || rank >= nranks) { set_error("seam_mg_export: at most %d ranks", MG_MAX_RANKS); return B2TEX_ERR_ARG; }
+    seam_mg_free(c);
+    MgState *m = new MgState();
+    c->seam_mg = m;
+    m->R = c->R; m->rank = rank; m->nranks = nranks;
+    const size_t bytes = mg_block_bytes(c->R);
+    B2_CUDA(cudaMalloc(&m->block, bytes));
+    B2_CUDA(cudaMemsetAsync(m->block, 0, bytes, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    m->peer[rank] = m->block;
+    cudaIpcMemHandle_t h;
+    B2_CUDA(cudaIpcGetMemHandle(&h, m->block));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle64, &h, 64);
+    return B2TEX_OK;
+}
+
+int seam_mg_import(b2tex_ctx *c, uint32_t peer_rank, const void *handle64)
+{
+    MgState *m = c->seam_mg;
+    if (!m || peer_rank >= m->nranks) { set_error("seam_mg_import: export first"); return B2TEX_ERR_ARG; }
+    if (peer_rank == m->rank) return B2TEX_OK;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    B2_CUDA(cudaIpcOpenMemHandle(&m->peer[peer_rank], h, cudaIpcMemLazyEnablePeerAccess));
+    m->opened[peer_rank] = true;
+    return B2TEX_OK;
+}
+
+int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info)
+{
+    MgState *m = c->seam_mg;
+    if (!m || m->R != c->R) { set_error("seam_mg_solve: export / import the peer blocks for this system first"); return B2TEX_ERR_ARG; }
+    for (uint32_t k = 0; k < m->nranks; ++k)
+        if (!m->peer[k]) { set_error("seam_mg_solve: peer %u not imported", k); return B2TEX_ERR_ARG; }
+    cudaStream_t s = c->stream;
+    const uint32_t R = c->R;
+    const uint32_t r0 = (uint32_t)((uint64_t)R * m->rank / m->nranks), r1 = (uint32_t)((uint64_t)R * (m->rank + 1) / m->nranks);
+    int per_sm = 0;
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_mg, MG_THREADS, 0));
+    if (per_sm < 1) { set_error("k_pcg_mg cannot be resident"); return B2TEX_ERR_CUDA; }
+    int grid = c->num_sms * per_sm;
+    const int need = (int)((r1 - r0 + MG_THREADS - 1) / MG_THREADS);
+    if (grid > need) grid = std::max(1, need);
+    B2_TRY(m->blockpart.alloc((size_t)grid * 8));
+    B2_TRY(m->status.alloc(16));
+    B2_TRY(m->status.zero(s));
+    PcgMg q;
+    q.R = R; q.r0 = r0; q.r1 = r1; q.rank = m->rank; q.nranks = m->nranks;
+    q.csr_ptr = c->csr_ptr.p; q.csr_enc = c->csr_enc.p; q.diag_val = c->seam_dval.p; q.inv_diag = c->seam_diag.p; q.rhs = c->seam_rhs.p;
+    q.r = c->seam_r.p; q.t = c->seam_t.p; q.blockpart = m->blockpart.p; q.status = m->status.p;
+    for (int k = 0; k < MG_MAX_RANKS; ++k) q.peer[k] = m->peer[k];
+    q.max_iters = 1000u; q.tol = 0.0001f; q.epoch0 = m->epoch; q.spin_limit = 50ull * 1000 * 1000;
+    void *args[] = {&q};
+    cudaEvent_t e0, e1;
+    B2_CUDA(cudaEventCreate(&e0)); B2_CUDA(cudaEventCreate(&e1));
+    B2_CUDA(cudaEventRecord(e0, s));
+    B2_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg_mg, dim3(grid), dim3(MG_THREADS), args, 0, s));
+    B2_CUDA(cudaEventRecord(e1, s));
+    uint32_t st[16];
+    B2_CUDA(cudaMemcpyAsync(st, m->status.p, sizeof(st), cudaMemcpyDeviceToHost, s));
+    // the complete solution sits in the own peer block: copy it where the single-GPU path leaves it
+    B2_CUDA(cudaMemcpyAsync(c->seam_x.p, mg_carve(m->block, R).x, 3 * (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    m->epoch = st[8];
+    if (st[7]) { set_error("k_pcg_mg: %u cross-GPU barrier timeouts (a peer did not arrive)", st[7]); return B2TEX_ERR_CUDA; }
+    for (int ch = 0; ch < 3; ++ch) { info->iterations[ch] = st[ch]; memcpy(&info->residual[ch], &st[3 + ch], 4); }
+    info->cg_launch_iterations = st[6];
+    info->cg_ms = ms;
+    c->have_seam = true;
+    return B2TEX_OK;
+}
+
+}  // namespace b2

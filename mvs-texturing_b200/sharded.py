@@ -14,6 +14,7 @@ torch.distributed (NCCL) is plumbing only; every kernel is in libb2tex.so.
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -145,11 +146,34 @@ class ShardedPipeline:
         mrf.energy_final = efix[t] / 4294967296.0
         mrf.sweep_bytes = 14 * total_nnz + 20 * F
         t2 = time.perf_counter()
-        seam = c.seam_run()
+        if os.environ.get("B2TEX_SEAM_P2P", "0") == "1" and P <= 8:
+            seam = self._seam_p2p(torch, dist, dev)
+        else:
+            seam = c.seam_run()
         t3 = time.perf_counter()
         info.nnz = total_nnz
         return dict(dc=info, mrf=mrf, seam=seam, trace=np.array(efix) / 4294967296.0,
                     stage_s=dict(data_costs=t1 - t0, view_selection=t2 - t1, seam_leveling=t3 - t2))
+
+    def _seam_p2p(self, torch, dist, dev):
+        """Row-partitioned PCG with the exchange inside the kernel (csrc/seam_mg.cu) instead of the replicated solve:
+        every rank assembles, the cudaIpc handles of the peer blocks go round once (all-gather of 64 bytes), then each
+        GPU runs one fused compute + exchange kernel.  Opt-in (B2TEX_SEAM_P2P=1) until it has run on hardware."""
+        c = self.ctx
+        seam = c.seam_assemble()
+        if getattr(self, "_mg_rows", None) != int(seam.num_rows):   # peer blocks are kept while the system size stays
+            handle = c.seam_mg_export(self.rank, self.world)
+            mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+            allh = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(self.world)]
+            dist.all_gather(allh, mine)
+            for k in range(self.world):
+                if k != self.rank:
+                    c.seam_mg_import(k, bytes(allh[k].cpu().numpy().tobytes()))
+            self._mg_rows = int(seam.num_rows)
+        dist.barrier()           # every peer block is mapped (and the previous solve left) before anybody stores into it
+        c.seam_mg_solve(seam)
+        dist.barrier()           # nobody frees / reuses its block while a peer may still be inside the kernel
+        return seam
 
     def _allreduce_energy(self, e):
         import torch

@@ -31,10 +31,12 @@ struct Warp { Barrier bar; unsigned long long slot[32]; };
 struct Fiber {
     ucontext_t ctx;
     std::vector<char> stack;
-    unsigned tx = 0, bx = 0;
+    unsigned tx = 0, bx = 0, rank = 0;
     bool done = false;
     Warp *warp = nullptr;
     Barrier *block = nullptr;
+    Barrier *grid = nullptr;      // grid.sync() scope: one per emulated device
+    std::vector<char> *shared = nullptr;   // per-block scratch for emul_block_shared()
 };
 
 static ucontext_t g_sched;
@@ -63,7 +65,7 @@ static void entry()
     g_body();
     Fiber *f = g_cur;
     f->done = true;
-    leave(f->warp->bar); leave(*f->block); leave(g_grid);
+    leave(f->warp->bar); leave(*f->block); leave(*f->grid);
     swapcontext(&f->ctx, &g_sched);
 }
 
@@ -82,7 +84,7 @@ static bool launch(unsigned grid, unsigned block, F body, unsigned long long max
         blocks[b].expected = block;
         for (unsigned t = 0; t < block; ++t) {
             Fiber &f = fibers[(size_t)b * block + t];
-            f.tx = t; f.bx = b; f.warp = &warps[(size_t)b * wpb + t / 32]; f.block = &blocks[b];
+            f.tx = t; f.bx = b; f.warp = &warps[(size_t)b * wpb + t / 32]; f.block = &blocks[b]; f.grid = &g_grid;
             f.warp->bar.expected++;
             f.stack.resize(stack_bytes);
             getcontext(&f.ctx);
@@ -104,6 +106,62 @@ static bool launch(unsigned grid, unsigned block, F body, unsigned long long max
     }
     g_cur = nullptr;
     return true;
+}
+
+// Several emulated DEVICES at once (one process per GPU in the real run): `ranks` grids of `grid` x `block` threads, each
+// with its own grid.sync() scope, all scheduled round robin, so that kernels which spin on flags in "peer memory" (plain
+// host pointers here) make progress.  body(rank) runs as the kernel of that rank; blockIdx / gridDim are per rank.
+template <typename F>
+static bool launch_ranks(unsigned ranks, unsigned grid, unsigned block, F body, unsigned long long max_switches = 4000000000ull,
+                         size_t stack_bytes = 128 * 1024)
+{
+    gridDim.x = grid; blockDim.x = block;
+    const unsigned wpb = (block + 31) / 32;
+    std::vector<Fiber> fibers((size_t)ranks * grid * block);
+    std::vector<Warp> warps((size_t)ranks * grid * wpb);
+    std::vector<Barrier> blocks((size_t)ranks * grid), grids(ranks);
+    std::vector<std::vector<char> > shared((size_t)ranks * grid);
+    g_body = [&] { body(g_cur->rank); };
+    for (unsigned r = 0; r < ranks; ++r) {
+        grids[r].expected = grid * block;
+        for (unsigned b = 0; b < grid; ++b) {
+            const size_t gb = (size_t)r * grid + b;
+            blocks[gb].expected = block;
+            for (unsigned t = 0; t < block; ++t) {
+                Fiber &f = fibers[gb * block + t];
+                f.tx = t; f.bx = b; f.rank = r; f.warp = &warps[gb * wpb + t / 32]; f.block = &blocks[gb]; f.grid = &grids[r];
+                f.shared = &shared[gb];
+                f.warp->bar.expected++;
+                f.stack.resize(stack_bytes);
+                getcontext(&f.ctx);
+                f.ctx.uc_stack.ss_sp = f.stack.data(); f.ctx.uc_stack.ss_size = f.stack.size(); f.ctx.uc_link = &g_sched;
+                makecontext(&f.ctx, (void (*)())entry, 0);
+            }
+        }
+    }
+    size_t remaining = fibers.size();
+    g_switches = 0;
+    while (remaining) {
+        for (size_t i = 0; i < fibers.size(); ++i) {
+            Fiber &f = fibers[i];
+            if (f.done) continue;
+            g_cur = &f; threadIdx.x = f.tx; blockIdx.x = f.bx;
+            swapcontext(&g_sched, &f.ctx);
+            if (f.done) --remaining;
+            if (++g_switches > max_switches) { g_cur = nullptr; return false; }
+        }
+    }
+    g_cur = nullptr;
+    return true;
+}
+
+// per-block scratch standing in for a static __shared__ array when several blocks are alive at once (launch_ranks):
+// the harness replaces `__shared__ T name[N];` by `T *name = (T *)emul_block_shared(sizeof(T) * N);` in the kernel text
+static inline void *block_shared(size_t bytes)
+{
+    std::vector<char> &s = *g_cur->shared;
+    if (s.size() < bytes) s.resize(bytes);
+    return s.data();
 }
 
 // kernels WITHOUT any synchronisation: every (block, thread) index runs to completion in order, no fibers (fast).
@@ -178,6 +236,7 @@ template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T __ldcg(const T *p) { return *(const volatile T *)p; }
 template <typename T> static inline void __stcg(T *p, T v) { *(volatile T *)p = v; }
 static inline void __threadfence() {}
+static inline void __threadfence_system() {}
 template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <typename T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 template <typename T> static inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }

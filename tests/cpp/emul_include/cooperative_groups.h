@@ -7,7 +7,7 @@
 namespace cooperative_groups {
 
 struct grid_group {
-    void sync() const { emul::wait(emul::g_grid); }
+    void sync() const { emul::wait(*emul::g_cur->grid); }
     unsigned long long thread_rank() const { return (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; }
     unsigned long long size() const { return (unsigned long long)gridDim.x * blockDim.x; }
 };

@@ -1,0 +1,105 @@
+// tests/cpp/emul_seam_mg.cpp -- multi-rank fiber emulation (cuda_fiber.h, emul::launch_ranks) of csrc/seam_mg.cu: the
+// seam system is assembled once with the emulated kernels of csrc/seam.cu, then `ranks` emulated devices run k_pcg_mg
+// concurrently, exchanging p / partial sums / barrier epochs through each other's blocks exactly as peers do through
+// cudaIpc-mapped memory.  seam_mg_kernels.inc: kernel part of seam_mg.cu, text unchanged except (a) the two PTX
+// ld/st helpers are replaced by the plain C++ below and (b) the static __shared__ reduction scratch becomes per-block
+// scratch of the emulator (several blocks of different ranks are alive at the same time).
+#include "cuda_fiber.h"
+
+#include <algorithm>
+#include <vector>
+
+#include "oracle.h"   // orc_view only
+#include "seam_kernels.inc"
+
+namespace b2 {
+namespace {
+inline void st_release_sys(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
+inline uint32_t ld_acquire_sys(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+}  // namespace
+}  // namespace b2
+#include "seam_mg_kernels.inc"
+
+using namespace b2;
+
+extern "C" {
+
+void emul_seam_mg_free(void *p) { free(p); }
+
+// x_out: [ranks][R][3] -- the complete solution as every rank ends up with it; status_out: [ranks][16]
+int emul_seam_mg(const float *verts, uint32_t Vn, const uint32_t *faces, uint32_t F, const uint32_t *vf_ptr, const uint32_t *vf_idx,
+                 const uint32_t *vv_ptr, const uint32_t *vv_idx, const uint32_t *labels, const orc_view *views, uint32_t K,
+                 uint32_t ranks, uint32_t grid, uint32_t *R_out, float **x_out, uint32_t *status_out)
+{
+    (void)F;
+    if (ranks < 1 || ranks > (uint32_t)MG_MAX_RANKS) return -2;
+    std::vector<ViewDev> vd(K);
+    for (uint32_t v = 0; v < K; ++v) {
+        ViewDev &d = vd[v];
+        for (int i = 0; i < 3; ++i) { d.pos[i] = views[v].pos[i]; d.dir[i] = views[v].viewdir[i]; }
+        for (int i = 0; i < 9; ++i) d.proj[i] = views[v].proj[i];
+        for (int i = 0; i < 12; ++i) d.w2c[i] = views[v].w2c[i];
+        d.w = views[v].width; d.h = views[v].height; d.rgb = views[v].rgb; d.grad = nullptr; d.valid4 = nullptr;
+    }
+    // ---- assembly (seam_run with solve = false), identical on every rank ----
+    const uint32_t vb = (Vn + 127) / 128;
+    std::vector<uint32_t> cnt((size_t)Vn + 1, 0u), row_ptr((size_t)Vn + 1, 0u);
+    emul::launch_serial(vb, 128, [&] { k_vertex_labels<false>(Vn, vf_ptr, vf_idx, labels, cnt.data(), nullptr, nullptr, nullptr); });
+    for (uint32_t i = 0; i < Vn; ++i) row_ptr[i + 1] = row_ptr[i] + cnt[i];
+    const uint32_t R = row_ptr[Vn];
+    std::vector<uint32_t> row_label(R ? R : 1), row_vertex(R ? R : 1);
+    emul::launch_serial(vb, 128, [&] { k_vertex_labels<true>(Vn, vf_ptr, vf_idx, labels, nullptr, row_ptr.data(), row_label.data(), row_vertex.data()); });
+    SeamMesh m{verts, faces, vf_ptr, vf_idx, vv_ptr, vv_idx, labels, row_ptr.data(), row_label.data(), vd.data()};
+    std::fill(cnt.begin(), cnt.end(), 0u);
+    emul::launch_serial(vb, 128, [&] { k_arows<false>(Vn, m, cnt.data(), nullptr, nullptr, nullptr); });
+    std::vector<uint32_t> arow_ptr((size_t)Vn + 1, 0u);
+    for (uint32_t i = 0; i < Vn; ++i) arow_ptr[i + 1] = arow_ptr[i] + cnt[i];
+    const uint32_t A = arow_ptr[Vn];
+    std::vector<uint32_t> arow_rows(2 * (size_t)A + 2);
+    std::vector<float> arow_b(3 * (size_t)A + 3);
+    emul::launch_serial(vb, 128, [&] { k_arows<true>(Vn, m, nullptr, arow_ptr.data(), arow_rows.data(), arow_b.data()); });
+    std::vector<uint32_t> rcnt((size_t)R + 1, 0u), csr_ptr((size_t)R + 1, 0u);
+    const uint32_t rb = (R + 127) / 128;
+    if (R) emul::launch_serial(rb, 128, [&] { k_matrix<false>(R, m, row_vertex.data(), arow_ptr.data(), arow_rows.data(), arow_b.data(), rcnt.data(),
+                                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr); });
+    for (uint32_t r = 0; r < R; ++r) csr_ptr[r + 1] = csr_ptr[r] + rcnt[r];
+    const uint32_t nnzL = csr_ptr[R];
+    std::vector<uint32_t> csr_col(nnzL ? nnzL : 1), csr_enc(nnzL ? nnzL : 1);
+    std::vector<float> csr_val(nnzL ? nnzL : 1), dval(R ? R : 1), inv_diag(R ? R : 1), rhs3(3 * (size_t)(R ? R : 1));
+    if (R) emul::launch_serial(rb, 128, [&] { k_matrix<true>(R, m, row_vertex.data(), arow_ptr.data(), arow_rows.data(), arow_b.data(), nullptr,
+                                                             csr_ptr.data(), csr_col.data(), csr_val.data(), inv_diag.data(), rhs3.data(), csr_enc.data(),
+                                                             dval.data()); });
+    *R_out = R;
+    float *x = (float *)malloc(sizeof(float) * 3 * (size_t)(R ? R : 1) * ranks);
+    *x_out = x;
+    if (!R) return 0;
+
+    // ---- one "device" per rank: own peer block, own scratch; peer tables point at each other's blocks ----
+    std::vector<std::vector<char> > blocks(ranks, std::vector<char>(mg_block_bytes(R), 0));
+    std::vector<std::vector<float> > rr(ranks, std::vector<float>(3 * (size_t)R)), tt(ranks, std::vector<float>(3 * (size_t)R));
+    std::vector<std::vector<double> > bp(ranks, std::vector<double>((size_t)grid * 8, 0.0));
+    std::vector<std::vector<uint32_t> > st(ranks, std::vector<uint32_t>(16, 0u));
+    std::vector<PcgMg> q(ranks);
+    for (uint32_t k = 0; k < ranks; ++k) {
+        PcgMg &p = q[k];
+        p.R = R; p.r0 = (uint32_t)((uint64_t)R * k / ranks); p.r1 = (uint32_t)((uint64_t)R * (k + 1) / ranks);
+        p.rank = k; p.nranks = ranks;
+        p.csr_ptr = csr_ptr.data(); p.csr_enc = csr_enc.data(); p.diag_val = dval.data(); p.inv_diag = inv_diag.data(); p.rhs = rhs3.data();
+        p.r = rr[k].data(); p.t = tt[k].data(); p.blockpart = bp[k].data(); p.status = st[k].data();
+        for (uint32_t j = 0; j < (uint32_t)MG_MAX_RANKS; ++j) p.peer[j] = j < ranks ? (void *)blocks[j].data() : nullptr;
+        p.max_iters = 1000u; p.tol = 0.0001f; p.epoch0 = 0xFFFFFFF0u;   // start close to the wrap-around of the epoch counter
+        p.spin_limit = 1000000000ull;
+    }
+    for (uint32_t k = 0; k < ranks; ++k)      // flags start at epoch0 ("everybody reached the epochs used so far")
+        for (uint32_t j = 0; j < (uint32_t)MG_MAX_RANKS; ++j) mg_carve(blocks[k].data(), R).flag[j] = 0xFFFFFFF0u;
+    if (!emul::launch_ranks(ranks, grid, MG_THREADS, [&](unsigned rank) { k_pcg_mg(q[rank]); })) return -1;
+    for (uint32_t k = 0; k < ranks; ++k) {
+        const float *xs = mg_carve(blocks[k].data(), R).x;
+        for (uint32_t r = 0; r < R; ++r)
+            for (int c = 0; c < 3; ++c) x[((size_t)k * R + r) * 3 + c] = xs[(size_t)c * R + r];
+        for (int i = 0; i < 16; ++i) status_out[16 * k + i] = st[k][i];
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -57,13 +57,18 @@ def emul():
                              "    extern __shared__ uint32_t sm[];  // [rounds+1] level counts\n", close=2))
     with open(os.path.join(OUT, "seam_kernels.inc"), "w") as f:
         f.write(_kernel_part("seam.cu", "int seam_run(b2tex_ctx"))
+    with open(os.path.join(OUT, "seam_mg_kernels.inc"), "w") as f:
+        f.write(_kernel_part("seam_mg.cu", "// ---- host side: peer block management and launch",
+                             ("__device__ __forceinline__ void st_release_sys", "__device__ __forceinline__ void mg_block_reduce6"))
+                .replace("    __shared__ double smem[(MG_THREADS / 32) * 6];\n",
+                         "    double *smem = (double *)emul::block_shared(sizeof(double) * (MG_THREADS / 32) * 6);\n"))
     with open(os.path.join(OUT, "patches_kernels.inc"), "w") as f:
         f.write(_kernel_part("patches.cu", "void patches_free(b2tex_ctx"))
     with open(os.path.join(OUT, "localseam_kernels.inc"), "w") as f:
         f.write(_kernel_part("localseam.cu", "int local_seam_run(b2tex_ctx"))
     libs = {}
     cpp = os.path.join(ROOT, "tests", "cpp")
-    for name in ("emul_bvh", "emul_datacosts", "emul_mrf", "emul_seam", "emul_patches", "emul_localseam"):
+    for name in ("emul_bvh", "emul_datacosts", "emul_mrf", "emul_seam", "emul_seam_mg", "emul_patches", "emul_localseam"):
         so = os.path.join(OUT, name + ".so")
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w",
                                "-I" + os.path.join(cpp, "emul_include"), "-I" + cpp, "-I" + CUDA_INC, "-I" + CSRC,
@@ -506,3 +511,36 @@ def test_device_view_selection_generic_paths(emul, orc, case):
     assert it == o["iterations"] and np.array_equal(labels, o["labels"])
     if extra:
         assert int(np.diff(ap).max()) > 3
+
+
+# ---- multi-GPU seam solve: compute + exchange in one kernel per GPU (csrc/seam_mg.cu) ------------------------------------
+@pytest.mark.parametrize("ranks,grid", [(2, 1), (3, 2)])
+def test_device_multi_gpu_seam_solve(emul, orc, scene_mod, get_scene, ranks, grid):
+    """k_pcg_mg on `ranks` emulated devices at once (emul::launch_ranks: one grid.sync scope per device, peer blocks =
+    each other's host buffers): the rows are split across the ranks, the search direction is all-gathered by peer stores,
+    dot products go through per-rank slots summed in rank order, barriers are epoch flags in peer memory (started 16 below
+    the 32-bit wrap-around).  Every rank must end with the SAME complete solution, with the single-GPU iteration counts,
+    within 1e-4 of the oracle, and no barrier may time out."""
+    s = get_scene("tiny")
+    adj = scene_mod.face_adjacency(s.faces)
+    rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
+    dc = orc.data_costs(s)
+    labels = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1)["labels"]
+    o = orc.global_seam_leveling(s, rings, labels)
+    views, keep = orc.make_views(s)
+    L = emul["emul_seam_mg"]
+    R, xp = C.c_uint32(), C.c_void_p()
+    status = np.zeros(16 * ranks, np.uint32)
+    rc = L.emul_seam_mg(orc._p(s.verts), C.c_uint32(s.verts.shape[0]), orc._p(s.faces), C.c_uint32(s.num_faces), orc._p(rings[0]),
+                        orc._p(rings[1]), orc._p(rings[2]), orc._p(rings[3]), orc._p(np.ascontiguousarray(labels, np.uint32)), views,
+                        C.c_uint32(s.num_views), C.c_uint32(ranks), C.c_uint32(grid), C.byref(R), C.byref(xp), orc._p(status))
+    assert rc == 0, "a rank never left the kernel (barrier protocol hang)" if rc == -1 else rc
+    Rn = R.value
+    x = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_float)), (ranks * Rn * 3,)).copy().reshape(ranks, Rn, 3)
+    L.emul_seam_mg_free(xp)
+    st = status.reshape(ranks, 16)
+    assert Rn == len(o["row_label"]) and not st[:, 7].any()
+    for k in range(ranks):
+        assert np.array_equal(x[k].view(np.uint32), x[0].view(np.uint32))
+        assert st[k, :3].tolist() == list(o["iterations"])
+    assert np.linalg.norm(x[0] - o["x"]) / np.linalg.norm(o["x"]) < 1e-4

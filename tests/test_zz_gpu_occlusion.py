@@ -121,3 +121,30 @@ def test_local_seam_leveling(b2, get_scene, scene_mod, orc):
     for a, b in zip(got, pa):
         assert np.array_equal(a["validity"], b.validity)
         assert np.abs(a["image"] - b.image).max() < 1e-4
+
+
+def test_multi_gpu_seam_kernel_on_one_rank(b2, get_scene, oracle_pipeline):
+    """k_pcg_mg (csrc/seam_mg.cu) with a single rank: the peer table holds only the own block, the cross-GPU barrier
+    degenerates to a self-signal.  Must reproduce the single-GPU k_pcg: same iteration counts, same solution up to the
+    reduction order.  (The real multi-GPU run is tools/check_sharded.py with B2TEX_SEAM_P2P=1 under torchrun.)"""
+    name = "C1d"
+    s = get_scene(name)
+    r = oracle_pipeline(name)
+    c = b2.Context(0)
+    c.set_scene(s)
+    c.set_vertex_rings(*r["rings"])
+    c.set_labels(r["mrf"]["labels"])
+    i1 = c.seam_run()
+    x1 = c.seam_download(i1)["x"]
+    i2 = c.seam_assemble()
+    assert i2.num_rows == i1.num_rows and i2.nnz_full == i1.nnz_full
+    handle = c.seam_mg_export(0, 1)
+    assert len(handle) == 64
+    c.seam_mg_solve(i2)
+    x2 = c.seam_download(i2)["x"]
+    c.seam_mg_solve(i2)                                    # second solve on the same blocks: epochs keep counting
+    x3 = c.seam_download(i2)["x"]
+    c.close()
+    assert list(i2.iterations) == list(i1.iterations)
+    assert np.linalg.norm(x2 - x1) / np.linalg.norm(x1) < 1e-5
+    assert np.array_equal(x2.view(np.uint32), x3.view(np.uint32))
