@@ -167,6 +167,9 @@ def main():
     ap_.add_argument("--cpu-faces", type=int, default=0, help="faces in the CPU baseline sample (0 = auto)")
     ap_.add_argument("--no-cpu-baseline", action="store_true")
     ap_.add_argument("--no-e2e", action="store_true")
+    ap_.add_argument("--with-patches", action="store_true",
+                     help="also time texture patches + adjust_colors + local seam leveling (reported under 'extra_stages'; "
+                          "never part of the headline metric, which is the three north_star stages)")
     args = ap_.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -262,6 +265,23 @@ def main():
         e2e = runner.e2e(torch, steps=max(1, min(args.steps, 3)), warmup=1)
     sync_all()
 
+    extra = None
+    if args.with_patches and rank == 0 and world == 1:
+        # after the timed region, on the labels / offsets the last step left on the device
+        ctx = runner.ctx
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        ev[0].record(ext)
+        pinfo = ctx.texture_patches_run(apply_adjust=True)
+        ev[1].record(ext)
+        linfo = ctx.local_seam_leveling_run()
+        ev[2].record(ext)
+        torch.cuda.synchronize()
+        extra = {"texture_patches_ms": ev[0].elapsed_time(ev[1]), "local_seam_leveling_ms": ev[1].elapsed_time(ev[2]),
+                 "patches": int(pinfo.num_patches), "patch_pixels": int(pinfo.num_pixels), "seam_edges": int(linfo.num_seam_edges),
+                 "poisson_unknowns": int(linfo.num_unknowns), "poisson_iterations": list(linfo.iterations),
+                 "note": "includes the host bookkeeping (component BFS, merge plan, seam edges) inside each call"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -286,7 +306,7 @@ def main():
                           "cg_residual": [float(x) for x in res["seam"].residual],
                           "scene_setup_s": round(gen_s, 1)},
                "stage_ms": stage_ms, "kernels": kernels[:8], "roofline": roofline, "cpu_baseline": cpu,
-               "e2e": e2e, "gpu_launches": launches * args.steps, "clocks": clocks,
+               "e2e": e2e, "extra_stages": extra, "gpu_launches": launches * args.steps, "clocks": clocks,
                "wall_ms_per_step": 1e3 * wall / args.steps}
         print(json.dumps(out), flush=True)
     if world > 1:
