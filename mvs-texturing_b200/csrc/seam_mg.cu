@@ -34,17 +34,19 @@ struct MgBlock {
     double *part;
     uint32_t *flag;
 };
+// every section starts on a 64-byte boundary (R may be odd: 28 R bytes would leave the doubles misaligned)
+__host__ __device__ inline size_t mg_align64(size_t n) { return (n + 63) & ~(size_t)63; }
 __host__ __device__ inline size_t mg_block_bytes(uint32_t R)
 {
-    return (size_t)R * 16 + (size_t)R * 12 + 2 * MG_MAX_RANKS * 8 * sizeof(double) + 64;
+    return mg_align64((size_t)R * 16) + mg_align64((size_t)R * 12) + mg_align64(2 * MG_MAX_RANKS * 8 * sizeof(double)) + 64;
 }
 __host__ __device__ inline MgBlock mg_carve(void *base, uint32_t R)
 {
     MgBlock b;
     char *c = (char *)base;
-    b.p = (float4 *)c; c += (size_t)R * 16;
-    b.x = (float *)c; c += (size_t)R * 12;
-    b.part = (double *)c; c += 2 * MG_MAX_RANKS * 8 * sizeof(double);
+    b.p = (float4 *)c; c += mg_align64((size_t)R * 16);
+    b.x = (float *)c; c += mg_align64((size_t)R * 12);
+    b.part = (double *)c; c += mg_align64(2 * MG_MAX_RANKS * 8 * sizeof(double));
     b.flag = (uint32_t *)c;
     return b;
 }

@@ -68,12 +68,19 @@ def emul():
         f.write(_kernel_part("localseam.cu", "int local_seam_run(b2tex_ctx"))
     libs = {}
     cpp = os.path.join(ROOT, "tests", "cpp")
-    for name in ("emul_bvh", "emul_datacosts", "emul_mrf", "emul_seam", "emul_seam_mg", "emul_patches", "emul_localseam"):
+    names = ("emul_bvh", "emul_datacosts", "emul_mrf", "emul_seam", "emul_seam_mg", "emul_patches", "emul_localseam")
+
+    def compile_one(name):
         so = os.path.join(OUT, name + ".so")
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w",
                                "-I" + os.path.join(cpp, "emul_include"), "-I" + cpp, "-I" + CUDA_INC, "-I" + CSRC,
                                "-I" + os.path.join(ROOT, "oracle"), "-I" + OUT, os.path.join(cpp, name + ".cpp"), "-o", so])
-        libs[name] = C.CDLL(so)
+        return so
+
+    import concurrent.futures as cf
+    with cf.ThreadPoolExecutor(max_workers=len(names)) as ex:
+        for name, so in zip(names, ex.map(compile_one, names)):
+            libs[name] = C.CDLL(so)
     return libs
 
 
