@@ -18,7 +18,7 @@ import oracle as O  # noqa: E402
 
 scene = importlib.import_module("mvs-texturing_b200.scene")
 out = {}
-for name in ["tiny", "small", "C1", "C1d", "C2s", "C3s"]:
+for name in ["tiny", "small", "C1", "C1d", "C2s", "C3s", "occ", "occ2"]:   # occ*: real occlusion, unseen faces, several components
     s = scene.config(name)
     dc = O.data_costs(s)
     ap, ai = scene.face_adjacency(s.faces)
@@ -32,5 +32,18 @@ for name in ["tiny", "small", "C1", "C1d", "C2s", "C3s"]:
                      mrf_energy=m["energy"], mrf_energy_fixed=O.mrf_energy_fixed(ap, ai, dc["face_ptr"], dc["view"], dc["cost"], m["labels"]),
                      seam_rows=len(sm["row_label"]), seam_a_rows=sm["num_a_rows"],
                      cg_iterations=list(sm["iterations"]))
+    if name in ("tiny", "occ"):   # texture patches + adjust_colors with zero offsets (oracle/patches.py, pinned to the reference TUs)
+        import numpy as np
+        import patches as P
+        pp, _ = P.generate_texture_patches(O, s, (ap, ai), m["labels"])
+        crc = dict(tex=0, img=0, val=0, bl=0)
+        for q in pp:
+            img, val, bl = P.adjust_colors(q, np.zeros((3 * len(q.faces), 3), np.float32))
+            crc["tex"] = zlib.crc32(np.ascontiguousarray(q.texcoords, np.float32).tobytes(), crc["tex"])
+            crc["img"] = zlib.crc32(np.ascontiguousarray(img).tobytes(), crc["img"])
+            crc["val"] = zlib.crc32(np.ascontiguousarray(val).tobytes(), crc["val"])
+            crc["bl"] = zlib.crc32(np.ascontiguousarray(bl).tobytes(), crc["bl"])
+        out[name].update(patches=len(pp), patch_faces=sum(len(q.faces) for q in pp), crc_patch_texcoords=crc["tex"],
+                         crc_patch_images=crc["img"], crc_patch_validity=crc["val"], crc_patch_blending=crc["bl"])
     print(name, out[name])
 json.dump(out, open(os.path.join(ROOT, "tests", "golden", "oracle_snapshots.json"), "w"), indent=1)

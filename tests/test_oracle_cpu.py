@@ -412,6 +412,20 @@ def test_oracle_matches_golden_snapshots(orc, scene_mod, oracle_pipeline):
         assert m["energy"] == pytest.approx(g["mrf_energy"], rel=1e-12)
         assert len(sm["row_label"]) == g["seam_rows"]
         assert list(sm["iterations"]) == g["cg_iterations"]
+        if "patches" in g:                                  # texture patches + zero adjust_colors (oracle/patches.py)
+            import patches as P
+            s = scene_mod.config(name)
+            pp, _ = P.generate_texture_patches(orc, s, r["adj"], m["labels"])
+            crc = dict(tex=0, img=0, val=0, bl=0)
+            for q in pp:
+                img, val, bl = P.adjust_colors(q, np.zeros((3 * len(q.faces), 3), np.float32))
+                crc["tex"] = zlib.crc32(np.ascontiguousarray(q.texcoords, np.float32).tobytes(), crc["tex"])
+                crc["img"] = zlib.crc32(np.ascontiguousarray(img).tobytes(), crc["img"])
+                crc["val"] = zlib.crc32(np.ascontiguousarray(val).tobytes(), crc["val"])
+                crc["bl"] = zlib.crc32(np.ascontiguousarray(bl).tobytes(), crc["bl"])
+            assert (len(pp), sum(len(q.faces) for q in pp)) == (g["patches"], g["patch_faces"])
+            assert (crc["tex"], crc["img"], crc["val"], crc["bl"]) == (g["crc_patch_texcoords"], g["crc_patch_images"],
+                                                                       g["crc_patch_validity"], g["crc_patch_blending"])
 
 
 # ---- texture patches: the reference's patch-relative colour sampling vs the stage-isolated shortcut ----
