@@ -237,6 +237,17 @@ int b2tex_texture_hot_path(const float *verts, uint32_t num_verts, const uint32_
                            uint32_t *row_ptr_out, uint32_t **row_label_out, float **x_out,
                            b2tex_dc_info *dc_info, b2tex_mrf_info *mrf_info, b2tex_seam_info *seam_info);
 
+/* Everything texrecon does between texrecon.cpp:160 and :189 on one upload: texture patches for the seen faces,
+ * global seam leveling (do_global; else the zero-offset validity pass of :174-183), local seam leveling (do_local).
+ * Outputs are malloc'ed (b2tex_free) and laid out as b2tex_texture_patches_download describes; info structs may be NULL. */
+int b2tex_seam_leveling_patches(const float *verts, uint32_t num_verts, const uint32_t *faces, uint32_t num_faces,
+                                const uint32_t *adj_ptr, const uint32_t *adj_idx, const uint32_t *vf_ptr,
+                                const uint32_t *vf_idx, const uint32_t *vv_ptr, const uint32_t *vv_idx,
+                                const uint32_t *labels, const b2tex_view *views, uint32_t num_views, int do_global,
+                                int do_local, int32_t **desc_out, uint32_t **faces_out, float **texcoords_out,
+                                float **images_out, uint8_t **validity_out, b2tex_patch_info *patch_info,
+                                b2tex_seam_info *seam_info, b2tex_local_seam_info *local_info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -511,6 +511,42 @@ int b2tex_global_seam_leveling(const float *verts, uint32_t nv, const uint32_t *
     return rc;
 }
 
+int b2tex_seam_leveling_patches(const float *verts, uint32_t nv, const uint32_t *faces, uint32_t nf, const uint32_t *adj_ptr,
+                                const uint32_t *adj_idx, const uint32_t *vf_ptr, const uint32_t *vf_idx, const uint32_t *vv_ptr,
+                                const uint32_t *vv_idx, const uint32_t *labels, const b2tex_view *views, uint32_t K, int do_global,
+                                int do_local, int32_t **desc_out, uint32_t **faces_out, float **texcoords_out, float **images_out,
+                                uint8_t **validity_out, b2tex_patch_info *pi, b2tex_seam_info *si, b2tex_local_seam_info *li)
+{
+    if (K > 65535u) { set_error("Exeeded maximal number of views"); return B2TEX_ERR_LIMITS; }
+    b2tex_ctx *c = nullptr;
+    B2_TRY(b2tex_create(0, &c));
+    b2tex_patch_info pl; b2tex_seam_info sl; b2tex_local_seam_info ll;
+    if (!pi) pi = &pl;
+    if (!si) si = &sl;
+    if (!li) li = &ll;
+    memset(si, 0, sizeof(*si)); memset(li, 0, sizeof(*li));
+    std::vector<float> dummy_normals(3 * (size_t)nf, 0.0f);
+    int rc = b2tex_set_mesh(c, verts, nv, faces, dummy_normals.data(), nf);
+    if (rc == B2TEX_OK) rc = b2tex_set_views(c, views, K);
+    if (rc == B2TEX_OK) rc = b2tex_set_adjacency(c, adj_ptr, adj_idx);
+    if (rc == B2TEX_OK) rc = b2tex_set_vertex_rings(c, vf_ptr, vf_idx, vv_ptr, vv_idx);
+    if (rc == B2TEX_OK) rc = b2tex_set_labels(c, labels);
+    if (rc == B2TEX_OK && do_global) rc = b2tex_seam_run(c, si);
+    if (rc == B2TEX_OK) rc = b2tex_texture_patches_run(c, do_global ? 1 : 0, pi);
+    if (rc == B2TEX_OK && do_local) rc = b2tex_local_seam_leveling_run(c, li);
+    if (rc == B2TEX_OK) {
+        const size_t n = pi->num_patches, T = pi->num_faces, P = pi->num_pixels;
+        *desc_out = (int32_t *)malloc(sizeof(int32_t) * 8 * (n ? n : 1));
+        *faces_out = (uint32_t *)malloc(sizeof(uint32_t) * (T ? T : 1));
+        *texcoords_out = (float *)malloc(sizeof(float) * 6 * (T ? T : 1));
+        *images_out = (float *)malloc(sizeof(float) * 3 * (P ? P : 1));
+        *validity_out = (uint8_t *)malloc(P ? P : 1);
+        rc = b2tex_texture_patches_download(c, *desc_out, *faces_out, *texcoords_out, *images_out, *validity_out, nullptr);
+    }
+    b2tex_destroy(c);
+    return rc;
+}
+
 int b2tex_texture_hot_path(const float *verts, uint32_t nv, const uint32_t *faces, const float *normals, uint32_t nf,
                            const b2tex_view *views, uint32_t K, const uint32_t *adj_ptr, const uint32_t *adj_idx,
                            const uint32_t *vf_ptr, const uint32_t *vf_idx, const uint32_t *vv_ptr,

@@ -152,6 +152,23 @@ struct TextureView {
 };
 typedef std::vector<TextureView> TextureViews;
 
+/* libs/tex/texture_patch.h:23-69 reduced to what texture atlas packing reads: label, faces, texcoords, the float image and
+ * the validity mask.  min_x / min_y = view pixel of patch pixel (0, 0). */
+struct TexturePatch {
+    int label = 0;
+    int min_x = 0, min_y = 0, width = 0, height = 0;
+    std::vector<std::size_t> faces;
+    std::vector<math::Vec2f> texcoords;       // 3 per face
+    std::vector<float> image;                 // height x width x 3
+    std::vector<std::uint8_t> validity_mask;  // height x width, 255 = valid
+    int get_label() const { return label; }
+    int get_width() const { return width; }
+    int get_height() const { return height; }
+    std::vector<std::size_t> const &get_faces() const { return faces; }
+    std::vector<math::Vec2f> const &get_texcoords() const { return texcoords; }
+};
+typedef std::vector<TexturePatch> TexturePatches;
+
 /* per-(vertex,label) colour adjustment, the product of global_seam_leveling.cpp:251,283-289 */
 typedef std::vector<std::map<std::size_t, math::Vec3f> > AdjustValues;
 

@@ -171,4 +171,46 @@ void global_seam_leveling(UniGraph const &graph, mve::TriangleMesh::ConstPtr mes
     b2tex_free(row_label); b2tex_free(x);
 }
 
+void seam_leveling(UniGraph const &graph, mve::TriangleMesh::ConstPtr mesh, mve::MeshInfo const &mesh_info,
+                   TextureViews const &texture_views, Settings const &settings, TexturePatches *texture_patches)
+{
+    std::uint32_t const Vn = (std::uint32_t)mesh->get_vertices().size();
+    std::uint32_t const F = (std::uint32_t)(mesh->get_faces().size() / 3);
+    std::vector<std::uint32_t> vf_ptr(Vn + 1, 0), vv_ptr(Vn + 1, 0), vf_idx, vv_idx, labels(F), ap, ai;
+    for (std::uint32_t v = 0; v < Vn; ++v) {
+        vf_ptr[v + 1] = vf_ptr[v] + (std::uint32_t)mesh_info[v].faces.size();
+        vv_ptr[v + 1] = vv_ptr[v] + (std::uint32_t)mesh_info[v].verts.size();
+        for (std::size_t f : mesh_info[v].faces) vf_idx.push_back((std::uint32_t)f);
+        for (std::size_t w : mesh_info[v].verts) vv_idx.push_back((std::uint32_t)w);
+    }
+    for (std::uint32_t f = 0; f < F; ++f) labels[f] = (std::uint32_t)graph.get_label(f);
+    flatten_graph(graph, &ap, &ai);
+    std::vector<b2tex_view> views = flatten_views(texture_views);
+    std::int32_t *desc = nullptr;
+    std::uint32_t *faces = nullptr;
+    float *tex = nullptr, *img = nullptr;
+    std::uint8_t *val = nullptr;
+    b2tex_patch_info pinfo;
+    check(b2tex_seam_leveling_patches(*mesh->get_vertices()[0], Vn, mesh->get_faces().data(), F, ap.data(), ai.data(), vf_ptr.data(),
+                                      vf_idx.data(), vv_ptr.data(), vv_idx.data(), labels.data(), views.data(),
+                                      (std::uint32_t)views.size(), settings.global_seam_leveling ? 1 : 0,
+                                      settings.local_seam_leveling ? 1 : 0, &desc, &faces, &tex, &img, &val, &pinfo, nullptr, nullptr));
+    texture_patches->clear();
+    texture_patches->resize(pinfo.num_patches);
+    std::size_t off = 0;
+    for (std::uint32_t q = 0; q < pinfo.num_patches; ++q) {
+        std::int32_t const *d = desc + 8 * (std::size_t)q;
+        TexturePatch &p = (*texture_patches)[q];
+        p.label = d[0]; p.min_x = d[1]; p.min_y = d[2]; p.width = d[3]; p.height = d[4];
+        std::size_t const first = (std::size_t)d[5], n = (std::size_t)d[6], px = (std::size_t)d[3] * (std::size_t)d[4];
+        p.faces.assign(faces + first, faces + first + n);
+        p.texcoords.resize(3 * n);
+        for (std::size_t i = 0; i < 3 * n; ++i) { p.texcoords[i][0] = tex[2 * (3 * first + i)]; p.texcoords[i][1] = tex[2 * (3 * first + i) + 1]; }
+        p.image.assign(img + 3 * off, img + 3 * (off + px));
+        p.validity_mask.assign(val + off, val + off + px);
+        off += px;
+    }
+    b2tex_free(desc); b2tex_free(faces); b2tex_free(tex); b2tex_free(img); b2tex_free(val);
+}
+
 }  // namespace tex

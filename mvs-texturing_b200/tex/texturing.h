@@ -25,4 +25,12 @@ void global_seam_leveling(UniGraph const &graph, mve::TriangleMesh::ConstPtr mes
                           mve::MeshInfo const &mesh_info, TextureViews const &texture_views,
                           AdjustValues *adjust_values);
 
+/* texrecon.cpp:160-189 in one call: tex::generate_texture_patches (seen faces; hole filling is not built),
+ * tex::global_seam_leveling (settings.global_seam_leveling, else the zero-offset validity pass) and
+ * tex::local_seam_leveling (settings.local_seam_leveling) -> b2tex_seam_leveling_patches.  The reference threads
+ * TexturePatches through three calls; on the device the patches stay resident between them, so the veneer offers the
+ * sequence as one function and returns the finished patches. */
+void seam_leveling(UniGraph const &graph, mve::TriangleMesh::ConstPtr mesh, mve::MeshInfo const &mesh_info,
+                   TextureViews const &texture_views, Settings const &settings, TexturePatches *texture_patches);
+
 }  // namespace tex

@@ -4,6 +4,7 @@
 // library's error (no CPU fallback) and exits 0 when invoked with --link-only.
 #include <cmath>
 #include <cstdio>
+#include <string>
 #include <cstring>
 #include <vector>
 
@@ -59,6 +60,16 @@ int main(int argc, char **argv)
         tex::global_seam_leveling(graph, mesh, mesh_info, views, &adjust);
         std::printf("nnz=%zu labels=%zu %zu %zu %zu\n", data_costs.get_nnz(), graph.get_label(0), graph.get_label(1),
                     graph.get_label(2), graph.get_label(3));
+        if (argc > 1 && std::string(argv[1]) == "--patches") {          // texrecon.cpp:160-189
+            tex::TexturePatches patches;
+            tex::seam_leveling(graph, mesh, mesh_info, views, settings, &patches);
+            std::size_t faces = 0, valid = 0;
+            for (tex::TexturePatch const &p : patches) {
+                faces += p.get_faces().size();
+                for (std::uint8_t v : p.validity_mask) valid += v == 255;
+            }
+            std::printf("patches=%zu faces=%zu valid_pixels=%zu\n", patches.size(), faces, valid);
+        }
     } catch (std::exception const &e) {
         std::printf("tex:: call failed: %s\n", e.what());
         return 2;

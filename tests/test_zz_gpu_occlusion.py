@@ -187,3 +187,16 @@ def test_cuda_path_matches_committed_golden_snapshots_late(b2, scene_mod, get_sc
         assert (crc["tex"], crc["img"], crc["val"], crc["bl"]) == (gold["crc_patch_texcoords"], gold["crc_patch_images"],
                                                                    gold["crc_patch_validity"], gold["crc_patch_blending"])
     c.close()
+
+
+def test_veneer_seam_leveling_patches(b2):
+    """tex::seam_leveling of the C++ veneer (texrecon.cpp:160-189 in one call -> b2tex_seam_leveling_patches): the
+    tetrahedron of tests/cpp/texrecon_hotpath.cpp comes back as patches that cover all four faces."""
+    import os, subprocess
+    import test_veneer as tv
+    tv._build(b2)
+    r = subprocess.run([tv.EXE, "--patches"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [l for l in r.stdout.splitlines() if l.startswith("patches=")][0]
+    vals = dict(kv.split("=") for kv in line.split())
+    assert 1 <= int(vals["patches"]) <= 4 and int(vals["faces"]) == 4 and int(vals["valid_pixels"]) > 10
