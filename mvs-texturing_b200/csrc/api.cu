@@ -542,6 +542,10 @@ int b2tex_seam_leveling_patches(const float *verts, uint32_t nv, const uint32_t 
         *images_out = (float *)malloc(sizeof(float) * 3 * (P ? P : 1));
         *validity_out = (uint8_t *)malloc(P ? P : 1);
         rc = b2tex_texture_patches_download(c, *desc_out, *faces_out, *texcoords_out, *images_out, *validity_out, nullptr);
+        if (rc != B2TEX_OK) {   // nothing half-filled leaves the library
+            free(*desc_out); free(*faces_out); free(*texcoords_out); free(*images_out); free(*validity_out);
+            *desc_out = nullptr; *faces_out = nullptr; *texcoords_out = nullptr; *images_out = nullptr; *validity_out = nullptr;
+        }
     }
     b2tex_destroy(c);
     return rc;
