@@ -390,10 +390,13 @@ def _emul_pipeline(emul, orc, s, adj, labels, seam, stage):
     ptrs = [C.c_void_p() for _ in range(6)]
     sizes = np.zeros(8, np.uint64)
     labels = np.ascontiguousarray(labels, np.uint32)
-    x = np.ascontiguousarray(seam["x"], np.float32)
+    if seam is not None:
+        x = np.ascontiguousarray(seam["x"], np.float32)
+        sargs = (orc._p(seam["row_ptr"]), orc._p(seam["row_label"]), orc._p(x), C.c_uint32(len(seam["row_label"])))
+    else:                                                      # no global leveling: zero offsets (texrecon.cpp:174-183)
+        sargs = (None, None, None, C.c_uint32(0))
     rc = L.emul_texture_pipeline(orc._p(s.verts), C.c_uint32(s.verts.shape[0]), orc._p(s.faces), C.c_uint32(s.num_faces), orc._p(adj[0]),
-                                 orc._p(adj[1]), orc._p(labels), views, C.c_uint32(s.num_views), orc._p(seam["row_ptr"]),
-                                 orc._p(seam["row_label"]), orc._p(x), C.c_uint32(len(seam["row_label"])), stage,
+                                 orc._p(adj[1]), orc._p(labels), views, C.c_uint32(s.num_views), *sargs, stage,
                                  *[C.byref(p) for p in ptrs], orc._p(sizes))
     assert rc == 0, "the Poisson CG launch did not terminate" if rc == -1 else rc
     n, T, Pn = (int(v) for v in sizes[:3])
@@ -551,3 +554,32 @@ def test_device_multi_gpu_seam_solve(emul, orc, scene_mod, get_scene, ranks, gri
         assert np.array_equal(x[k].view(np.uint32), x[0].view(np.uint32))
         assert st[k, :3].tolist() == list(o["iterations"])
     assert np.linalg.norm(x[0] - o["x"]) / np.linalg.norm(o["x"]) < 1e-4
+
+
+def test_device_local_seam_leveling_without_global_leveling(emul, orc, local_inputs):
+    """texrecon --skip_global_seam_leveling: zero-offset adjust_colors pass (texrecon.cpp:174-183), then local seam leveling on
+    the raw patch colours (larger seam differences to blend away).  Against the reference TUs when available, else the oracle."""
+    import patches as P
+    s, adj, rings, labels, seam, pp, pvpi = local_inputs("tiny")
+    ep, sizes = _emul_pipeline(emul, orc, s, adj, labels, None, 2)
+    try:
+        import refpin
+        have_ref = refpin.available()
+    except Exception:
+        have_ref = False
+    if have_ref:
+        rp, _ = refpin.seam_leveling(s, rings, adj, labels, do_global=False, do_local=True)
+        exp = [(q.image, q.validity) for q in rp if q.label != 0]
+    else:
+        pa = []
+        for q in pp:
+            img, val, bl = P.adjust_colors(q, np.zeros((3 * len(q.faces), 3), np.float32))
+            z = P.Patch(q.label, q.faces, q.texcoords, img, q.bbox)
+            z.validity, z.blending = val, bl
+            pa.append(z)
+        P.local_seam_leveling(s, adj, labels, pa, pvpi)
+        exp = [(q.image, q.validity) for q in pa]
+    assert len(ep) == len(exp)
+    for a, (img, val) in zip(ep, exp):
+        assert np.array_equal(a["validity"], val)
+        assert np.abs(a["image"] - img).max() < 1e-4           # raw gain/bias differences are ~10x larger than after global leveling
