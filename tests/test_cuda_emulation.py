@@ -524,7 +524,7 @@ def test_device_view_selection_generic_paths(emul, orc, case):
 
 
 # ---- multi-GPU seam solve: compute + exchange in one kernel per GPU (csrc/seam_mg.cu) ------------------------------------
-@pytest.mark.parametrize("ranks,grid", [(2, 1), (3, 2)])
+@pytest.mark.parametrize("ranks,grid", [(2, 2), (3, 1)])
 def test_device_multi_gpu_seam_solve(emul, orc, scene_mod, get_scene, ranks, grid):
     """k_pcg_mg on `ranks` emulated devices at once (emul::launch_ranks: one grid.sync scope per device, peer blocks =
     each other's host buffers): the rows are split across the ranks, the search direction is all-gathered by peer stores,
