@@ -288,6 +288,38 @@ def occluder_scene(nu, k, width, height, plates=5, displace=0.05, dist=3.0, name
     return _assemble(name, V, F, cams, width, height, with_images)
 
 
+def messy_scene(nu, k, width, height, name="messy", with_images=True):
+    """Input hygiene cases real scans have and the clean generators lack: non-manifold edges (fins glued onto existing
+    edges: three faces per edge, face-graph degree 4), zero-area faces (coincident vertices: zero normal, dropped because their
+    quality is 0), an unreferenced vertex, a sliver, and a small detached component."""
+    V, F = icosphere(nu, 0.04)
+    V = V.astype(np.float64)
+    F = F.astype(np.int64)
+    extra_v, extra_f = [], []
+    nv = len(V)
+    for f in (7, 101, 350):                                   # fins
+        a, b, c = F[f]
+        tip = V[[a, b, c]].mean(0) * 1.25
+        extra_v.append(tip); extra_f += [[a, b, nv], [b, c, nv]]; nv += 1
+    a, b, c = F[33]                                           # zero-area faces: coincident POSITIONS, distinct indices
+    extra_v += [V[a].copy(), V[c].copy(), V[c].copy()]
+    extra_f += [[a, nv, b], [c, nv + 1, nv + 2]]; nv += 3
+    extra_v.append(np.array([0.0, 0.0, 2.0])); nv += 1        # unreferenced vertex
+    a, b, c = F[60]
+    extra_v.append(V[a] * 0.999 + V[b] * 0.001 + 1e-5); extra_f.append([a, nv, b]); nv += 1   # sliver on an edge
+    base = nv
+    d = np.array([0.3, -0.8, 0.52]); d /= np.linalg.norm(d)
+    e1 = np.cross(d, [0, 0, 1.0]); e1 /= np.linalg.norm(e1); e2 = np.cross(d, e1)
+    extra_v += [d * 1.5 - 0.1 * e1 - 0.1 * e2, d * 1.5 + 0.1 * e1 - 0.1 * e2, d * 1.5 + 0.1 * e2]
+    extra_f.append([base, base + 1, base + 2])                # detached triangle facing outwards
+    V = np.concatenate([V, np.array(extra_v)], 0).astype(np.float32)
+    F = np.concatenate([F, np.array(extra_f, np.int64)], 0).astype(np.uint32)
+    half = 0.8 * min(width, height) / 2.0
+    flen = half / np.tan(np.arcsin(min(0.99, 1.7 / 3.0)))
+    cams = [look_at_camera(dd * 3.0, (0, 0, 0), flen, width, height) for dd in fibonacci_dirs(k)]
+    return _assemble(name, V, F, cams, width, height, with_images)
+
+
 def terrain_scene(n, k, width, height, dist=3.2, name="terrain", with_images=True):
     V, F = terrain(n)
     dirs = fibonacci_dirs(k, hemisphere=True)
@@ -304,6 +336,8 @@ def config(name: str, with_images=True) -> Scene:
         return sphere_scene(10, 12, 320, 240, displace=0.05, name=name, with_images=with_images)
     if name == "occ":       # 2 010 faces, 12 views, floating plates: real occlusion
         return occluder_scene(10, 12, 320, 240, plates=9, name=name, with_images=with_images)
+    if name == "messy":     # 1 290 faces / 653 vertices: non-manifold fins, zero-area faces, sliver, detached triangle, unreferenced vertex
+        return messy_scene(8, 10, 320, 240, name=name, with_images=with_images)
     if name == "occ2":      # 32 030 faces, 24 views
         return occluder_scene(40, 24, 640, 480, plates=15, name=name, with_images=with_images)
     if name == "C1":

@@ -307,6 +307,9 @@ int ref_seam_leveling(const float* verts, uint32_t num_verts, const uint32_t* fa
         tex::TextureViews tvs;
         make_views(views, num_views, &tvs);
         tex::Settings settings;
+        /* fill_hole (:140-451) walks MeshInfo's RING-ORDERED adjacency; the shim hands over ascending ids, and hole
+         * filling is not restated by the oracle anyway: switched off, as texrecon --skip_hole_filling does */
+        settings.hole_filling = false;
         g_patches.patches.clear(); g_patches.vpi.clear();
         tex::generate_texture_patches(graph, mesh, mi, &tvs, settings, &g_patches.vpi, &g_patches.patches);
         if (do_global) {

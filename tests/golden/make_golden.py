@@ -18,7 +18,8 @@ import oracle as O  # noqa: E402
 
 scene = importlib.import_module("mvs-texturing_b200.scene")
 out = {}
-for name in ["tiny", "small", "C1", "C1d", "C2s", "C3s", "occ", "occ2"]:   # occ*: real occlusion, unseen faces, several components
+for name in ["tiny", "small", "C1", "C1d", "C2s", "C3s", "occ", "occ2", "messy"]:   # occ*: real occlusion, unseen faces, several
+    # components; messy: non-manifold fins, zero-area faces, a sliver, a detached triangle
     s = scene.config(name)
     dc = O.data_costs(s)
     ap, ai = scene.face_adjacency(s.faces)
@@ -32,7 +33,7 @@ for name in ["tiny", "small", "C1", "C1d", "C2s", "C3s", "occ", "occ2"]:   # occ
                      mrf_energy=m["energy"], mrf_energy_fixed=O.mrf_energy_fixed(ap, ai, dc["face_ptr"], dc["view"], dc["cost"], m["labels"]),
                      seam_rows=len(sm["row_label"]), seam_a_rows=sm["num_a_rows"],
                      cg_iterations=list(sm["iterations"]))
-    if name in ("tiny", "occ"):   # texture patches + adjust_colors with zero offsets (oracle/patches.py, pinned to the reference TUs)
+    if name in ("tiny", "occ", "messy"):   # texture patches + adjust_colors with zero offsets (oracle/patches.py, pinned to the reference TUs)
         import numpy as np
         import patches as P
         pp, _ = P.generate_texture_patches(O, s, (ap, ai), m["labels"])

@@ -111,7 +111,7 @@ def test_device_bvh_build_and_traversal(emul, orc, scene_mod, name):
 
 
 @pytest.mark.parametrize("name,data_term,vis", [("tiny", 1, True), ("occ", 1, True), ("occ", 0, True), ("occ", 1, False),
-                                                ("occ2", 1, True), ("C2s", 1, True)])
+                                                ("occ2", 1, True), ("C2s", 1, True), ("messy", 1, True)])
 def test_device_data_cost_kernels(emul, orc, get_scene, name, data_term, vis):
     """cull -> ray bitmaps -> rays -> quality -> compaction (csrc/datacosts.cu) vs orc_data_costs: identical
     (face, view) set and bit-identical qualities, with real occlusion in the `occ` scenes."""
@@ -143,7 +143,7 @@ def test_device_data_cost_kernels(emul, orc, get_scene, name, data_term, vis):
 
 
 @pytest.mark.parametrize("name,kw", [("tiny", {}), ("occ", {}), ("occ", dict(root_div=0, rounds=200)), ("occ", dict(num_parts=2)),
-                                     ("occ", dict(group=32))])
+                                     ("occ", dict(group=32)), ("messy", {})])
 def test_device_view_selection_kernels(emul, orc, scene_mod, get_scene, name, kw):
     """csrc/mrf.cu on fibers vs orc_view_selection: identical forest levels in iteration 1, identical iteration count,
     identical labels (=> identical energy).  `occ`: unseen faces (label 0, excluded from the graph), ten components,
@@ -173,7 +173,7 @@ def test_device_view_selection_kernels(emul, orc, scene_mod, get_scene, name, kw
         assert (o["labels"] == 0).sum() > 10
 
 
-@pytest.mark.parametrize("name", ["tiny", "occ"])
+@pytest.mark.parametrize("name", ["tiny", "occ", "messy"])
 def test_device_seam_leveling_kernels(emul, orc, scene_mod, get_scene, name):
     """csrc/seam.cu on fibers vs orc_global_seam_leveling: identical unknown numbering, identical Laplacian, bit-identical
     right-hand side, same CG iteration counts, solution within 1e-4 relative (the reductions are ordered differently)."""
@@ -253,7 +253,7 @@ def _same_patch(a, label, faces, texcoords, image, validity, blending):
             and np.array_equal(a["validity"], validity) and np.array_equal(a["blending"], blending))
 
 
-@pytest.mark.parametrize("name,adjust", [("tiny", False), ("tiny", True), ("occ", True)])
+@pytest.mark.parametrize("name,adjust", [("tiny", False), ("tiny", True), ("occ", True), ("messy", True)])
 def test_device_texture_patch_kernels(emul, orc, scene_mod, get_scene, name, adjust):
     """csrc/patches.cu vs oracle/patches.py (itself pinned to the reference TUs): same patches, face order, bit-identical
     texcoords, images after adjust_colors (zero and solved offsets), validity and blending masks."""
@@ -434,7 +434,7 @@ def local_inputs(orc, scene_mod, get_scene):
     return _get
 
 
-@pytest.mark.parametrize("name", ["tiny", "occ"])
+@pytest.mark.parametrize("name", ["tiny", "occ", "messy"])
 def test_device_seam_colours_stamping_and_blending_mask(emul, orc, local_inputs, name, monkeypatch):
     """csrc/localseam.cu up to the Poisson solve vs oracle/patches.local_seam_leveling with the solve switched off: the
     images with the mean seam / vertex colours stamped in ("last writer wins" by atomicMax on the write order) and the
@@ -449,7 +449,7 @@ def test_device_seam_colours_stamping_and_blending_mask(emul, orc, local_inputs,
     for a, b in zip(ep, pa):
         assert np.array_equal(a["blending"], b.blending)
         assert np.array_equal(a["image"].view(np.uint32), b.image.view(np.uint32))
-        assert (a["blending"] == 128).any() and (a["blending"] == 255).any()
+    assert sum(int((a["blending"] == 128).sum()) for a in ep) > 100 and sum(int((a["blending"] == 255).sum()) for a in ep) > 100
 
 
 def test_device_local_seam_leveling(emul, orc, local_inputs):

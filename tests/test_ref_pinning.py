@@ -19,7 +19,7 @@ def ref():
     return refpin
 
 
-@pytest.mark.parametrize("name", ["tiny", "small", "occ"])
+@pytest.mark.parametrize("name", ["tiny", "small", "occ", "messy"])
 @pytest.mark.parametrize("data_term", [1, 0])
 def test_data_costs_match_reference_tu(ref, orc, get_scene, name, data_term):
     """tex::calculate_data_costs (calculate_data_costs.cpp:131-323) vs orc_data_costs: same (face, view) set,
@@ -144,7 +144,7 @@ def test_pixel_coords_match_reference_tu(ref, orc, get_scene):
 
 
 # ---- adjacency graph and MRF model (build_adjacency_graph.cpp, view_selection.cpp) ------------------------------
-@pytest.mark.parametrize("name", ["tiny", "small", "occ", "C2s"])
+@pytest.mark.parametrize("name", ["tiny", "small", "occ", "C2s", "messy"])
 def test_adjacency_matches_reference_tu(ref, scene_mod, get_scene, name):
     """tex::build_adjacency_graph (:16-53) on the reference's UniGraph vs scene.face_adjacency (what the oracle and the
     C ABI are fed): same neighbours in the same adjacency-list order, borders (C2s) and separate components (occ) included."""
@@ -232,7 +232,7 @@ def seam_inputs(orc, scene_mod, get_scene):
     return _get
 
 
-@pytest.mark.parametrize("name", ["tiny", "occ"])
+@pytest.mark.parametrize("name", ["tiny", "occ", "messy"])
 def test_texture_patches_match_reference_tu(ref, orc, seam_inputs, name):
     """generate_texture_patches.cpp:453-538 (+ generate_candidate :78-138, merge_vertex_projection_infos :40-65) and the
     zero-adjust pass texrecon.cpp:174-183 (TexturePatch::adjust_colors, texture_patch.cpp:41-116) vs oracle/patches.py:
@@ -257,7 +257,7 @@ def test_texture_patches_match_reference_tu(ref, orc, seam_inputs, name):
             assert np.array_equal(np.asarray(mine[pid], np.float32).view(np.uint32), theirs[pid].view(np.uint32))
 
 
-@pytest.mark.parametrize("name", ["tiny", "occ"])
+@pytest.mark.parametrize("name", ["tiny", "occ", "messy"])
 def test_global_seam_leveling_matches_reference_tu(ref, orc, seam_inputs, name):
     """tex::global_seam_leveling (global_seam_leveling.cpp:140-324: unknown numbering, Gamma, A, b from patch-relative
     edge samples, Lhs, CG per channel, mean subtraction, adjust_colors per patch) vs orc_global_seam_leveling +

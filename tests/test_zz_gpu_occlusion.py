@@ -150,7 +150,7 @@ def test_multi_gpu_seam_kernel_on_one_rank(b2, get_scene, oracle_pipeline):
     assert np.array_equal(x2.view(np.uint32), x3.view(np.uint32))
 
 
-@pytest.mark.parametrize("name", ["occ", "occ2", "tiny"])
+@pytest.mark.parametrize("name", ["occ", "occ2", "tiny", "messy"])
 def test_cuda_path_matches_committed_golden_snapshots_late(b2, scene_mod, get_scene, name):
     """CUDA outputs against tests/golden/oracle_snapshots.json directly (no oracle run involved): the occlusion scenes through
     data costs / view selection / seam assembly, and -- where the snapshot holds them -- the texture patches after the
