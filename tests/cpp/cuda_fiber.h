@@ -15,6 +15,7 @@
 #include <string.h>
 #include <ucontext.h>
 
+#include <algorithm>
 #include <functional>
 #include <vector>
 
@@ -44,6 +45,11 @@ static Fiber *g_cur = nullptr;
 static std::function<void()> g_body;
 static Barrier g_grid;
 static unsigned long long g_switches = 0, g_switch_limit = 0;
+// 0 = round robin in thread order; otherwise every scheduler pass visits the live fibers in a fresh pseudo-random order
+// (hardware gives no ordering guarantee either: protocols must not depend on who runs first)
+static unsigned long long g_schedule_seed = 0;
+static inline void set_schedule(unsigned long long seed) { g_schedule_seed = seed; }
+static inline unsigned long long next_rand() { g_schedule_seed = g_schedule_seed * 6364136223846793005ull + 1442695040888963407ull; return g_schedule_seed >> 33; }
 
 static inline void yield() { Fiber *f = g_cur; swapcontext(&f->ctx, &g_sched); }
 
@@ -94,9 +100,12 @@ static bool launch(unsigned grid, unsigned block, F body, unsigned long long max
     }
     size_t remaining = fibers.size();
     g_switches = 0;
+    std::vector<unsigned> order_(fibers.size());
+    for (size_t i = 0; i < order_.size(); ++i) order_[i] = (unsigned)i;
     while (remaining) {
-        for (size_t i = 0; i < fibers.size(); ++i) {
-            Fiber &f = fibers[i];
+        if (g_schedule_seed) for (size_t i = order_.size(); i > 1; --i) std::swap(order_[i - 1], order_[next_rand() % i]);
+        for (size_t oi = 0; oi < fibers.size(); ++oi) {
+            Fiber &f = fibers[order_[oi]];
             if (f.done) continue;
             g_cur = &f; threadIdx.x = f.tx; blockIdx.x = f.bx;
             swapcontext(&g_sched, &f.ctx);
@@ -141,9 +150,12 @@ static bool launch_ranks(unsigned ranks, unsigned grid, unsigned block, F body, 
     }
     size_t remaining = fibers.size();
     g_switches = 0;
+    std::vector<unsigned> order_(fibers.size());
+    for (size_t i = 0; i < order_.size(); ++i) order_[i] = (unsigned)i;
     while (remaining) {
-        for (size_t i = 0; i < fibers.size(); ++i) {
-            Fiber &f = fibers[i];
+        if (g_schedule_seed) for (size_t i = order_.size(); i > 1; --i) std::swap(order_[i - 1], order_[next_rand() % i]);
+        for (size_t oi = 0; oi < fibers.size(); ++oi) {
+            Fiber &f = fibers[order_[oi]];
             if (f.done) continue;
             g_cur = &f; threadIdx.x = f.tx; blockIdx.x = f.bx;
             swapcontext(&g_sched, &f.ctx);

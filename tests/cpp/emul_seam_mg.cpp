@@ -24,6 +24,8 @@ using namespace b2;
 
 extern "C" {
 
+void emul_set_schedule(unsigned long long seed) { emul::set_schedule(seed); }   // 0 = round robin
+
 void emul_seam_mg_free(void *p) { free(p); }
 
 // x_out: [ranks][R][3] -- the complete solution as every rank ends up with it; status_out: [ranks][16]

@@ -583,3 +583,46 @@ def test_device_local_seam_leveling_without_global_leveling(emul, orc, local_inp
     for a, (img, val) in zip(ep, exp):
         assert np.array_equal(a["validity"], val)
         assert np.abs(a["image"] - img).max() < 1e-4           # raw gain/bias differences are ~10x larger than after global leveling
+
+
+@pytest.mark.parametrize("seed", [0x9E3779B97F4A7C15, 12345])
+def test_protocols_do_not_depend_on_the_thread_schedule(emul, orc, scene_mod, get_scene, seed):
+    """Hardware promises no execution order between warps, blocks or GPUs.  The fiber scheduler can visit the live threads in
+    a fresh pseudo-random order on every pass; the dataflow sweeps of the MRF (flags), the cooperative PCG (grid.sync) and
+    the multi-GPU solve (epoch flags in peer memory) must give the very same results as under round robin."""
+    s = get_scene("tiny")
+    adj = scene_mod.face_adjacency(s.faces)
+    rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
+    dc = orc.data_costs(s)
+    o = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1)
+    os_ = orc.global_seam_leveling(s, rings, o["labels"])
+    views, keep = orc.make_views(s)
+    F = s.num_faces
+    for lib in ("emul_mrf", "emul_seam_mg"):
+        emul[lib].emul_set_schedule(C.c_uint64(seed))
+    try:
+        P = dict(orc.DEFAULT_MRF)
+        params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], P["num_parts"], 0, 2, 2], np.uint32)
+        labels = np.zeros(F, np.uint32)
+        trace = np.full(P["max_iterations"] + 1, np.nan)
+        it = emul["emul_mrf"].emul_view_selection(C.c_uint32(F), C.c_uint32(s.num_views), orc._p(adj[0]), orc._p(adj[1]), orc._p(dc["face_ptr"]),
+                                                  orc._p(dc["view"]), orc._p(dc["cost"]), orc._p(params), C.c_float(P["ratio"]), orc._p(labels),
+                                                  orc._p(trace), None)
+        assert it == o["iterations"] and np.array_equal(labels, o["labels"])
+        ranks = 2
+        R, xp = C.c_uint32(), C.c_void_p()
+        status = np.zeros(16 * ranks, np.uint32)
+        L = emul["emul_seam_mg"]
+        rc = L.emul_seam_mg(orc._p(s.verts), C.c_uint32(s.verts.shape[0]), orc._p(s.faces), C.c_uint32(F), orc._p(rings[0]), orc._p(rings[1]),
+                            orc._p(rings[2]), orc._p(rings[3]), orc._p(np.ascontiguousarray(o["labels"], np.uint32)), views,
+                            C.c_uint32(s.num_views), C.c_uint32(ranks), C.c_uint32(1), C.byref(R), C.byref(xp), orc._p(status))
+        assert rc == 0
+        x = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_float)), (ranks * R.value * 3,)).copy().reshape(ranks, R.value, 3)
+        L.emul_seam_mg_free(xp)
+        st = status.reshape(ranks, 16)
+        assert not st[:, 7].any() and st[0, :3].tolist() == list(os_["iterations"])
+        assert np.array_equal(x[0].view(np.uint32), x[1].view(np.uint32))
+        assert np.linalg.norm(x[0] - os_["x"]) / np.linalg.norm(os_["x"]) < 1e-4
+    finally:
+        for lib in ("emul_mrf", "emul_seam_mg"):
+            emul[lib].emul_set_schedule(C.c_uint64(0))
