@@ -480,7 +480,7 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
     B2_CUDA(cudaStreamSynchronize(s));
     std::vector<uint32_t> seam_edges;
     find_seam_edges(F, adj_ptr.data(), adj_idx.data(), labels.data(), mesh_faces.data(), seam_edges);
-    std::vector<std::vector<VertexProj> > vpi;
+    VertexProjections vpi;
     vertex_projections(c->Vn, mesh_faces.data(), pl, ps.faces.data(), tex.data(), seam_edges, vpi);
     SeamLines sl;
     plan_seam_lines(seam_edges, vpi, sl);

@@ -176,12 +176,20 @@ inline void find_seam_edges(uint32_t F, const uint32_t *adj_ptr, const uint32_t 
 // generate_texture_patches.cpp:520-535 + merge: per vertex one entry per patch (ascending patch id), first projection
 // wins, faces appended.  slot order is patch major, so entries arrive in ascending patch order.  Only the vertices local
 // seam leveling looks at get entries: those lying in more than one patch (:157) and the end points of seam edges (:117);
-// for the two million faces of the C3 workload that is 1.5 % of the vertices (400 ms -> 30 ms on one host core).
+// for the two million faces of the C3 workload that is 3 % of the vertices (400 ms -> 85 ms on one host core, incl.
+// find_seam_edges).
+// Entries exist only for the vertices local seam leveling looks at; `index[v]` is the position of vertex v in `entries`
+// or 0xFFFFFFFF.  (A vector per vertex of the mesh costs more than the rest of the bookkeeping at two million faces.)
+struct VertexProjections {
+    std::vector<uint32_t> index;                       // [num_verts]
+    std::vector<uint32_t> vertex;                      // [entries] vertex id, ascending
+    std::vector<std::vector<VertexProj> > entries;
+    const std::vector<VertexProj> *find(uint32_t v) const { return index[v] == 0xFFFFFFFFu ? nullptr : &entries[index[v]]; }
+};
+
 inline void vertex_projections(uint32_t num_verts, const uint32_t *mesh_faces, const PatchPlan &plan, const uint32_t *slot_face,
-                               const float *tex /* [slots][3][2] */, const std::vector<uint32_t> &seam_edges,
-                               std::vector<std::vector<VertexProj> > &vpi)
+                               const float *tex /* [slots][3][2] */, const std::vector<uint32_t> &seam_edges, VertexProjections &vpi)
 {
-    vpi.assign(num_verts, std::vector<VertexProj>());
     const uint32_t T = plan.num_slots();
     std::vector<uint32_t> first(num_verts, 0xFFFFFFFFu);
     std::vector<uint8_t> need(num_verts, 0);
@@ -194,12 +202,17 @@ inline void vertex_projections(uint32_t num_verts, const uint32_t *mesh_faces, c
         }
     }
     for (uint32_t v : seam_edges) need[v] = 1;
+    vpi.index.assign(num_verts, 0xFFFFFFFFu);
+    vpi.vertex.clear();
+    for (uint32_t v = 0; v < num_verts; ++v)
+        if (need[v]) { vpi.index[v] = (uint32_t)vpi.vertex.size(); vpi.vertex.push_back(v); }
+    vpi.entries.assign(vpi.vertex.size(), std::vector<VertexProj>());
     for (uint32_t t = 0; t < T; ++t) {
         const uint32_t f = slot_face[t], q = plan.slot_patch[t];
         for (int j = 0; j < 3; ++j) {
             const uint32_t v = mesh_faces[3 * (size_t)f + j];
             if (!need[v]) continue;
-            std::vector<VertexProj> &e = vpi[v];
+            std::vector<VertexProj> &e = vpi.entries[vpi.index[v]];
             if (e.empty() || e.back().patch != q) {
                 VertexProj p; p.patch = q; p.x = tex[6 * (size_t)t + 2 * j]; p.y = tex[6 * (size_t)t + 2 * j + 1];
                 e.push_back(p);
@@ -226,15 +239,16 @@ struct SeamLines {
 
 // find_mesh_edge_projections (seam_leveling.cpp:61-91) per seam edge, the sampling density of
 // local_seam_leveling.cpp:131-140 and the vertex list of :155-176
-inline void plan_seam_lines(const std::vector<uint32_t> &seam_edges, const std::vector<std::vector<VertexProj> > &vpi, SeamLines &out)
+inline void plan_seam_lines(const std::vector<uint32_t> &seam_edges, const VertexProjections &vpi, SeamLines &out)
 {
     out = SeamLines();
     for (size_t ei = 0; ei + 1 < seam_edges.size(); ei += 2) {
             const uint32_t v1 = seam_edges[ei], v2 = seam_edges[ei + 1];
             const uint32_t pb = (uint32_t)out.proj_patch.size();
             float max_length = 1.0f;
-            for (const VertexProj &p1 : vpi[v1])
-                for (const VertexProj &p2 : vpi[v2]) {
+            const std::vector<VertexProj> *e1 = vpi.find(v1), *e2 = vpi.find(v2);
+            if (e1 && e2) for (const VertexProj &p1 : *e1)
+                for (const VertexProj &p2 : *e2) {
                     if (p1.patch != p2.patch) continue;
                     bool common = false;
                     for (uint32_t f1 : p1.faces) { for (uint32_t f2 : p2.faces) if (f1 == f2) { common = true; break; } if (common) break; }
@@ -252,11 +266,12 @@ inline void plan_seam_lines(const std::vector<uint32_t> &seam_edges, const std::
             const uint32_t info[4] = {pb, (uint32_t)out.proj_patch.size() - pb, sb, n};
             out.edge_info.insert(out.edge_info.end(), info, info + 4);
         }
-    for (uint32_t v = 0; v < (uint32_t)vpi.size(); ++v) {
-        if (vpi[v].size() <= 1) continue;                            // :157
-        const uint32_t info[2] = {(uint32_t)out.vert_proj_patch.size(), (uint32_t)vpi[v].size()};
+    for (size_t k = 0; k < vpi.entries.size(); ++k) {                // ascending vertex id
+        const std::vector<VertexProj> &e = vpi.entries[k];
+        if (e.size() <= 1) continue;                                 // :157
+        const uint32_t info[2] = {(uint32_t)out.vert_proj_patch.size(), (uint32_t)e.size()};
         out.vert_info.insert(out.vert_info.end(), info, info + 2);
-        for (const VertexProj &p : vpi[v]) { out.vert_proj_patch.push_back(p.patch); out.vert_proj.push_back(p.x); out.vert_proj.push_back(p.y); }
+        for (const VertexProj &p : e) { out.vert_proj_patch.push_back(p.patch); out.vert_proj.push_back(p.x); out.vert_proj.push_back(p.y); }
     }
 }
 
