@@ -11,11 +11,29 @@
 #include <algorithm>
 #include <cmath>
 #include <deque>
+#include <thread>
 #include <vector>
 
 namespace b2 {
 
 constexpr int PATCH_BORDER = 1;  // texture_patch.h:21
+
+// fn(chunk, begin, end) over [0, n) in `chunks` contiguous pieces on up to 16 host threads; results that depend on the
+// order are collected per chunk and concatenated in chunk order by the callers, so they equal the sequential ones
+template <typename Fn>
+inline void host_parallel_chunks(size_t n, unsigned chunks, Fn fn)
+{
+    if (chunks <= 1 || n < 4096) { fn(0u, (size_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (unsigned k = 0; k < chunks; ++k)
+        th.emplace_back([=] { fn(k, n * k / chunks, n * (k + 1) / chunks); });
+    for (std::thread &t : th) t.join();
+}
+inline unsigned host_threads()
+{
+    unsigned h = std::thread::hardware_concurrency();
+    return h < 1 ? 1u : (h > 16 ? 16u : h);
+}
 
 struct PatchComponent {
     uint32_t label;
@@ -29,39 +47,54 @@ inline void label_components(uint32_t F, const uint32_t *adj_ptr, const uint32_t
                              std::vector<uint32_t> &comp_faces, std::vector<PatchComponent> &comps)
 {
     comp_faces.clear(); comps.clear();
-    comp_faces.reserve(F);
+    // faces grouped by label (counting sort, ascending face id inside a label); labels are independent of each other:
+    // a breadth-first search never leaves its label, so the labels are searched in parallel and concatenated in order
+    uint32_t maxl = 0;
+    for (uint32_t i = 0; i < F; ++i) maxl = std::max(maxl, labels[i]);
+    std::vector<uint32_t> lptr((size_t)maxl + 2, 0);
+    for (uint32_t i = 0; i < F; ++i) lptr[labels[i] + 1]++;
+    for (uint32_t l = 0; l <= maxl; ++l) lptr[l + 1] += lptr[l];
+    std::vector<uint32_t> by_label(F), cur(lptr.begin(), lptr.end() - 1);
+    for (uint32_t i = 0; i < F; ++i) by_label[cur[labels[i]]++] = i;
     std::vector<uint8_t> used(F, 0);
-    std::deque<uint32_t> queue;
-    for (uint32_t i = 0; i < F; ++i) {
-        if (labels[i] == 0 || used[i]) continue;
-        const uint32_t label = labels[i];
-        PatchComponent c; c.label = label; c.begin = (uint32_t)comp_faces.size();
-        queue.clear(); queue.push_back(i); used[i] = 1;
-        while (!queue.empty()) {
-            const uint32_t node = queue.front(); queue.pop_front();
-            comp_faces.push_back(node);
-            for (uint32_t a = adj_ptr[node]; a < adj_ptr[node + 1]; ++a) {
-                const uint32_t w = adj_idx[a];
-                if (labels[w] == label && !used[w]) { queue.push_back(w); used[w] = 1; }
+    std::vector<std::vector<uint32_t> > faces_of((size_t)maxl + 1);
+    std::vector<std::vector<PatchComponent> > comps_of((size_t)maxl + 1);
+    const unsigned nthreads = F > 50000 ? host_threads() : 1u;
+    auto search = [&](unsigned k) {
+        std::deque<uint32_t> queue;
+        for (uint32_t label = 1 + k; label <= maxl; label += nthreads) {   // interleaved: balances the threads
+            std::vector<uint32_t> &out = faces_of[label];
+            out.reserve(lptr[label + 1] - lptr[label]);
+            for (uint32_t p = lptr[label]; p < lptr[label + 1]; ++p) {
+                const uint32_t i = by_label[p];
+                if (used[i]) continue;
+                PatchComponent c; c.label = label; c.begin = (uint32_t)out.size();
+                queue.clear(); queue.push_back(i); used[i] = 1;
+                while (!queue.empty()) {
+                    const uint32_t node = queue.front(); queue.pop_front();
+                    out.push_back(node);
+                    for (uint32_t a = adj_ptr[node]; a < adj_ptr[node + 1]; ++a) {
+                        const uint32_t w = adj_idx[a];
+                        if (labels[w] == label && !used[w]) { queue.push_back(w); used[w] = 1; }
+                    }
+                }
+                c.end = (uint32_t)out.size();
+                comps_of[label].push_back(c);
             }
         }
-        c.end = (uint32_t)comp_faces.size();
-        comps.push_back(c);
+    };
+    if (nthreads == 1) search(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned k = 0; k < nthreads; ++k) th.emplace_back(search, k);
+        for (std::thread &t : th) t.join();
     }
-    // group by label, keeping the ascending-first-face order inside a label; rebuild the face list in that order
-    std::vector<uint32_t> order(comps.size());
-    for (size_t k = 0; k < order.size(); ++k) order[k] = (uint32_t)k;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return comps[a].label < comps[b].label; });
-    std::vector<uint32_t> faces2; faces2.reserve(comp_faces.size());
-    std::vector<PatchComponent> comps2; comps2.reserve(comps.size());
-    for (uint32_t k : order) {
-        PatchComponent c = comps[k];
-        const uint32_t b = (uint32_t)faces2.size();
-        faces2.insert(faces2.end(), comp_faces.begin() + c.begin, comp_faces.begin() + c.end);
-        c.begin = b; c.end = (uint32_t)faces2.size();
-        comps2.push_back(c);
+    comp_faces.reserve(F - (lptr[1] - lptr[0]));
+    for (uint32_t label = 1; label <= maxl; ++label) {
+        const uint32_t base = (uint32_t)comp_faces.size();
+        comp_faces.insert(comp_faces.end(), faces_of[label].begin(), faces_of[label].end());
+        for (PatchComponent c : comps_of[label]) { c.begin += base; c.end += base; comps.push_back(c); }
     }
-    comp_faces.swap(faces2); comps.swap(comps2);
 }
 
 struct PatchPlan {
@@ -149,7 +182,12 @@ inline void plan_patches(const std::vector<PatchComponent> &comps, const int32_t
 struct VertexProj {          // VertexProjectionInfo after merge_vertex_projection_infos (:40-65)
     uint32_t patch;
     float x, y;              // the FIRST projection of the vertex met in the patch
-    std::vector<uint32_t> faces;
+    // faces of the patch around the vertex: a handful, kept inline (a heap vector per entry dominated the bookkeeping)
+    uint32_t num_faces = 0;
+    uint32_t inline_faces[7];
+    std::vector<uint32_t> more_faces;   // beyond 7 (high-valence vertices)
+    void add_face(uint32_t f) { if (num_faces < 7) inline_faces[num_faces] = f; else more_faces.push_back(f); ++num_faces; }
+    uint32_t face(uint32_t i) const { return i < 7 ? inline_faces[i] : more_faces[i - 7]; }
 };
 
 // find_seam_edges (seam_leveling.cpp:16-59): one edge (v1 < v2) per pair of adjacent faces with different labels,
@@ -157,27 +195,32 @@ struct VertexProj {          // VertexProjectionInfo after merge_vertex_projecti
 inline void find_seam_edges(uint32_t F, const uint32_t *adj_ptr, const uint32_t *adj_idx, const uint32_t *labels,
                             const uint32_t *mesh_faces, std::vector<uint32_t> &edges /* pairs */)
 {
+    const unsigned chunks = F > 50000 ? host_threads() : 1u;
+    std::vector<std::vector<uint32_t> > part(chunks);
+    host_parallel_chunks(F, chunks, [&](unsigned k, size_t f0, size_t f1) {
+        std::vector<uint32_t> &out = part[k];
+        for (uint32_t node = (uint32_t)f0; node < (uint32_t)f1; ++node)
+            for (uint32_t a = adj_ptr[node]; a < adj_ptr[node + 1]; ++a) {
+                const uint32_t adj = adj_idx[a];
+                if (node > adj || labels[node] == labels[adj]) continue;
+                uint32_t shared[4]; int ns = 0;
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j)
+                        if (mesh_faces[3 * (size_t)node + i] == mesh_faces[3 * (size_t)adj + j] && ns < 4) shared[ns++] = mesh_faces[3 * (size_t)node + i];
+                if (ns != 2 || shared[0] == shared[1]) continue;   // the reference asserts this
+                uint32_t v1 = shared[0], v2 = shared[1];
+                if (v1 > v2) std::swap(v1, v2);
+                out.push_back(v1); out.push_back(v2);
+            }
+    });
     edges.clear();
-    for (uint32_t node = 0; node < F; ++node)
-        for (uint32_t a = adj_ptr[node]; a < adj_ptr[node + 1]; ++a) {
-            const uint32_t adj = adj_idx[a];
-            if (node > adj || labels[node] == labels[adj]) continue;
-            uint32_t shared[4]; int ns = 0;
-            for (int i = 0; i < 3; ++i)
-                for (int j = 0; j < 3; ++j)
-                    if (mesh_faces[3 * (size_t)node + i] == mesh_faces[3 * (size_t)adj + j] && ns < 4) shared[ns++] = mesh_faces[3 * (size_t)node + i];
-            if (ns != 2 || shared[0] == shared[1]) continue;   // the reference asserts this
-            uint32_t v1 = shared[0], v2 = shared[1];
-            if (v1 > v2) std::swap(v1, v2);
-            edges.push_back(v1); edges.push_back(v2);
-        }
+    for (unsigned k = 0; k < chunks; ++k) edges.insert(edges.end(), part[k].begin(), part[k].end());   // face-major order
 }
 
 // generate_texture_patches.cpp:520-535 + merge: per vertex one entry per patch (ascending patch id), first projection
 // wins, faces appended.  slot order is patch major, so entries arrive in ascending patch order.  Only the vertices local
 // seam leveling looks at get entries: those lying in more than one patch (:157) and the end points of seam edges (:117);
-// for the two million faces of the C3 workload that is 3 % of the vertices (400 ms -> 85 ms on one host core, incl.
-// find_seam_edges).
+// for the two million faces of the C3 workload that is 3 % of the vertices.
 // Entries exist only for the vertices local seam leveling looks at; `index[v]` is the position of vertex v in `entries`
 // or 0xFFFFFFFF.  (A vector per vertex of the mesh costs more than the rest of the bookkeeping at two million faces.)
 struct VertexProjections {
@@ -191,35 +234,56 @@ inline void vertex_projections(uint32_t num_verts, const uint32_t *mesh_faces, c
                                const float *tex /* [slots][3][2] */, const std::vector<uint32_t> &seam_edges, VertexProjections &vpi)
 {
     const uint32_t T = plan.num_slots();
+    const unsigned chunks = T > 50000 ? host_threads() : 1u;
+    // pass 1 (parallel): which vertices are touched by more than one patch.  first[v] is claimed by compare-and-swap, so
+    // whichever patch gets there first, a second DIFFERENT patch always notices: need[] does not depend on the order.
     std::vector<uint32_t> first(num_verts, 0xFFFFFFFFu);
     std::vector<uint8_t> need(num_verts, 0);
-    for (uint32_t t = 0; t < T; ++t) {
-        const uint32_t f = slot_face[t], q = plan.slot_patch[t];
-        for (int j = 0; j < 3; ++j) {
-            const uint32_t v = mesh_faces[3 * (size_t)f + j];
-            if (first[v] == 0xFFFFFFFFu) first[v] = q;
-            else if (first[v] != q) need[v] = 1;
+    host_parallel_chunks(T, chunks, [&](unsigned, size_t t0, size_t t1) {
+        for (size_t t = t0; t < t1; ++t) {
+            const uint32_t f = slot_face[t], q = plan.slot_patch[t];
+            for (int j = 0; j < 3; ++j) {
+                const uint32_t v = mesh_faces[3 * (size_t)f + j];
+                uint32_t seen = __atomic_load_n(&first[v], __ATOMIC_RELAXED);
+                if (seen == 0xFFFFFFFFu) {
+                    uint32_t expected = 0xFFFFFFFFu;
+                    if (__atomic_compare_exchange_n(&first[v], &expected, q, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) continue;
+                    seen = expected;
+                }
+                if (seen != q) __atomic_store_n(&need[v], (uint8_t)1, __ATOMIC_RELAXED);
+            }
         }
-    }
+    });
     for (uint32_t v : seam_edges) need[v] = 1;
     vpi.index.assign(num_verts, 0xFFFFFFFFu);
     vpi.vertex.clear();
     for (uint32_t v = 0; v < num_verts; ++v)
         if (need[v]) { vpi.index[v] = (uint32_t)vpi.vertex.size(); vpi.vertex.push_back(v); }
     vpi.entries.assign(vpi.vertex.size(), std::vector<VertexProj>());
-    for (uint32_t t = 0; t < T; ++t) {
-        const uint32_t f = slot_face[t], q = plan.slot_patch[t];
-        for (int j = 0; j < 3; ++j) {
-            const uint32_t v = mesh_faces[3 * (size_t)f + j];
-            if (!need[v]) continue;
-            std::vector<VertexProj> &e = vpi.entries[vpi.index[v]];
-            if (e.empty() || e.back().patch != q) {
-                VertexProj p; p.patch = q; p.x = tex[6 * (size_t)t + 2 * j]; p.y = tex[6 * (size_t)t + 2 * j + 1];
-                e.push_back(p);
-            }
-            e.back().faces.push_back(f);
+    // pass 2 (parallel): the slots that touch such a vertex, per chunk, concatenated in slot order
+    std::vector<std::vector<uint32_t> > hit(chunks);
+    host_parallel_chunks(T, chunks, [&](unsigned k, size_t t0, size_t t1) {
+        for (size_t t = t0; t < t1; ++t) {
+            const uint32_t f = slot_face[t];
+            if (need[mesh_faces[3 * (size_t)f]] | need[mesh_faces[3 * (size_t)f + 1]] | need[mesh_faces[3 * (size_t)f + 2]]) hit[k].push_back((uint32_t)t);
         }
-    }
+    });
+    // pass 3 (sequential, a few per cent of the slots): entries in slot order = ascending patch id, first projection wins
+    for (unsigned k = 0; k < chunks; ++k)
+        for (uint32_t t : hit[k]) {
+            const uint32_t f = slot_face[t], q = plan.slot_patch[t];
+            for (int j = 0; j < 3; ++j) {
+                const uint32_t v = mesh_faces[3 * (size_t)f + j];
+                if (!need[v]) continue;
+                std::vector<VertexProj> &e = vpi.entries[vpi.index[v]];
+                if (e.empty()) e.reserve(3);
+                if (e.empty() || e.back().patch != q) {
+                    VertexProj p; p.patch = q; p.x = tex[6 * (size_t)t + 2 * j]; p.y = tex[6 * (size_t)t + 2 * j + 1];
+                    e.push_back(p);
+                }
+                e.back().add_face(f);
+            }
+        }
 }
 
 struct SeamLines {
@@ -251,7 +315,8 @@ inline void plan_seam_lines(const std::vector<uint32_t> &seam_edges, const Verte
                 for (const VertexProj &p2 : *e2) {
                     if (p1.patch != p2.patch) continue;
                     bool common = false;
-                    for (uint32_t f1 : p1.faces) { for (uint32_t f2 : p2.faces) if (f1 == f2) { common = true; break; } if (common) break; }
+                    for (uint32_t i1 = 0; i1 < p1.num_faces && !common; ++i1)
+                        for (uint32_t i2 = 0; i2 < p2.num_faces; ++i2) if (p1.face(i1) == p2.face(i2)) { common = true; break; }
                     if (!common) continue;
                     out.proj_patch.push_back(p1.patch);
                     out.edge_proj.push_back(p1.x); out.edge_proj.push_back(p1.y); out.edge_proj.push_back(p2.x); out.edge_proj.push_back(p2.y);
