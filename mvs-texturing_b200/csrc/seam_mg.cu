@@ -317,9 +317,10 @@ int seam_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t nranks, void *handle64)
     B2_CUDA(cudaMemsetAsync(m->block, 0, bytes, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     m->peer[rank] = m->block;
-    cudaIpcMemHandle_t h;
-    B2_CUDA(cudaIpcGetMemHandle(&h, m->block));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    if (nranks > 1) B2_CUDA(cudaIpcGetMemHandle(&h, m->block));   // a single rank has nobody to hand its block to
     memcpy(handle64, &h, 64);
     return B2TEX_OK;
 }
