@@ -11,7 +11,14 @@ leveling in the reference, and of the patch-based colour sampling that global_se
   sample_edge / calculate_difference   libs/tex/global_seam_leveling.cpp:26-43, 86-138
   TexturePatch::get_pixel_value        libs/tex/texture_patch.cpp:162-169 (FloatImage::linear_at)
 
-Purpose: pin the "stage-isolated" shortcut used by oracle/seam.c and by the CUDA path (colours sampled
+  TexturePatch::adjust_colors          libs/tex/texture_patch.cpp:41-116, applied per patch as global_seam_leveling.cpp:293-323
+  tex::local_seam_leveling             libs/tex/local_seam_leveling.cpp:105-204 with draw_line :39-92, find_seam_edges
+                                       seam_leveling.cpp:16-59, prepare_blending_mask texture_patch.cpp:197-297,
+                                       poisson_blend poisson_blending.cpp:49-138 (scipy splu for Eigen::SparseLU)
+All of it is held to the reference's own translation units by tests/test_ref_pinning.py (patches, masks, zero-adjust images
+bit for bit; leveled images to 2e-5) and is the checker of csrc/patches.cu / csrc/localseam.cu.
+
+Purpose of the first part: pin the "stage-isolated" shortcut used by oracle/seam.c and by the CUDA path (colours sampled
 from the whole view of a label at get_pixel_coords(vertex)) against the patch-relative sampling of the
 reference.  tests/test_oracle_cpu.py::test_patch_sampling_equals_view_sampling compares Rhs = A^T b.
 Patch ids are assigned in ascending label order (the reference's order depends on OpenMP scheduling,
