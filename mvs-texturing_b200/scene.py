@@ -6,6 +6,7 @@ oracle, the parity tests and bench.py consume is generated here:
   C1  geodesic icosphere nu=22  (9 680 faces),  6 axis cameras, 640x480
   C2  heightfield terrain 500x500 quads (500 000 faces), 50 cameras, 1920x1080
   C3  displaced icosphere nu=316 (1 997 120 faces), 200 cameras, 1920x1080
+  C5  heightfield terrain 2236x2236 quads (9 999 392 faces), 1000 cameras, 3840x2160 (C5s: 1 % scale)
 
 Conventions follow the reference's TextureView (texture_view.h:43-48, 161-166):
   pos, viewdir (world), proj (3x3 row major, pixels), world_to_cam (4x4 row major).
@@ -350,6 +351,10 @@ def config(name: str, with_images=True) -> Scene:
         return terrain_scene(60, 10, 480, 270, name=name, with_images=with_images)
     if name == "C3":
         return sphere_scene(316, 200, 1920, 1080, displace=0.05, name=name, with_images=with_images)
+    if name == "C5":        # BASELINE.json configs[4]: 10M-face terrain, 1000 views at 4K (24.9 GB of images: 8-GPU runs only)
+        return terrain_scene(2236, 1000, 3840, 2160, name=name, with_images=with_images)
+    if name == "C5s":       # C5 scaled to 1 %: 100 352 faces, 100 views, same camera layout
+        return terrain_scene(224, 100, 768, 432, name=name, with_images=with_images)
     if name == "C3s":       # 1/16-size C3
         return sphere_scene(79, 50, 960, 540, displace=0.05, name=name, with_images=with_images)
     raise KeyError(name)

@@ -18,8 +18,9 @@ import oracle as O  # noqa: E402
 
 scene = importlib.import_module("mvs-texturing_b200.scene")
 out = {}
-for name in ["tiny", "small", "C1", "C1d", "C2s", "C3s", "occ", "occ2", "messy"]:   # occ*: real occlusion, unseen faces, several
-    # components; messy: non-manifold fins, zero-area faces, a sliver, a detached triangle
+for name in ["tiny", "small", "C1", "C1d", "C2s", "C3s", "occ", "occ2", "messy", "C5s"]:   # occ*: real occlusion, unseen faces, several
+    # components; messy: non-manifold fins, zero-area faces, a sliver, a detached triangle; C5s: 92 candidate views per face
+    # (32 lanes per node in the MRF sweeps)
     s = scene.config(name)
     dc = O.data_costs(s)
     ap, ai = scene.face_adjacency(s.faces)

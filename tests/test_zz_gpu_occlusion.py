@@ -52,7 +52,7 @@ def test_view_selection_and_seam_leveling_with_unseen_faces(b2, get_scene, scene
     assert rel < 5e-3, rel
 
 
-@pytest.mark.parametrize("name", ["occ", "occ2", "tiny", "messy"])
+@pytest.mark.parametrize("name", ["occ", "occ2", "tiny", "messy", "C5s"])
 def test_golden_snapshots_of_the_occlusion_and_messy_scenes(b2, scene_mod, get_scene, name):
     """CUDA outputs of the three measured stages against tests/golden/oracle_snapshots.json directly (no oracle run involved) on the
     scenes added after the GPU budget of round 1 was spent (kernels that HAVE run on hardware, inputs that have not)."""
