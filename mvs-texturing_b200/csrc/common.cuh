@@ -53,7 +53,8 @@ struct DevBuf {
             p = nullptr;
             cap = 0;
             size_t want = count ? count : 1;
-            cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+            // 64 bytes of slack: 16-byte-granular bulk copies (cp.async.bulk) may read past the last element
+            cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T) + 64);
             if (e != cudaSuccess) {
                 set_error("cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
                 n = 0;
@@ -179,15 +180,21 @@ struct b2tex_ctx {
     bool have_adj = false, have_labels = false;
 
     // mrf scratch
-    b2::DevBuf<float> mrf_H, mrf_hminp1;
-    b2::DevBuf<uint32_t> mrf_amin, mrf_level, mrf_order, mrf_flags, mrf_ctl;
-    b2::DevBuf<unsigned long long> mrf_energy;
-    b2::DevBuf<uint32_t> mrf_mask;     // per-node label bitmasks
-    b2::DevBuf<uint16_t> mrf_mpre;     // labels in lower mask words
+    b2::DevBuf<float> mrf_H, mrf_hminp1;    // global-memory DP tables (trees that do not fit in shared memory only)
+    b2::DevBuf<uint32_t> mrf_amin, mrf_level, mrf_order, mrf_ctl, mrf_state;
+    b2::DevBuf<uint32_t> mrf_lidx;          // position of every node's label in its label list
+    b2::DevBuf<uint16_t> mrf_olev;          // level of order[i]
+    b2::DevBuf<uint32_t> mrf_pos;           // position of a node in order (forest nodes), else 0xFFFFFFFF
+    b2::DevBuf<uint2> mrf_tjoin;            // per node (tree, arrival number)
+    b2::DevBuf<uint4> mrf_ttab;             // per tree (nodes, labels, first order index, flags)
+    b2::DevBuf<unsigned long long> mrf_energy;   // [max_iterations + 2] fixed-point energies
     uint32_t mrf_mask_words = 0;
+    uint32_t mrf_tree_smem = 0;
     b2::DevBuf<uint4> mrf_adj4;        // compact degree<=3 adjacency
     b2::DevBuf<uint32_t> mrf_queue;    // forest frontier lists + stamps
-    b2::DevBuf<uint32_t> mrf_sort;     // radix sort keys/values of the level bucketing
+    uint32_t *mrf_host_flags = nullptr;   // pinned: stop flags the host polls behind the launches it queued
+    unsigned long long mrf_forest_nodes = 0, mrf_forest_nnz = 0;   // summed over the iterations of the last run
+    uint32_t mrf_slow_trees = 0;
     b2tex_mrf_params mrf_params{};
     bool mrf_ready = false;
     int mrf_group = 32;
@@ -240,6 +247,7 @@ int data_costs_histogram(b2tex_ctx *c, float gmax);
 int data_costs_normalize(b2tex_ctx *c, float gmax, const uint32_t *bins_host, b2tex_dc_info *info);
 int mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *energy_fixed);
 int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *energy_fixed);
+int mrf_run(b2tex_ctx *c, const b2tex_mrf_params *p, b2tex_mrf_info *info, double *trace);
 int mrf_energy_only(b2tex_ctx *c, int64_t *energy_fixed);
 int mrf_sample_only(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t, uint32_t *level_host);
 int mrf_energy_double(b2tex_ctx *c, double *e, uint64_t *unseen);

@@ -102,7 +102,6 @@ __device__ __forceinline__ bool mg_barrier(cg::grid_group &grid, const PcgMg &q,
 {
     __threadfence_system();   // this thread's peer stores before the rank-wide barrier
     grid.sync();
-    bool ok = true;
     if (blockIdx.x == 0 && threadIdx.x < q.nranks) {
         const uint32_t k = threadIdx.x;
         st_release_sys(mg_carve(q.peer[k], q.R).flag + q.rank, epoch);          // tell peer k: rank `rank` reached `epoch`
@@ -110,11 +109,13 @@ __device__ __forceinline__ bool mg_barrier(cg::grid_group &grid, const PcgMg &q,
         unsigned long long spins = 0;
         while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
             __nanosleep(64);
-            if (++spins > q.spin_limit) { ok = false; atomicAdd(q.status + 7, 1u); break; }
+            if (++spins > q.spin_limit) { atomicAdd(q.status + 7, 1u); break; }
         }
     }
     grid.sync();
-    return ok;
+    // the verdict must be grid-uniform: every thread reads the timeout counter the pollers wrote before the
+    // grid-wide barrier, so all threads leave the PCG loop in the same iteration (no mismatched grid.sync)
+    return __ldcg(q.status + 7) == 0u;
 }
 
 // sum of the per-block partials of this rank (every thread computes the same value), pushed to all peers by block 0

@@ -92,7 +92,7 @@ def make_views(scene, images=None):
     return arr, imgs
 
 
-DEFAULT_MRF = dict(max_iterations=100, rounds=32, root_div=256, seed=548923723, window=5,
+DEFAULT_MRF = dict(max_iterations=100, rounds=16, root_div=64, seed=548923723, window=5,
                    ratio=0.01, num_parts=1)
 
 

@@ -224,6 +224,16 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned d
     emul::wait(w->bar);
     return r;
 }
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned delta)
+{
+    emul::Warp *w = emul::g_cur->warp;
+    const unsigned lane = threadIdx.x & 31u;
+    w->slot[lane] = emul::to_bits(v);
+    emul::wait(w->bar);
+    const T r = lane >= delta ? emul::from_bits<T>(w->slot[lane - delta]) : v;
+    emul::wait(w->bar);
+    return r;
+}
 static inline unsigned __ballot_sync(unsigned, bool p)
 {
     emul::Warp *w = emul::g_cur->warp;
@@ -239,6 +249,7 @@ static inline unsigned __ballot_sync(unsigned, bool p)
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
@@ -246,6 +257,8 @@ static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T __ldcg(const T *p) { return *(const volatile T *)p; }
+static inline uint2 __ldcg(const uint2 *p) { return *p; }
+static inline uint4 __ldcg(const uint4 *p) { return *p; }
 template <typename T> static inline void __stcg(T *p, T v) { *(volatile T *)p = v; }
 static inline void __threadfence() {}
 static inline void __threadfence_system() {}

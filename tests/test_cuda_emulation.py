@@ -53,8 +53,8 @@ def emul():
         f.write(_kernel_part("datacosts.cu", "int data_costs_qualities(", ("int cub_exclusive_sum_u64", "namespace {")))
     with open(os.path.join(OUT, "mrf_kernels.inc"), "w") as f:
         f.write(_kernel_part("mrf.cu", "Mrf make_mrf(b2tex_ctx",
-                             ("__device__ __forceinline__ uint32_t ld_acquire", "template <int G>\n__global__ void __launch_bounds__(256) k_init_labels"),
-                             "    extern __shared__ uint32_t sm[];  // [rounds+1] level counts\n", close=2))
+                             ("// ---- shared-memory / async-copy primitives", "// ---- end of primitives ----"),
+                             "    extern __shared__ __align__(16) unsigned char tree_dyn[];\n", close=2))
     with open(os.path.join(OUT, "seam_kernels.inc"), "w") as f:
         f.write(_kernel_part("seam.cu", "int seam_run(b2tex_ctx"))
     with open(os.path.join(OUT, "seam_mg_kernels.inc"), "w") as f:
@@ -143,7 +143,8 @@ def test_device_data_cost_kernels(emul, orc, get_scene, name, data_term, vis):
 
 
 @pytest.mark.parametrize("name,kw", [("tiny", {}), ("occ", {}), ("occ", dict(root_div=0, rounds=200)), ("occ", dict(num_parts=2)),
-                                     ("occ", dict(group=32)), ("messy", {})])
+                                     ("occ", dict(group=32)), ("messy", {}), ("occ", dict(smem=6144)), ("occ", dict(smem=2048, group=8)),
+                                     ("occ", dict(rounds=32, root_div=256, smem=16384))])
 def test_device_view_selection_kernels(emul, orc, scene_mod, get_scene, name, kw):
     """csrc/mrf.cu on fibers vs orc_view_selection: identical forest levels in iteration 1, identical iteration count,
     identical labels (=> identical energy).  `occ`: unseen faces (label 0, excluded from the graph), ten components,
@@ -152,18 +153,19 @@ def test_device_view_selection_kernels(emul, orc, scene_mod, get_scene, name, kw
     adj = scene_mod.face_adjacency(s.faces)
     dc = orc.data_costs(s)
     P = dict(orc.DEFAULT_MRF)
-    okw = {k: v for k, v in kw.items() if k != "group"}
+    okw = {k: v for k, v in kw.items() if k not in ("group", "smem")}
     P.update(okw)
     o = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1, **okw)
     F = s.num_faces
-    params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], P["num_parts"], kw.get("group", 0), 2, 2],
-                      np.uint32)
+    params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], P["num_parts"], kw.get("group", 0),
+                       kw.get("smem", 0), 0], np.uint32)
+    stats = np.zeros(4, np.uint64)
     labels = np.zeros(F, np.uint32)
     trace = np.full(P["max_iterations"] + 1, np.nan)
     lvl = np.zeros(F, np.uint32)
     it = emul["emul_mrf"].emul_view_selection(C.c_uint32(F), C.c_uint32(s.num_views), orc._p(adj[0]), orc._p(adj[1]), orc._p(dc["face_ptr"]),
                                               orc._p(dc["view"]), orc._p(dc["cost"]), orc._p(params), C.c_float(P["ratio"]), orc._p(labels),
-                                              orc._p(trace), orc._p(lvl))
+                                              orc._p(trace), orc._p(lvl), orc._p(stats))
     assert it >= 0, "a kernel launch did not terminate (protocol hang)" if it == -1 else "bad parameters"
     assert np.array_equal(lvl, orc.mrf_sample_forest(adj[0], adj[1], dc["face_ptr"], 1, **okw))
     assert it == o["iterations"]
@@ -171,6 +173,10 @@ def test_device_view_selection_kernels(emul, orc, scene_mod, get_scene, name, kw
     assert abs(trace[it] - o["energy"]) <= 1e-6 * max(1.0, o["energy"])
     if name == "occ":
         assert (o["labels"] == 0).sum() > 10
+    if kw.get("root_div", 1) == 0 or kw.get("smem", 1 << 20) <= 6144:
+        assert stats[0] > 0          # trees that do not fit the pool took the global-memory recursion
+    elif name != "messy" and "smem" not in kw:
+        assert stats[0] == 0, stats  # default pool: every tree of these scenes is solved in shared memory
 
 
 @pytest.mark.parametrize("name", ["tiny", "occ", "messy"])
@@ -517,7 +523,7 @@ def test_device_view_selection_generic_paths(emul, orc, case):
     labels = np.zeros(n, np.uint32)
     trace = np.full(P["max_iterations"] + 1, np.nan)
     it = emul["emul_mrf"].emul_view_selection(C.c_uint32(n), C.c_uint32(Kdev), orc._p(ap), orc._p(ai), orc._p(ptr), orc._p(view), orc._p(cost),
-                                              orc._p(params), C.c_float(P["ratio"]), orc._p(labels), orc._p(trace), None)
+                                              orc._p(params), C.c_float(P["ratio"]), orc._p(labels), orc._p(trace), None, None)
     assert it == o["iterations"] and np.array_equal(labels, o["labels"])
     if extra:
         assert int(np.diff(ap).max()) > 3
@@ -607,7 +613,7 @@ def test_protocols_do_not_depend_on_the_thread_schedule(emul, orc, scene_mod, ge
         trace = np.full(P["max_iterations"] + 1, np.nan)
         it = emul["emul_mrf"].emul_view_selection(C.c_uint32(F), C.c_uint32(s.num_views), orc._p(adj[0]), orc._p(adj[1]), orc._p(dc["face_ptr"]),
                                                   orc._p(dc["view"]), orc._p(dc["cost"]), orc._p(params), C.c_float(P["ratio"]), orc._p(labels),
-                                                  orc._p(trace), None)
+                                                  orc._p(trace), None, None)
         assert it == o["iterations"] and np.array_equal(labels, o["labels"])
         ranks = 2
         R, xp = C.c_uint32(), C.c_void_p()
