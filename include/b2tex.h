@@ -115,6 +115,7 @@ const char *b2tex_last_error(void);
 void b2tex_free(void *host_ptr);                 /* frees buffers returned by one-shot calls */
 int b2tex_device_synchronize(b2tex_ctx *ctx);
 uint64_t b2tex_stream(b2tex_ctx *ctx);            /* the cudaStream_t every kernel is launched on */
+uint64_t b2tex_launch_count(void);                /* kernels of this library launched by this process so far (CUB's not counted) */
 /* per-kernel CUDA-event timing: enable, run stages, read "name ms algorithmic_bytes" lines */
 int b2tex_profile(b2tex_ctx *ctx, int enable);
 int b2tex_profile_report(b2tex_ctx *ctx, char *buf, uint64_t cap);
@@ -148,6 +149,22 @@ int b2tex_data_costs_download(b2tex_ctx *ctx, uint64_t *face_ptr, uint16_t *view
 int b2tex_view_selection_run(b2tex_ctx *ctx, const b2tex_mrf_params *params, b2tex_mrf_info *info,
                              double *energy_trace_or_null);
 int b2tex_labels_download(b2tex_ctx *ctx, uint32_t *labels);
+/* Multi-GPU view selection (one process per GPU, at most 8): rank r owns the faces [r * ceil(F / P), (r + 1) * ceil(F / P))
+ * (b2tex_set_face_range) and runs b2tex_view_selection_run with params->num_parts = P like a single GPU would.  Before
+ * that, once per mesh size: every rank calls b2tex_mrf_mg_export (allocates a peer-visible block holding its full-length
+ * label array, the energy slots and the barrier flags; the context's labels live inside it from then on), the 64-byte
+ * cudaIpc handles are exchanged by the caller (e.g. one all-gather over torch.distributed) and imported with
+ * b2tex_mrf_mg_import.  Inside the run the ranks exchange only the labels of their boundary faces -- stored straight
+ * into the label arrays of the ranks that own a neighbouring face -- and their partial energies, through NVLink peer
+ * memory with epoch-flag barriers; every rank takes the identical stop decision (view_selection.cpp:84) from the
+ * identical fixed-point sum.  No NCCL call and no host round trip per iteration. */
+int b2tex_mrf_mg_export(b2tex_ctx *ctx, uint32_t rank, uint32_t num_ranks, void *ipc_handle_64_bytes);
+int b2tex_mrf_mg_import(b2tex_ctx *ctx, uint32_t peer_rank, const void *ipc_handle_64_bytes);
+/* Peers that live in the SAME process (several contexts driven by threads) cannot open each other's IPC handles: after
+ * the export they attach the raw device pointer of the peer's block instead.  which: 0 = view selection block
+ * (b2tex_mrf_mg_export), 1 = seam solve block (b2tex_seam_mg_export). */
+uint64_t b2tex_peer_block(b2tex_ctx *ctx, int which);
+int b2tex_peer_attach(b2tex_ctx *ctx, int which, uint32_t peer_rank, uint64_t peer_block_device_ptr);
 /* building blocks of one solver iteration, exposed so that a sharded run can exchange boundary
  * labels between iterations; view_selection_run = init + loop(iterate, energy) */
 int b2tex_mrf_init(b2tex_ctx *ctx, const b2tex_mrf_params *params, int64_t *energy_fixed);
@@ -163,7 +180,7 @@ int b2tex_seam_run(b2tex_ctx *ctx, b2tex_seam_info *info);
  * of all peers (exchanged by the caller, e.g. an all-gather over torch.distributed), then every rank calls
  * b2tex_seam_mg_solve: one persistent cooperative kernel per GPU that runs the PCG on its slice of the rows and exchanges
  * the search direction and the dot products with its peers through NVLink peer memory inside the kernel.  Every rank ends
- * with the complete solution (b2tex_seam_download).  At most 8 ranks.  Not yet run on hardware (emulation only). */
+ * with the complete solution (b2tex_seam_download).  At most 8 ranks. */
 int b2tex_seam_assemble(b2tex_ctx *ctx, b2tex_seam_info *info);
 int b2tex_seam_mg_export(b2tex_ctx *ctx, uint32_t rank, uint32_t num_ranks, void *ipc_handle_64_bytes);
 int b2tex_seam_mg_import(b2tex_ctx *ctx, uint32_t peer_rank, const void *ipc_handle_64_bytes);
@@ -195,7 +212,10 @@ int b2tex_local_seam_leveling_run(b2tex_ctx *ctx, b2tex_local_seam_info *info);
 /* raw device pointers of resident results (torch / NCCL plumbing); 0 if absent */
 uint64_t b2tex_device_ptr(b2tex_ctx *ctx, const char *name, uint64_t *num_elements);
 
-/* ---- one-shot host-buffer entry points (what the reference-side binding calls) ---- */
+/* ---- one-shot host-buffer entry points (what the reference-side binding calls) ----
+ * They run on the calling thread's current CUDA device (cudaGetDevice) and keep up to two finished contexts (stream +
+ * device buffers) cached for the next call; b2tex_release_cached_contexts() frees them. */
+void b2tex_release_cached_contexts(void);
 /* tex::calculate_data_costs: out arrays are malloc'ed by the library (b2tex_free), CSR by face:
  * face_ptr[F+1], view[nnz] ascending per face, cost[nnz]. */
 int b2tex_calculate_data_costs(const float *verts, uint32_t num_verts, const uint32_t *faces,

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, "libb2tex.so")
 
 EXPORTS = [
     "b2tex_create", "b2tex_destroy", "b2tex_last_error", "b2tex_free", "b2tex_device_synchronize",
-    "b2tex_stream", "b2tex_profile", "b2tex_profile_report",
+    "b2tex_stream", "b2tex_launch_count", "b2tex_profile", "b2tex_profile_report",
     "b2tex_default_mrf_params", "b2tex_set_mesh", "b2tex_set_views", "b2tex_set_adjacency",
     "b2tex_set_vertex_rings", "b2tex_set_data_costs", "b2tex_set_labels", "b2tex_set_face_range",
     "b2tex_data_costs_run", "b2tex_data_costs_qualities", "b2tex_data_costs_histogram",
@@ -30,9 +30,9 @@ EXPORTS = [
     "b2tex_labels_download", "b2tex_mrf_init", "b2tex_mrf_iterate", "b2tex_mrf_energy", "b2tex_mrf_sample_forest",
     "b2tex_seam_run", "b2tex_seam_download", "b2tex_seam_matrix_download", "b2tex_device_ptr",
     "b2tex_texture_patches_run", "b2tex_texture_patches_download", "b2tex_local_seam_leveling_run", "b2tex_seam_assemble", "b2tex_seam_mg_export", "b2tex_seam_mg_import",
-    "b2tex_seam_mg_solve",
+    "b2tex_seam_mg_solve", "b2tex_mrf_mg_export", "b2tex_mrf_mg_import", "b2tex_peer_block", "b2tex_peer_attach",
     "b2tex_calculate_data_costs", "b2tex_calculate_data_costs_into", "b2tex_view_selection",
-    "b2tex_global_seam_leveling", "b2tex_texture_hot_path", "b2tex_seam_leveling_patches",
+    "b2tex_global_seam_leveling", "b2tex_texture_hot_path", "b2tex_seam_leveling_patches", "b2tex_release_cached_contexts",
 ]
 
 
@@ -98,6 +98,8 @@ def lib():
         L.b2tex_last_error.restype = C.c_char_p
         L.b2tex_device_ptr.restype = C.c_uint64
         L.b2tex_stream.restype = C.c_uint64
+        L.b2tex_launch_count.restype = C.c_uint64
+        L.b2tex_peer_block.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -195,6 +197,11 @@ class Context:
     def set_face_range(self, begin, end):
         _check(lib().b2tex_set_face_range(self._h, C.c_uint32(begin), C.c_uint32(end)))
 
+    @staticmethod
+    def launch_count() -> int:
+        """kernels of libb2tex.so launched by this process so far"""
+        return int(lib().b2tex_launch_count())
+
     def synchronize(self):
         _check(lib().b2tex_device_synchronize(self._h))
 
@@ -221,8 +228,8 @@ class Context:
         _check(lib().b2tex_data_costs_run(self._h, C.byref(st), C.byref(info)))
         return info
 
-    def data_costs_qualities(self, data_term=1, visibility=True):
-        st = B2Settings(data_term, 0, 1 if visibility else 0)
+    def data_costs_qualities(self, data_term=1, visibility=True, outlier_removal=0):
+        st = B2Settings(data_term, outlier_removal, 1 if visibility else 0)
         info = B2DcInfo()
         _check(lib().b2tex_data_costs_qualities(self._h, C.byref(st), C.byref(info)))
         return info
@@ -255,6 +262,22 @@ class Context:
         trace = np.full(p.max_iterations + 1, np.nan)
         _check(lib().b2tex_view_selection_run(self._h, C.byref(p), C.byref(info), _p(trace)))
         return info, trace[:info.iterations + 1].copy()
+
+    # multi-GPU view selection (csrc/mrf.cu): peer-visible label block; handles are exchanged by the caller
+    def mrf_mg_export(self, rank, num_ranks) -> bytes:
+        h = C.create_string_buffer(64)
+        _check(lib().b2tex_mrf_mg_export(self._h, C.c_uint32(rank), C.c_uint32(num_ranks), h))
+        return h.raw
+
+    def mrf_mg_import(self, peer_rank, handle: bytes):
+        _check(lib().b2tex_mrf_mg_import(self._h, C.c_uint32(peer_rank), C.c_char_p(handle)))
+
+    def peer_block(self, which) -> int:
+        """raw device pointer of the own peer block (0 = view selection, 1 = seam solve) for same-process peers"""
+        return int(lib().b2tex_peer_block(self._h, C.c_int(which)))
+
+    def peer_attach(self, which, peer_rank, ptr):
+        _check(lib().b2tex_peer_attach(self._h, C.c_int(which), C.c_uint32(peer_rank), C.c_uint64(ptr)))
 
     def mrf_init(self, **kw):
         p = mrf_params(**kw)

@@ -5,7 +5,12 @@
 
 #include "common.cuh"
 
+#include <atomic>
+#include <mutex>
+
 namespace b2 {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static thread_local char g_err[1024] = "";
 void set_error(const char *fmt, ...)
 {
@@ -65,11 +70,13 @@ void b2tex_destroy(b2tex_ctx *c)
     cudaStreamSynchronize(c->stream);
     patches_free(c);
     seam_mg_free(c);
+    mrf_mg_free(c);
     if (c->mrf_host_flags) cudaFreeHost(c->mrf_host_flags);
     cudaStreamDestroy(c->stream);
     delete c;
 }
 
+uint64_t b2tex_launch_count(void) { return (uint64_t)b2::g_launches.load(); }
 uint64_t b2tex_stream(b2tex_ctx *c) { return (uint64_t)(uintptr_t)c->stream; }
 
 int b2tex_profile(b2tex_ctx *c, int enable)
@@ -271,6 +278,28 @@ int b2tex_mrf_sample_forest(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t,
     return mrf_sample_only(c, p, t, level);
 }
 
+int b2tex_mrf_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t num_ranks, void *ipc_handle_64_bytes)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return mrf_mg_export(c, rank, num_ranks, ipc_handle_64_bytes);
+}
+int b2tex_mrf_mg_import(b2tex_ctx *c, uint32_t peer_rank, const void *ipc_handle_64_bytes)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    return mrf_mg_import(c, peer_rank, ipc_handle_64_bytes);
+}
+
+uint64_t b2tex_peer_block(b2tex_ctx *c, int which)
+{
+    return (uint64_t)(uintptr_t)(which == 0 ? mrf_mg_block(c) : seam_mg_block(c));
+}
+int b2tex_peer_attach(b2tex_ctx *c, int which, uint32_t peer_rank, uint64_t peer_block_device_ptr)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    void *p = (void *)(uintptr_t)peer_block_device_ptr;
+    return which == 0 ? mrf_mg_attach(c, peer_rank, p) : seam_mg_attach(c, peer_rank, p);
+}
+
 int b2tex_view_selection_run(b2tex_ctx *c, const b2tex_mrf_params *params, b2tex_mrf_info *info, double *trace)
 {
     B2_CUDA(cudaSetDevice(c->device));
@@ -391,6 +420,50 @@ uint64_t b2tex_device_ptr(b2tex_ctx *c, const char *name, uint64_t *n)
 }
 
 // ---- one-shot host-buffer entry points ---------------------------------------------------------
+// A one-shot call needs a context: a stream plus some sixty device buffers (3 GB at C3).  Creating and destroying them
+// per call costs more than the kernels (cudaMalloc / cudaFree serialise the device), so finished one-shot calls park
+// their context here (buffers are grow-only and every stage re-derives its state from the set_* calls) and the next
+// call on the same device picks it up.  b2tex_release_cached_contexts() frees them.
+static std::mutex g_pool_mu;
+static std::vector<b2tex_ctx *> g_pool;
+constexpr size_t POOL_MAX = 2;
+
+static int acquire_ctx(b2tex_ctx **out)
+{
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;   // the calling thread's current device, like any runtime-API call
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i]->device == device) {
+                b2tex_ctx *c = g_pool[i];
+                g_pool.erase(g_pool.begin() + (long)i);
+                c->have_costs = c->have_labels = c->have_adj = c->have_rings = c->mrf_ready = c->have_seam = false;
+                c->images_prepared = false; c->prepared_data_term = -1; c->bvh_built = false;
+                c->Vn = c->F = c->K = 0; c->face_begin = c->face_end = 0; c->nnz = 0; c->R = 0;
+                *out = c;
+                return B2TEX_OK;
+            }
+    }
+    return b2tex_create(device, out);
+}
+
+static void release_ctx(b2tex_ctx *c, int rc)
+{
+    if (!c) return;
+    if (rc == B2TEX_OK && cudaStreamSynchronize(c->stream) == cudaSuccess && !c->profile) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool.size() < POOL_MAX) { g_pool.push_back(c); return; }
+    }
+    b2tex_destroy(c);   // failed calls never hand their context on
+}
+
+void b2tex_release_cached_contexts(void)
+{
+    std::vector<b2tex_ctx *> v;
+    { std::lock_guard<std::mutex> lk(g_pool_mu); v.swap(g_pool); }
+    for (b2tex_ctx *c : v) b2tex_destroy(c);
+}
 
 static int dc_oneshot(const float *verts, uint32_t nv, const uint32_t *faces, const float *normals, uint32_t nf,
                       const b2tex_view *views, uint32_t K, const b2tex_settings *st, b2tex_dc_info *info,
@@ -398,11 +471,11 @@ static int dc_oneshot(const float *verts, uint32_t nv, const uint32_t *faces, co
 {
     if (K > 65535u) { set_error("Exeeded maximal number of views"); return B2TEX_ERR_LIMITS; }
     b2tex_ctx *c = nullptr;
-    B2_TRY(b2tex_create(0, &c));
+    B2_TRY(acquire_ctx(&c));
     int rc = b2tex_set_mesh(c, verts, nv, faces, normals, nf);
     if (rc == B2TEX_OK) rc = b2tex_set_views(c, views, K);
     if (rc == B2TEX_OK) rc = b2tex_data_costs_run(c, st, info);
-    if (rc != B2TEX_OK) { b2tex_destroy(c); return rc; }
+    if (rc != B2TEX_OK) { release_ctx(c, rc); return rc; }
     *out = c;
     return B2TEX_OK;
 }
@@ -417,7 +490,7 @@ int b2tex_calculate_data_costs(const float *verts, uint32_t nv, const uint32_t *
     *view_out = (uint16_t *)malloc(sizeof(uint16_t) * (info->nnz ? info->nnz : 1));
     *cost_out = (float *)malloc(sizeof(float) * (info->nnz ? info->nnz : 1));
     int rc = b2tex_data_costs_download(c, *face_ptr_out, *view_out, *cost_out, nullptr);
-    b2tex_destroy(c);
+    release_ctx(c, rc);
     return rc;
 }
 
@@ -436,7 +509,7 @@ int b2tex_calculate_data_costs_into(const float *verts, uint32_t nv, const uint3
     } else {
         rc = b2tex_data_costs_download(c, face_ptr, view, cost, nullptr);
     }
-    b2tex_destroy(c);
+    release_ctx(c, rc);
     return rc;
 }
 
@@ -445,7 +518,7 @@ int b2tex_view_selection(uint32_t nf, const uint32_t *adj_ptr, const uint32_t *a
                          uint32_t *labels_out, b2tex_mrf_info *info)
 {
     b2tex_ctx *c = nullptr;
-    B2_TRY(b2tex_create(0, &c));
+    B2_TRY(acquire_ctx(&c));
     c->F = nf; c->face_begin = 0; c->face_end = nf;
     // DataCosts::rows() (= number of views) is not part of the CSR: params->num_views if the caller
     // knows it, otherwise bounded from the content (one host pass over nnz)
@@ -460,7 +533,7 @@ int b2tex_view_selection(uint32_t nf, const uint32_t *adj_ptr, const uint32_t *a
     if (rc == B2TEX_OK) rc = b2tex_set_adjacency(c, adj_ptr, adj_idx);
     if (rc == B2TEX_OK) rc = b2tex_view_selection_run(c, params, info, nullptr);
     if (rc == B2TEX_OK) rc = b2tex_labels_download(c, labels_out);
-    b2tex_destroy(c);
+    release_ctx(c, rc);
     return rc;
 }
 
@@ -470,7 +543,7 @@ int b2tex_global_seam_leveling(const float *verts, uint32_t nv, const uint32_t *
                                uint32_t *row_ptr_out, uint32_t **row_label_out, float **x_out, b2tex_seam_info *info)
 {
     b2tex_ctx *c = nullptr;
-    B2_TRY(b2tex_create(0, &c));
+    B2_TRY(acquire_ctx(&c));
     std::vector<float> dummy_normals(3 * (size_t)nf, 0.0f);
     int rc = b2tex_set_mesh(c, verts, nv, faces, dummy_normals.data(), nf);
     if (rc == B2TEX_OK) rc = b2tex_set_views(c, views, K);
@@ -482,7 +555,7 @@ int b2tex_global_seam_leveling(const float *verts, uint32_t nv, const uint32_t *
         *x_out = (float *)malloc(sizeof(float) * 3 * (info->num_rows ? info->num_rows : 1));
         rc = b2tex_seam_download(c, row_ptr_out, *row_label_out, *x_out, nullptr);
     }
-    b2tex_destroy(c);
+    release_ctx(c, rc);
     return rc;
 }
 
@@ -494,7 +567,7 @@ int b2tex_seam_leveling_patches(const float *verts, uint32_t nv, const uint32_t 
 {
     if (K > 65535u) { set_error("Exeeded maximal number of views"); return B2TEX_ERR_LIMITS; }
     b2tex_ctx *c = nullptr;
-    B2_TRY(b2tex_create(0, &c));
+    B2_TRY(acquire_ctx(&c));
     b2tex_patch_info pl; b2tex_seam_info sl; b2tex_local_seam_info ll;
     if (!pi) pi = &pl;
     if (!si) si = &sl;
@@ -522,7 +595,7 @@ int b2tex_seam_leveling_patches(const float *verts, uint32_t nv, const uint32_t 
             *desc_out = nullptr; *faces_out = nullptr; *texcoords_out = nullptr; *images_out = nullptr; *validity_out = nullptr;
         }
     }
-    b2tex_destroy(c);
+    release_ctx(c, rc);
     return rc;
 }
 
@@ -535,7 +608,7 @@ int b2tex_texture_hot_path(const float *verts, uint32_t nv, const uint32_t *face
 {
     if (K > 65535u) { set_error("Exeeded maximal number of views"); return B2TEX_ERR_LIMITS; }
     b2tex_ctx *c = nullptr;
-    B2_TRY(b2tex_create(0, &c));
+    B2_TRY(acquire_ctx(&c));
     b2tex_dc_info dc_local; b2tex_mrf_info mrf_local; b2tex_seam_info seam_local;
     if (!dci) dci = &dc_local;
     if (!mi) mi = &mrf_local;
@@ -553,7 +626,7 @@ int b2tex_texture_hot_path(const float *verts, uint32_t nv, const uint32_t *face
         *x_out = (float *)malloc(sizeof(float) * 3 * (si->num_rows ? si->num_rows : 1));
         rc = b2tex_seam_download(c, row_ptr_out, *row_label_out, *x_out, nullptr);
     }
-    b2tex_destroy(c);
+    release_ctx(c, rc);
     return rc;
 }
 

@@ -219,8 +219,8 @@ int build_bvh(b2tex_ctx *c, bool force)
     DevBuf<uint64_t> &keys_in = c->s_keys_in, &keys_out = c->s_keys_out;
     DevBuf<int> &parent_internal = c->s_parent_internal, &parent_leaf = c->s_parent_leaf;
     B2_TRY(bnd.alloc(8));
-    k_bounds_init<<<1, 32, 0, s>>>(bnd.p);
-    k_bounds<<<std::max(1, c->num_sms * 4), 256, 0, s>>>(c->verts.p, c->Vn, bnd.p);
+    B2_LAUNCH k_bounds_init<<<1, 32, 0, s>>>(bnd.p);
+    B2_LAUNCH k_bounds<<<std::max(1, c->num_sms * 4), 256, 0, s>>>(c->verts.p, c->Vn, bnd.p);
     B2_KERNEL_CHECK();
     uint32_t hb[6];
     B2_CUDA(cudaMemcpyAsync(hb, bnd.p, sizeof(hb), cudaMemcpyDeviceToHost, s));
@@ -237,17 +237,17 @@ int build_bvh(b2tex_ctx *c, bool force)
         DevBuf<uint32_t> &vi_in = c->s_vi_in;
         B2_TRY(vk_in.alloc(nv)); B2_TRY(vk_out.alloc(nv)); B2_TRY(vi_in.alloc(nv));
         B2_TRY(c->vorder.alloc(nv)); B2_TRY(c->vrank.alloc(nv));
-        k_morton_verts<<<(nv + 255) / 256, 256, 0, s>>>(c->verts.p, nv, bnd.p, vk_in.p, vi_in.p);
+        B2_LAUNCH k_morton_verts<<<(nv + 255) / 256, 256, 0, s>>>(c->verts.p, nv, bnd.p, vk_in.p, vi_in.p);
         size_t vb = 0;
         B2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, vb, vk_in.p, vk_out.p, vi_in.p, c->vorder.p, (int)nv, 0, 63, s));
         B2_TRY(c->cub_tmp.alloc(vb));
         B2_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, vb, vk_in.p, vk_out.p, vi_in.p, c->vorder.p, (int)nv, 0, 63, s));
-        k_invert_perm<<<(nv + 255) / 256, 256, 0, s>>>(c->vorder.p, nv, c->vrank.p);
+        B2_LAUNCH k_invert_perm<<<(nv + 255) / 256, 256, 0, s>>>(c->vorder.p, nv, c->vrank.p);
         B2_KERNEL_CHECK();
     }
     B2_TRY(keys_in.alloc(n)); B2_TRY(keys_out.alloc(n));
     B2_TRY(ids_in.alloc(n)); B2_TRY(ids_out.alloc(n));
-    k_morton<<<(n + 255) / 256, 256, 0, s>>>(c->verts.p, c->faces.p, n, bnd.p, keys_in.p, ids_in.p);
+    B2_LAUNCH k_morton<<<(n + 255) / 256, 256, 0, s>>>(c->verts.p, c->faces.p, n, bnd.p, keys_in.p, ids_in.p);
     B2_KERNEL_CHECK();
     size_t tmp_bytes = 0;
     B2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, keys_out.p, ids_in.p, ids_out.p,
@@ -256,15 +256,15 @@ int build_bvh(b2tex_ctx *c, bool force)
     B2_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, keys_in.p, keys_out.p, ids_in.p,
                                             ids_out.p, (int)n, 0, 63, s));
     B2_TRY(c->bvh.tri.alloc(9 * (size_t)n));
-    k_gather_tris<<<(n + 255) / 256, 256, 0, s>>>(c->verts.p, c->faces.p, ids_out.p, n, c->bvh.tri.p);
+    B2_LAUNCH k_gather_tris<<<(n + 255) / 256, 256, 0, s>>>(c->verts.p, c->faces.p, ids_out.p, n, c->bvh.tri.p);
     B2_KERNEL_CHECK();
     if (n >= 2) {
         B2_TRY(c->bvh.nodes.alloc(n - 1));
         B2_TRY(parent_internal.alloc(n)); B2_TRY(parent_leaf.alloc(n));
         B2_TRY(counters.alloc(n)); B2_TRY(counters.zero(s));
-        k_hierarchy<<<(n - 1 + 255) / 256, 256, 0, s>>>(keys_out.p, (int)n, c->bvh.nodes.p, parent_internal.p,
+        B2_LAUNCH k_hierarchy<<<(n - 1 + 255) / 256, 256, 0, s>>>(keys_out.p, (int)n, c->bvh.nodes.p, parent_internal.p,
                                                         parent_leaf.p);
-        k_refit<<<(n + 255) / 256, 256, 0, s>>>(c->bvh.nodes.p, parent_internal.p, parent_leaf.p, c->bvh.tri.p,
+        B2_LAUNCH k_refit<<<(n + 255) / 256, 256, 0, s>>>(c->bvh.nodes.p, parent_internal.p, parent_leaf.p, c->bvh.tri.p,
                                                 (int)n, pad, counters.p, nullptr);
         B2_KERNEL_CHECK();
     }

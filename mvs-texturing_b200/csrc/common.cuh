@@ -12,6 +12,9 @@
 namespace b2 {
 
 void set_error(const char *fmt, ...);
+// every launch of one of this library's kernels is counted (process wide): `B2_LAUNCH kernel<<<...>>>(...)`
+void count_launch();
+#define B2_LAUNCH b2::count_launch(),
 
 #define B2_CUDA(expr)                                                                         \
     do {                                                                                      \
@@ -35,20 +38,29 @@ struct DevBuf {
     T *p = nullptr;
     size_t n = 0;    // elements in use
     size_t cap = 0;  // elements allocated
+    bool borrowed = false;  // p points into memory somebody else owns (a peer-visible block): never freed, never grown
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p && !borrowed) cudaFree(p);
         p = nullptr;
         n = cap = 0;
+        borrowed = false;
+    }
+    // use `count` elements at `ptr` (owned by the caller) as this buffer
+    void borrow(T *ptr, size_t count)
+    {
+        release();
+        p = ptr; n = cap = count; borrowed = true;
     }
     // grow-only allocation; contents are NOT preserved
     int alloc(size_t count)
     {
         if (count > cap) {
+            if (borrowed) { set_error("a peer-mapped buffer cannot grow (%zu > %zu elements)", count, cap); return B2TEX_ERR_ARG; }
             if (p) cudaFree(p);
             p = nullptr;
             cap = 0;
@@ -121,6 +133,7 @@ struct KTimer {
 
 namespace b2 { struct PatchState; }  // texture patches (patches.cu)
 namespace b2 { struct MgState; }     // multi-GPU seam solve (seam_mg.cu)
+namespace b2 { struct MrfMgState; }  // multi-GPU view selection: peer-visible labels + energy slots (mrf.cu)
 
 // The opaque C-ABI context.
 struct b2tex_ctx {
@@ -188,6 +201,7 @@ struct b2tex_ctx {
     b2::DevBuf<uint2> mrf_tjoin;            // per node (tree, arrival number)
     b2::DevBuf<uint4> mrf_ttab;             // per tree (nodes, labels, first order index, flags)
     b2::DevBuf<unsigned long long> mrf_energy;   // [max_iterations + 2] fixed-point energies
+    b2::DevBuf<unsigned long long> mrf_dbg;      // phase timers of k_forest (diagnostic)
     uint32_t mrf_mask_words = 0;
     uint32_t mrf_tree_smem = 0;
     b2::DevBuf<uint4> mrf_adj4;        // compact degree<=3 adjacency
@@ -218,6 +232,8 @@ struct b2tex_ctx {
     b2::PatchState *patches = nullptr;
     // peer-memory blocks of the multi-GPU seam solve (seam_mg.cu)
     b2::MgState *seam_mg = nullptr;
+    // peer-memory block of the multi-GPU view selection (mrf.cu): c->labels lives inside it while it exists
+    b2::MrfMgState *mrf_mg = nullptr;
 };
 
 namespace b2 {
@@ -256,6 +272,13 @@ int seam_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t nranks, void *handle64)
 int seam_mg_import(b2tex_ctx *c, uint32_t peer_rank, const void *handle64);
 int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info);
 void seam_mg_free(b2tex_ctx *c);
+int mrf_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t nranks, void *handle64);
+int mrf_mg_import(b2tex_ctx *c, uint32_t peer_rank, const void *handle64);
+void mrf_mg_free(b2tex_ctx *c);
+int mrf_mg_attach(b2tex_ctx *c, uint32_t peer_rank, void *peer_block);
+void *mrf_mg_block(b2tex_ctx *c);
+int seam_mg_attach(b2tex_ctx *c, uint32_t peer_rank, void *peer_block);
+void *seam_mg_block(b2tex_ctx *c);
 int patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info);
 int patches_download(b2tex_ctx *c, int32_t *desc, uint32_t *faces, float *texcoords, float *images, uint8_t *validity,
                      uint8_t *blending);

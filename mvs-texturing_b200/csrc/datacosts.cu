@@ -616,7 +616,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     const double mesh_bytes = 24.0 * nf + 12.0 * c->Vn;
     if (nf) {
         ScopedTimer tm(c, "k_cull<count>", mesh_bytes + 8.0 * nf);
-        k_cull<false><<<blocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->normals.p, c->views_dev.p, K, fb, fe,
+        B2_LAUNCH k_cull<false><<<blocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->normals.p, c->views_dev.p, K, fb, fe,
                                              cos_thr, cnt.p, nullptr, nullptr, nullptr, nullptr, vwords, nullptr, c->s_pass_bits.p, kwords);
     }
     B2_KERNEL_CHECK();
@@ -636,7 +636,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     }
     if (nf) {
         ScopedTimer tm(c, "k_cull<fill>", mesh_bytes + 6.0 * (double)num_cand);
-        k_cull<true><<<blocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->normals.p, c->views_dev.p, K, fb, fe,
+        B2_LAUNCH k_cull<true><<<blocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->normals.p, c->views_dev.p, K, fb, fe,
                                             cos_thr, nullptr, c->cand_ptr.p, c->cand_view.p, c->cand_face.p,
                                             vis ? c->need_bits.p : nullptr, vwords, c->vrank.p, c->s_pass_bits.p, kwords);
     }
@@ -646,7 +646,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
         size_t warps = (size_t)K * vwords;
         size_t rblocks = (warps * 32 + 255) / 256;
         ScopedTimer tm(c, "k_rays", 8.0 * (double)warps + 12.0 * c->Vn);
-        k_rays<<<(unsigned)rblocks, 256, 0, s>>>(c->verts.p, c->Vn, c->views_dev.p, K, c->need_bits.p, c->occ_bits.p,
+        B2_LAUNCH k_rays<<<(unsigned)rblocks, 256, 0, s>>>(c->verts.p, c->Vn, c->views_dev.p, K, c->need_bits.p, c->occ_bits.p,
                                                  vwords, c->vorder.p, c->bvh.nodes.p, c->bvh.tri.p, c->bvh.num_tris,
                                                  ray_count);
         B2_KERNEL_CHECK();
@@ -654,7 +654,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     if (num_cand) {
         size_t qblocks = (num_cand + 255) / 256;
         ScopedTimer tm(c, "k_quality", 10.0 * (double)num_cand + mesh_bytes);
-        k_quality<<<(unsigned)qblocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->views_dev.p, c->cand_view.p,
+        B2_LAUNCH k_quality<<<(unsigned)qblocks, 256, 0, s>>>(c->verts.p, c->faces.p, c->views_dev.p, c->cand_view.p,
                                                     c->cand_face.p, num_cand, vis ? c->occ_bits.p : nullptr, vwords,
                                                     c->vrank.p,
                                                     st->data_term, c->cand_q.p, c->scalars.p,
@@ -663,13 +663,13 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     }
     if (outlier && nf) {
         ScopedTimer tm(c, "k_outlier", 16.0 * (double)num_cand);
-        k_outlier<<<(nf + 127) / 128, 128, 0, s>>>(c->cand_ptr.p, c->cand_q.p, c->cand_ycc.p, c->cand_flag.p, fb, fe,
+        B2_LAUNCH k_outlier<<<(nf + 127) / 128, 128, 0, s>>>(c->cand_ptr.p, c->cand_q.p, c->cand_ycc.p, c->cand_flag.p, fb, fe,
                                                    st->outlier_removal, c->scalars.p);
         B2_KERNEL_CHECK();
     }
     {
         ScopedTimer tm(c, "k_count_survivors", 4.0 * (double)num_cand + 16.0 * F);
-        k_count_survivors<<<(F + 1 + 255) / 256, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, fb, fe, F, cnt.p);
+        B2_LAUNCH k_count_survivors<<<(F + 1 + 255) / 256, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, fb, fe, F, cnt.p);
     }
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u64(c, cnt.p, c->dc_ptr.p, (size_t)F + 1));
@@ -686,7 +686,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     B2_TRY(c->dc_cost.alloc(nnz));
     if (nf) {
         ScopedTimer tm(c, "k_compact", 6.0 * (double)num_cand + 6.0 * (double)nnz + 16.0 * nf);
-        k_compact<<<blocks, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, c->cand_view.p, c->dc_ptr.p, fb, fe,
+        B2_LAUNCH k_compact<<<blocks, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, c->cand_view.p, c->dc_ptr.p, fb, fe,
                                          c->dc_view.p, c->dc_quality.p);
     }
     B2_KERNEL_CHECK();
@@ -709,7 +709,7 @@ int data_costs_histogram(b2tex_ctx *c, float gmax)
     if (c->nnz) {
         int blocks = std::max(1, c->num_sms * 2);
         ScopedTimer tm(c, "k_histogram", 4.0 * (double)c->nnz);
-        k_histogram<<<blocks, 512, 0, s>>>(c->dc_quality.p, c->nnz, gmax, c->hist.p);
+        B2_LAUNCH k_histogram<<<blocks, 512, 0, s>>>(c->dc_quality.p, c->nnz, gmax, c->hist.p);
         B2_KERNEL_CHECK();
     }
     return B2TEX_OK;
@@ -729,7 +729,7 @@ int data_costs_normalize(b2tex_ctx *c, float gmax, const uint32_t *bins, b2tex_d
     }
     if (c->nnz) {
         ScopedTimer tm(c, "k_normalize", 8.0 * (double)c->nnz);
-        k_normalize<<<(unsigned)((c->nnz + 255) / 256), 256, 0, c->stream>>>(c->dc_quality.p, c->nnz, percentile,
+        B2_LAUNCH k_normalize<<<(unsigned)((c->nnz + 255) / 256), 256, 0, c->stream>>>(c->dc_quality.p, c->nnz, percentile,
                                                                             c->dc_cost.p);
         B2_KERNEL_CHECK();
     }

@@ -242,13 +242,13 @@ int prepare_images(b2tex_ctx *c, int data_term, bool force)
         if (uniform && K <= 65535u && !scalar_sobel) {  // one launch for all views (blockIdx.z = view)
             int w = c->views_host[0].width, h = c->views_host[0].height;
             dim3 grid((w + TW2 - 1) / TW2, (h + TH2 - 1) / TH2, K);
-            k_lum_sobel_vec<<<grid, 256, 0, s>>>(c->rgb.p, c->grad.p, w, h, (size_t)w * h, c->rgb.p,
+            B2_LAUNCH k_lum_sobel_vec<<<grid, 256, 0, s>>>(c->rgb.p, c->grad.p, w, h, (size_t)w * h, c->rgb.p,
                                                  c->rgb.p + c->rgb.n);
         } else {
             for (uint32_t v = 0; v < K; ++v) {
                 int w = c->views_host[v].width, h = c->views_host[v].height;
                 dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH);
-                k_lum_sobel<<<grid, 256, 0, s>>>(c->rgb.p + 3 * c->img_off[v], c->grad.p + c->img_off[v], w, h);
+                B2_LAUNCH k_lum_sobel<<<grid, 256, 0, s>>>(c->rgb.p + 3 * c->img_off[v], c->grad.p + c->img_off[v], w, h);
             }
         }
         B2_KERNEL_CHECK();
@@ -269,7 +269,7 @@ int prepare_images(b2tex_ctx *c, int data_term, bool force)
     }
     B2_TRY(c->views_dev.upload(vd.data(), K, s));
     B2_TRY(c->scalars.alloc(std::max<size_t>(K + 64, 256)));
-    k_corner_check<<<(K + 127) / 128, 128, 0, s>>>(c->views_dev.p, (int)K, c->scalars.p + 64);
+    B2_LAUNCH k_corner_check<<<(K + 127) / 128, 128, 0, s>>>(c->views_dev.p, (int)K, c->scalars.p + 64);
     B2_KERNEL_CHECK();
     std::vector<uint32_t> flags(K);
     B2_CUDA(cudaMemcpyAsync(flags.data(), c->scalars.p + 64, K * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -289,11 +289,11 @@ int prepare_images(b2tex_ctx *c, int data_term, bool force)
             int w = c->views_host[v].width, h = c->views_host[v].height;
             const uint8_t *rgb = c->rgb.p + 3 * c->img_off[v];
             B2_CUDA(cudaMemsetAsync(inv.p, 0, (size_t)w * h, s));
-            k_flood_seed<<<1, 32, 0, s>>>(rgb, inv.p, w, h);
+            B2_LAUNCH k_flood_seed<<<1, 32, 0, s>>>(rgb, inv.p, w, h);
             dim3 fgrid((w + 31) / 32, (h + 31) / 32);
             for (int it = 0; it < 100000; ++it) {
                 B2_CUDA(cudaMemsetAsync(c->scalars.p, 0, sizeof(uint32_t), s));
-                k_flood<<<fgrid, 256, 0, s>>>(rgb, inv.p, w, h, c->scalars.p);
+                B2_LAUNCH k_flood<<<fgrid, 256, 0, s>>>(rgb, inv.p, w, h, c->scalars.p);
                 uint32_t changed = 0;
                 B2_CUDA(cudaMemcpyAsync(&changed, c->scalars.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
                 B2_CUDA(cudaStreamSynchronize(s));
@@ -302,10 +302,10 @@ int prepare_images(b2tex_ctx *c, int data_term, bool force)
             dim3 b(32, 8), g((w + 31) / 32, (h + 7) / 8);
             const uint8_t *src = inv.p;
             if (data_term == 1) {
-                k_erode<<<g, b, 0, s>>>(inv.p, er.p, w, h);
+                B2_LAUNCH k_erode<<<g, b, 0, s>>>(inv.p, er.p, w, h);
                 src = er.p;
             }
-            k_valid4<<<g, b, 0, s>>>(src, c->valid4.p + c->img_off[v], w, h);
+            B2_LAUNCH k_valid4<<<g, b, 0, s>>>(src, c->valid4.p + c->img_off[v], w, h);
             B2_KERNEL_CHECK();
             vd[v].valid4 = c->valid4.p + c->img_off[v];
         }

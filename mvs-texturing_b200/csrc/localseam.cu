@@ -511,22 +511,22 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
     B2_TRY(ps.layer.alloc(P));
     const unsigned pb = (unsigned)((P + 255) / 256);
     if (P) B2_CUDA(cudaMemcpyAsync(ps.orig.p, ps.img.p, 3 * P * sizeof(float), cudaMemcpyDeviceToDevice, s));   // :181 duplicate()
-    if (S) k_edge_colors<<<(S + 255) / 256, 256, 0, s>>>(S, d_sample_edge.p, d_edge_info.p, d_proj.p, ps.edge_proj.p, ps.desc.p, ps.pix_off.p,
+    if (S) B2_LAUNCH k_edge_colors<<<(S + 255) / 256, 256, 0, s>>>(S, d_sample_edge.p, d_edge_info.p, d_proj.p, ps.edge_proj.p, ps.desc.p, ps.pix_off.p,
                                                          ps.img.p, ps.edge_color.p);
-    if (NV) k_vertex_colors<<<(NV + 255) / 256, 256, 0, s>>>(NV, d_vert_info.p, d_vproj.p, ps.vert_proj.p, ps.desc.p, ps.pix_off.p, ps.img.p,
+    if (NV) B2_LAUNCH k_vertex_colors<<<(NV + 255) / 256, 256, 0, s>>>(NV, d_vert_info.p, d_vproj.p, ps.vert_proj.p, ps.desc.p, ps.pix_off.p, ps.img.p,
                                                              ps.vert_color.p);
     B2_KERNEL_CHECK();
     if (P) {
         B2_CUDA(cudaMemsetAsync(ps.key.p, 0, P * sizeof(uint32_t), s));
-        if (NVP + NL) k_stamp_keys<<<(NVP + NL + 255) / 256, 256, 0, s>>>(NVP, NL, d_vproj.p, ps.vert_proj.p, d_proj.p, ps.edge_proj.p, ps.desc.p,
+        if (NVP + NL) B2_LAUNCH k_stamp_keys<<<(NVP + NL + 255) / 256, 256, 0, s>>>(NVP, NL, d_vproj.p, ps.vert_proj.p, d_proj.p, ps.edge_proj.p, ps.desc.p,
                                                                          ps.pix_off.p, ps.key.p);
-        k_stamp_apply<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.key.p, d_vproj.p + NVP, ps.vert_color.p, d_proj.p + NL, ps.edge_proj.p,
+        B2_LAUNCH k_stamp_apply<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.key.p, d_vproj.p + NVP, ps.vert_color.p, d_proj.p + NL, ps.edge_proj.p,
                                          d_edge_info.p, ps.edge_color.p, ps.img.p, ps.blend.p);
         // ---- blending mask ----
-        k_layer_init<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.valid.p, ps.layer.p);
-        for (int it = 1; it <= STRIP_SIZE; ++it) k_layer_step<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.valid.p, ps.layer.p, it);
-        k_sanitize<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.blend.p);
-        k_mask_final<<<pb, 256, 0, s>>>(P, ps.valid.p, ps.layer.p, ps.blend.p);
+        B2_LAUNCH k_layer_init<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.valid.p, ps.layer.p);
+        for (int it = 1; it <= STRIP_SIZE; ++it) B2_LAUNCH k_layer_step<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.valid.p, ps.layer.p, it);
+        B2_LAUNCH k_sanitize<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.blend.p);
+        B2_LAUNCH k_mask_final<<<pb, 256, 0, s>>>(P, ps.valid.p, ps.layer.p, ps.blend.p);
         B2_KERNEL_CHECK();
     }
     // ---- Poisson blending ----
@@ -536,7 +536,7 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
         B2_TRY(ps.uflag.alloc(P + 1));
         B2_TRY(ps.uidx.alloc(P + 1));
         B2_CUDA(cudaMemsetAsync(ps.uflag.p + P, 0, sizeof(uint32_t), s));
-        k_unknowns<<<pb, 256, 0, s>>>(P, ps.blend.p, ps.uflag.p);
+        B2_LAUNCH k_unknowns<<<pb, 256, 0, s>>>(P, ps.blend.p, ps.uflag.p);
         B2_TRY(cub_exclusive_sum_u32(c, ps.uflag.p, ps.uidx.p, (size_t)P + 1));
         B2_CUDA(cudaMemcpyAsync(&n, ps.uidx.p + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         B2_CUDA(cudaStreamSynchronize(s));
@@ -550,7 +550,7 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
         B2_TRY(ps.cg_p.alloc(n));
         B2_TRY(ps.cg_status.alloc(16));
         B2_TRY(ps.cg_status.zero(s));
-        k_poisson_setup<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.blend.p, ps.uidx.p, ps.img.p, ps.orig.p, n, ps.ulist.p,
+        B2_LAUNCH k_poisson_setup<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.blend.p, ps.uidx.p, ps.img.p, ps.orig.p, n, ps.ulist.p,
                                            unb.p, ps.cg_b.p);
         B2_KERNEL_CHECK();
         int per_sm = 0;
@@ -563,10 +563,11 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
         PoissonCg q{n, unb.p, ps.cg_b.p, ps.cg_x.p, ps.cg_r.p, ps.cg_t.p, ps.cg_p.p, ps.cg_partials.p,
                     ps.cg_status.p, 2000u, 1e-5f};
         void *args[] = {&q};
+        count_launch();
         B2_CUDA(cudaLaunchCooperativeKernel((void *)k_poisson_cg, dim3(grid), dim3(LCG_THREADS), args, 0, s));
         B2_CUDA(cudaMemcpyAsync(st, ps.cg_status.p, sizeof(st), cudaMemcpyDeviceToHost, s));
     }
-    if (P) k_poisson_write<<<pb, 256, 0, s>>>(P, ps.blend.p, ps.uidx.p, ps.orig.p, n ? ps.cg_x.p : nullptr, n, ps.img.p, ps.valid.p);
+    if (P) B2_LAUNCH k_poisson_write<<<pb, 256, 0, s>>>(P, ps.blend.p, ps.uidx.p, ps.orig.p, n ? ps.cg_x.p : nullptr, n, ps.img.p, ps.valid.p);
     B2_KERNEL_CHECK();
     B2_CUDA(cudaStreamSynchronize(s));
     ps.leveled = true;

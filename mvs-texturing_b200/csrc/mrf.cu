@@ -19,8 +19,8 @@
 //              ends at a node whose label is fixed in this iteration), so the whole min-sum DP of a
 //              tree -- bottom-up messages AND top-down assignment -- runs inside ONE warp on data staged
 //              in shared memory: a CTA claims a chunk of trees, packs as many as fit into its shared
-//              memory pool, every warp stages its trees with bulk async copies (cp.async.bulk = TMA,
-//              one copy per node for the cost row and one for the view row, completion on an mbarrier),
+//              memory pool, every warp stages its trees with 16-byte asynchronous copies (cp.async, one commit
+//              group per tree, so the copies of the next tree overlap the DP of the current one),
 //              builds per-node label bitmasks in shared memory (O(1) merge-join of the sorted label
 //              lists by popcount), sweeps the levels up and down with __syncwarp() between levels, and
 //              writes the new labels.  The messages H never exist in global memory: DRAM traffic per
@@ -85,6 +85,7 @@ struct Mrf {
     uint32_t *state;             // per-run state, see ST_*
     uint32_t *queue, *qstamp;    // frontier lists [2][F] and push de-duplication stamps [F]
     unsigned long long *efix;    // [max_iterations + 1] fixed-point energies
+    unsigned long long *dbg;     // optional phase timers of k_forest (B2TEX_FOREST_TIMING), else null
     uint32_t K, mask_words;
     uint32_t part_size, rounds, rdiv, seed, iter;
     uint32_t tree_smem;          // dynamic shared memory of k_tree (bytes)
@@ -104,6 +105,7 @@ constexpr int ST_UNSEEN = 3;    // faces with label 0
 constexpr int ST_FNODES = 4;    // 64-bit: forest nodes summed over the iterations (roofline accounting)
 constexpr int ST_FNNZ = 6;      // 64-bit: labels of forest nodes summed over the iterations
 constexpr int ST_SLOW = 8;      // trees that went through global memory
+constexpr int ST_ERR = 9;       // cross-GPU barrier timeouts (a peer did not arrive)
 constexpr int ST_WORDS = 16;
 
 __device__ __forceinline__ bool same_part(const Mrf &m, uint32_t a, uint32_t b)
@@ -148,30 +150,34 @@ __global__ void __launch_bounds__(256) k_build_adj4(uint32_t F, const uint32_t *
     adj4[v] = r;
 }
 
-// ---- shared-memory / async-copy primitives (sm_90+ PTX; the host emulation replaces this block) ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+// ---- shared-memory / async-copy primitives (the host emulation replaces this block) ----
+// 16-byte asynchronous global -> shared copies (LDGSTS, L2 only: every row is read exactly once), grouped per tree.
+// (A first version staged every row with one cp.async.bulk -- the TMA engine: ~90 descriptor-less bulk copies of
+// ~200 bytes per tree ran at about one copy per 260 cycles per SM and made the kernel 10x slower than these.)
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem) : "memory");
 }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-// generic-proxy accesses to shared memory before / async-proxy (bulk copy) writes after
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes)
+__device__ __forceinline__ unsigned long long global_timer_ns()
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` of this thread's committed groups are still in flight
+__device__ __forceinline__ void cp_async_wait_pending(uint32_t pending)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    while (!done)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    switch (pending) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
 }
 // ---- end of primitives ----
 
@@ -235,6 +241,15 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
     if (__ldcg(m.state + ST_STOP)) return;  // the stop rule fired in an earlier iteration (grid-uniform)
     __shared__ uint32_t s_cnt, s_base, s_warp[FOREST_THREADS / 32];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    unsigned long long t_prev = 0;
+    auto stamp = [&](int slot) {   // diagnostic: nanoseconds per phase, accumulated over the iterations
+        if (m.dbg && tid == 0) {
+            const unsigned long long t = global_timer_ns();
+            if (t_prev) m.dbg[slot] += t - t_prev;
+            t_prev = t;
+        }
+    };
+    stamp(0);
     const uint32_t seed_t = iter_seed(m.seed, m.iter);
     const uint32_t n_own = m.ne - m.nb;
     unsigned long long *maxprio = reinterpret_cast<unsigned long long *>(m.ctl + CTL_MAXPRIO);
@@ -292,6 +307,7 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
         }
     }
     grid.sync();
+    stamp(1);   // round 0
     // Growth rounds on a FRONTIER instead of full scans.  Only an undecided node with >= 1 forest
     // neighbour can change state in a round, and such a node is either newly adjacent to a node that
     // joined in the previous round (pushed by that node) or a candidate that lost and re-queues
@@ -315,6 +331,7 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
         }
     }
     grid.sync();
+    stamp(2);   // frontier seeding
     for (uint32_t r = 1; r <= m.rounds; ++r) {
         const uint32_t n = __ldcg(m.ctl + CTL_QN + r);
         const uint32_t *q = m.queue + (size_t)(r & 1u) * m.F;
@@ -360,6 +377,7 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
         }
         grid.sync();
     }
+    stamp(3);   // growth rounds
     if (!build_trees) return;
 
     // ---- lay the forest out tree by tree: arrival numbers grow with the rounds, so the nodes of a tree are
@@ -389,6 +407,7 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
         __syncthreads();
     }
     grid.sync();
+    stamp(4);   // tree allocation
     unsigned long long fn = 0, fz = 0;
     for (uint32_t v = m.nb + tid; v < m.ne; v += nth) {
         const uint32_t l = __ldcg(m.level + v);
@@ -406,24 +425,23 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
         atomicAdd(reinterpret_cast<unsigned long long *>(m.state + ST_FNODES), fn);
         atomicAdd(reinterpret_cast<unsigned long long *>(m.state + ST_FNNZ), fz);
     }
+    stamp(5);   // scatter (thread 0's share)
 }
 
 // ---- min-sum DP of whole trees inside one warp ---------------------------------------------------------------
 constexpr int TREE_THREADS = 128;
 constexpr int TREE_WARPS = TREE_THREADS / 32;
-constexpr int TREE_CHUNK = 16;       // trees claimed per global atomic
+constexpr int TREE_CHUNK = 16;       // trees claimed per global atomic (<= 8 per warp: cp_async_wait_pending)
 constexpr uint32_t NBR_SKIP = 0u, NBR_CHILD = 1u << 30, NBR_FIXED = 2u << 30, NBR_PARENT = 3u << 30;
 constexpr uint32_t NBR_KIND = 3u << 30, NBR_ARG = ~NBR_KIND;
 
-// upper bound of the shared memory one tree needs (the exact rows are padded to the 16-byte granules of the bulk
+// upper bound of the shared memory one tree needs (the exact rows are padded to the 16-byte granules of the async
 // copies: <= 6 extra floats and <= 14 extra u16 per node)
 __host__ __device__ __forceinline__ uint32_t tree_hcap(uint32_t cnt, uint32_t nnz) { return (nnz + 6u * cnt + 3u) & ~3u; }
 __host__ __device__ __forceinline__ uint32_t tree_vcap(uint32_t cnt, uint32_t nnz) { return (nnz + 14u * cnt + 7u) & ~7u; }
 __host__ __device__ __forceinline__ uint32_t tree_node_bytes(uint32_t W) { return 40u + 6u * W; }
 
 struct TreeStatic {
-    unsigned long long mbar[TREE_CHUNK];
-    uint32_t mphase[TREE_CHUNK];
     uint32_t t_cnt[TREE_CHUNK], t_nnz[TREE_CHUNK], t_start[TREE_CHUNK], t_flags[TREE_CHUNK];
     uint32_t t_node0[TREE_CHUNK], t_h0[TREE_CHUNK], t_v0[TREE_CHUNK], t_slow[TREE_CHUNK];
     uint32_t chunk_first, sb_n, sb_nodes, sb_hcap, sb_vcap;
@@ -506,11 +524,12 @@ __device__ __forceinline__ int row_find(const TreePool &p, uint32_t W, uint32_t 
     return (lo < n && (uint32_t)row[lo] + 1u == lab) ? lo : -1;
 }
 
-// stage one tree: node tables + one bulk copy per node and array; the copies complete on `bar`
+// stage one tree: node tables + asynchronous 16-byte copies of its cost and view rows (one commit group per tree)
 __device__ void tree_stage(const Mrf &m, const TreePool &p, uint32_t start, uint32_t cnt, uint32_t node0, uint32_t h0,
-                           uint32_t v0, unsigned long long *bar, uint32_t lane)
+                           uint32_t v0, uint32_t lane)
 {
-    uint32_t hcarry = h0, vcarry = v0, tx = 0;
+    uint32_t hcarry = h0, vcarry = v0;
+    const uint32_t half = lane >> 4, sl = lane & 15u;   // two rows per step, 16 lanes (= 16 chunks of 16 bytes) each
     for (uint32_t c = 0; c < cnt; c += 32) {
         const uint32_t i = c + lane;
         const bool valid = i < cnt;
@@ -534,10 +553,21 @@ __device__ void tree_stage(const Mrf &m, const TreePool &p, uint32_t start, uint
         const uint32_t ho = hcarry + hi - hsz, vo = vcarry + vi - vsz;
         hcarry += __shfl_sync(0xffffffffu, hi, 31);
         vcarry += __shfl_sync(0xffffffffu, vi, 31);
+        // the rows of this group of <= 32 nodes: 16-byte chunks from the aligned-down start of every row
+        const uint32_t rows = min(32u, cnt - c);
+        const unsigned long long src_c = (unsigned long long)(m.cost + (p0 & ~(uint64_t)3));
+        const unsigned long long src_v = (unsigned long long)(m.view + (p0 & ~(uint64_t)7));
+        for (uint32_t j = 0; j < rows; j += 2) {
+            const uint32_t jj = min(j + half, 31u);
+            const unsigned long long sc = __shfl_sync(0xffffffffu, src_c, jj), sv = __shfl_sync(0xffffffffu, src_v, jj);
+            const uint32_t rho = __shfl_sync(0xffffffffu, ho, jj), rvo = __shfl_sync(0xffffffffu, vo, jj);
+            const uint32_t hch = __shfl_sync(0xffffffffu, hsz, jj) >> 2, vch = __shfl_sync(0xffffffffu, vsz, jj) >> 3;
+            if (j + half < rows) {
+                for (uint32_t q = sl; q < hch; q += 16) cp_async16(p.H + rho + 4u * q, (const float *)sc + 4u * q);
+                for (uint32_t q = sl; q < vch; q += 16) cp_async16(p.V + rvo + 8u * q, (const uint16_t *)sv + 8u * q);
+            }
+        }
         if (valid) {
-            bulk_g2s(p.H + ho, m.cost + (p0 & ~(uint64_t)3), hsz * 4u, bar);
-            bulk_g2s(p.V + vo, m.view + (p0 & ~(uint64_t)7), vsz * 2u, bar);
-            tx += hsz * 4u + vsz * 2u;
             const uint32_t li = node0 + i;
             p.gid[li] = v;
             p.hoff[li] = ho + (uint32_t)(p0 & 3u);
@@ -562,9 +592,7 @@ __device__ void tree_stage(const Mrf &m, const TreePool &p, uint32_t start, uint
             }
         }
     }
-    for (int s = 16; s; s >>= 1) tx += __shfl_xor_sync(0xffffffffu, tx, s);
-    // the only arrival of this phase comes after every copy was issued, so the phase cannot complete early
-    if (lane == 0) mbar_arrive_expect_tx(bar, tx);
+    cp_async_commit();
 }
 
 // the DP of one staged tree: nodes [a, b) of the pool, sorted by level
@@ -750,9 +778,6 @@ __global__ void __launch_bounds__(TREE_THREADS) k_tree(Mrf m)
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t W = m.mask_words;
     const uint32_t nroots = m.ctl[CTL_NROOTS];
-    if (threadIdx.x < TREE_CHUNK) { mbar_init(&ts.mbar[threadIdx.x], 1u); ts.mphase[threadIdx.x] = 0u; }
-    if (threadIdx.x == 0) fence_mbar_init();
-    __syncthreads();
     for (;;) {
         if (threadIdx.x == 0) ts.chunk_first = atomicAdd(&m.ctl[CTL_CLAIM], (uint32_t)TREE_CHUNK);
         __syncthreads();
@@ -788,17 +813,18 @@ __global__ void __launch_bounds__(TREE_THREADS) k_tree(Mrf m)
             __syncthreads();
             const uint32_t sb_n = ts.sb_n;
             const TreePool pool = carve_pool(tree_dyn, ts.sb_nodes, ts.sb_hcap, ts.sb_vcap, W);
-            fence_proxy_async();   // the previous sub-batch's generic accesses to the pool precede the bulk copies
-            // every warp first stages all of its trees (the copies of the later ones overlap the DP of the earlier)
+            // every warp first stages all of its trees (one commit group each; the copies of the later trees overlap the
+            // DP of the earlier ones), then solves them in the same order
+            uint32_t staged = 0;
             for (uint32_t i = done + warp; i < done + sb_n; i += TREE_WARPS)
-                if (!ts.t_slow[i])
-                    tree_stage(m, pool, ts.t_start[i], ts.t_cnt[i], ts.t_node0[i], ts.t_h0[i], ts.t_v0[i], &ts.mbar[i - done], lane);
+                if (!ts.t_slow[i]) {
+                    tree_stage(m, pool, ts.t_start[i], ts.t_cnt[i], ts.t_node0[i], ts.t_h0[i], ts.t_v0[i], lane);
+                    ++staged;
+                }
             for (uint32_t i = done + warp; i < done + sb_n; i += TREE_WARPS) {
                 if (ts.t_slow[i]) { tree_solve_global(m, ts.t_start[i], ts.t_cnt[i], lane); continue; }
-                const uint32_t slot = i - done;
-                mbar_wait(&ts.mbar[slot], ts.mphase[slot]);
+                cp_async_wait_pending(--staged);   // this tree's group and all earlier ones have landed
                 __syncwarp();
-                if (lane == 0) ts.mphase[slot] ^= 1u;
                 tree_solve_smem<G>(m, pool, ts.t_node0[i], ts.t_node0[i] + ts.t_cnt[i], W, lane);
             }
             __syncthreads();
@@ -808,7 +834,7 @@ __global__ void __launch_bounds__(TREE_THREADS) k_tree(Mrf m)
 }
 
 // 32.32 fixed-point energy of the owned nodes: unaries + edges counted by their lower endpoint -> efix[slot]
-__global__ void __launch_bounds__(256) k_energy(Mrf m, uint32_t slot)
+__global__ void __launch_bounds__(256) k_energy(Mrf m, unsigned long long *out)
 {
     if (__ldcg(m.state + ST_STOP)) return;
     unsigned long long e = 0;
@@ -824,7 +850,7 @@ __global__ void __launch_bounds__(256) k_energy(Mrf m, uint32_t slot)
         }
     }
     for (int s = 16; s; s >>= 1) e += __shfl_xor_sync(0xffffffffu, e, s);
-    if ((threadIdx.x & 31) == 0 && e) atomicAdd(m.efix + slot, e);
+    if ((threadIdx.x & 31) == 0 && e) atomicAdd(out, e);
 }
 
 // StopWhenReturnsDiminish(window, ratio) (view_selection.cpp:84), the double arithmetic of oracle/mrf.c
@@ -856,6 +882,137 @@ __global__ void __launch_bounds__(256) k_label_check(Mrf m)
     }
 }
 
+
+// ---- multi-GPU (one process per GPU): boundary-label halo + energy all-reduce through NVLink peer memory -----------
+// Rank r owns the faces [r * part_size, (r + 1) * part_size) and holds a full-length label array inside a block its
+// peers have mapped (cudaIpc).  After every sweep a rank STORES the labels of its boundary faces -- the faces with a
+// neighbour on another rank, O(sqrt(F / P)) per cut (view_selection.cpp:29-42 couples faces only across an edge) --
+// straight into the label arrays of exactly the ranks that own such a neighbour, then all ranks meet at an epoch-flag
+// barrier in peer memory.  The energy for the stop rule goes the same way: every rank stores its fixed-point partial into
+// slot [t][rank] of every peer, meets, and adds the slots in rank order, so all ranks take the identical decision from
+// identical integers without a host round trip or an NCCL call.
+constexpr int MRF_MAX_RANKS = 8;
+constexpr uint32_t MRF_SLOTS = 1026;   // iterations 0 .. max_iterations (<= 1022) + scratch
+struct MrfPeers {
+    uint32_t rank, nranks;
+    uint32_t *labels[MRF_MAX_RANKS];            // every rank's full-length label array
+    unsigned long long *eslot[MRF_MAX_RANKS];   // [MRF_SLOTS][MRF_MAX_RANKS] partial energies, per rank
+    uint32_t *flag[MRF_MAX_RANKS];              // [MRF_MAX_RANKS] barrier epochs, per rank
+    unsigned long long spin_limit;
+};
+__host__ __device__ inline size_t mrf_align256(size_t n) { return (n + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t mrf_block_bytes(uint32_t F)
+{
+    return mrf_align256((size_t)F * 4) + mrf_align256((size_t)MRF_SLOTS * MRF_MAX_RANKS * 8) + 256;
+}
+
+// ---- system-scope flag primitives (the host emulation replaces this block) ----
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// ---- end of flag primitives ----
+
+// boundary faces of the owned range and the ranks each of them has a neighbour on
+__global__ void __launch_bounds__(256) k_halo_build(Mrf m, uint32_t *cnt, uint32_t *list, uint32_t *lmask)
+{
+    const uint32_t v = m.nb + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= m.ne) return;
+    const Nb nb = load_nb(m, v);
+    uint32_t mask = 0;
+    for (uint32_t i = 0; i < nb.deg; ++i) {
+        const uint32_t w = nb_at(m, nb, i);
+        if (!owned(m, w)) mask |= 1u << (w / m.part_size);
+    }
+    if (mask) {
+        const uint32_t i = atomicAdd(cnt, 1u);
+        list[i] = v;
+        lmask[i] = mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_halo_push(Mrf m, MrfPeers pr, const uint32_t *__restrict__ list,
+                                                   const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ cnt)
+{
+    if (__ldcg(m.state + ST_STOP)) return;
+    const uint32_t n = *cnt;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t v = list[i], x = m.labels[v];
+        for (uint32_t mk = lmask[i]; mk; mk &= mk - 1u) {
+            const uint32_t k = (uint32_t)__ffs((int)mk) - 1u;
+            if (k < pr.nranks && k != pr.rank) pr.labels[k][v] = x;
+        }
+    }
+    __threadfence_system();
+}
+
+// after the last iteration: every rank gets every label (the seam assembly that follows is replicated)
+__global__ void __launch_bounds__(256) k_range_push(Mrf m, MrfPeers pr)
+{
+    for (uint32_t v = m.nb + blockIdx.x * blockDim.x + threadIdx.x; v < m.ne; v += gridDim.x * blockDim.x) {
+        const uint32_t x = m.labels[v];
+        for (uint32_t k = 0; k < pr.nranks; ++k)
+            if (k != pr.rank) pr.labels[k][v] = x;
+    }
+    __threadfence_system();
+}
+
+// One warp.  phase 0: all ranks meet (every label pushed before is visible afterwards).  phase 1: additionally the
+// partial energies elocal[t] are all-reduced into m.efix[t] (rank order) and the stop rule of iteration t is applied.
+// phase 2: barrier that also runs after the stop rule has fired (the final label all-gather).
+__global__ void k_mg_sync(Mrf m, MrfPeers pr, uint32_t epoch, int phase, uint32_t t, uint32_t window, float ratio,
+                          uint32_t max_iterations, const unsigned long long *elocal)
+{
+    if (phase != 2 && __ldcg(m.state + ST_STOP)) return;
+    const uint32_t k = threadIdx.x;
+    if (k < pr.nranks) {
+        if (phase == 1) {
+            pr.eslot[k][(size_t)t * MRF_MAX_RANKS + pr.rank] = elocal[t];
+            __threadfence_system();
+        }
+        st_release_sys(pr.flag[k] + pr.rank, epoch);
+        unsigned long long spins = 0;
+        while ((int32_t)(ld_acquire_sys(pr.flag[pr.rank] + k) - epoch) < 0) {
+            __nanosleep(64);
+            if (++spins > pr.spin_limit) { atomicAdd(m.state + ST_ERR, 1u); break; }
+        }
+    }
+    __syncwarp();
+    if (k != 0) return;
+    if (__ldcg(m.state + ST_ERR)) { if (!m.state[ST_STOP]) m.state[ST_STOP] = t ? t : 1u; return; }   // a peer is gone: halt what is queued
+    if (phase != 1) return;
+    unsigned long long sum = 0;
+    for (uint32_t r = 0; r < pr.nranks; ++r) sum += __ldcg(pr.eslot[pr.rank] + (size_t)t * MRF_MAX_RANKS + r);
+    m.efix[t] = sum;
+    if (t == 0) return;
+    m.state[ST_DONE] = t;
+    bool stop = t >= max_iterations;
+    if (t >= window) {
+        const double e0 = (double)(long long)m.efix[t - window], e1 = (double)(long long)sum;
+        if (e0 <= 0.0 || (e0 - e1) / e0 < (double)ratio) stop = true;
+    }
+    if (stop) m.state[ST_STOP] = t;
+}
+
+}  // namespace
+
+struct MrfMgState {
+    void *block = nullptr;                      // own peer-visible block (cudaMalloc)
+    void *peer[MRF_MAX_RANKS] = {nullptr};      // opened peers (peer[rank] = block)
+    bool opened[MRF_MAX_RANKS] = {false};
+    uint32_t F = 0, rank = 0, nranks = 1, epoch = 0;
+    DevBuf<uint32_t> halo_list, halo_mask, halo_cnt;
+    DevBuf<unsigned long long> elocal;         // [MRF_SLOTS] partial energies of this rank
+};
+
+namespace {
+
 Mrf make_mrf(b2tex_ctx *c, uint32_t iter)
 {
     Mrf m;
@@ -870,6 +1027,7 @@ Mrf make_mrf(b2tex_ctx *c, uint32_t iter)
     m.ctl = c->mrf_ctl.p; m.state = c->mrf_state.p;
     m.queue = c->mrf_queue.p; m.qstamp = c->mrf_queue.p + 2 * (size_t)c->F;
     m.efix = c->mrf_energy.p;
+    m.dbg = c->mrf_dbg.n ? c->mrf_dbg.p : nullptr;
     m.K = c->K;
     m.mask_words = c->mrf_mask_words;
     const b2tex_mrf_params &p = c->mrf_params;
@@ -907,6 +1065,7 @@ int launch_forest(b2tex_ctx *c, Mrf &m, int build_trees)
     if (grid > need) grid = need > 0 ? need : 1;
     B2_CUDA(cudaMemsetAsync(m.ctl, 0, CTL_WORDS * sizeof(uint32_t), s));
     void *args[] = {&m, &build_trees};
+    count_launch();
     B2_CUDA(cudaLaunchCooperativeKernel((void *)k_forest, dim3(grid), dim3(FOREST_THREADS), args, 0, s));
     return B2TEX_OK;
 }
@@ -923,15 +1082,77 @@ int launch_tree(b2tex_ctx *c, Mrf &m)
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree<G>, TREE_THREADS, m.tree_smem));
     if (per_sm < 1) { set_error("k_tree cannot be resident with %u bytes of shared memory", m.tree_smem); return B2TEX_ERR_CUDA; }
     const int grid = c->num_sms * per_sm;
-    k_tree<G><<<grid, TREE_THREADS, m.tree_smem, c->stream>>>(m);
+    B2_LAUNCH k_tree<G><<<grid, TREE_THREADS, m.tree_smem, c->stream>>>(m);
     B2_KERNEL_CHECK();
     return B2TEX_OK;
 }
 
-int enqueue_iteration(b2tex_ctx *c, Mrf &m)
+// peers of this context, or nranks == 1
+MrfPeers make_peers(b2tex_ctx *c)
+{
+    MrfPeers pr;
+    memset(&pr, 0, sizeof(pr));
+    pr.nranks = 1;
+    MrfMgState *g = c->mrf_mg;
+    if (!g || g->nranks < 2) return pr;
+    pr.rank = g->rank; pr.nranks = g->nranks;
+    for (uint32_t k = 0; k < g->nranks; ++k) {
+        char *b = (char *)g->peer[k];
+        pr.labels[k] = (uint32_t *)b;
+        pr.eslot[k] = (unsigned long long *)(b + mrf_align256((size_t)g->F * 4));
+        pr.flag[k] = (uint32_t *)(b + mrf_align256((size_t)g->F * 4) + mrf_align256((size_t)MRF_SLOTS * MRF_MAX_RANKS * 8));
+    }
+    pr.spin_limit = 40ull * 1000 * 1000;   // x (64 ns sleep + a system-scope load): several seconds
+    return pr;
+}
+bool mg_active(b2tex_ctx *c) { return c->mrf_mg && c->mrf_mg->nranks > 1; }
+// epoch of the barrier of iteration t (0 = init), phase 0 (labels) / 1 (energy); 1 = entry barrier of the run
+uint32_t mg_epoch(b2tex_ctx *c, uint32_t t, int phase) { return c->mrf_mg->epoch + 2u + 2u * t + (uint32_t)phase; }
+
+int launch_energy(b2tex_ctx *c, Mrf &m, uint32_t t)
+{
+    unsigned long long *out = mg_active(c) ? c->mrf_mg->elocal.p + t : m.efix + t;
+    B2_LAUNCH k_energy<<<std::max(1, c->num_sms * 8), 256, 0, c->stream>>>(m, out);
+    B2_KERNEL_CHECK();
+    return B2TEX_OK;
+}
+
+// label halo -> barrier -> partial energies -> barrier + all-reduce + stop rule (multi-GPU), or energy + stop rule
+int enqueue_exchange_and_energy(b2tex_ctx *c, Mrf &m, uint32_t t, bool stop_rule)
 {
     cudaStream_t s = c->stream;
-    if (m.ne <= m.nb) return B2TEX_OK;
+    const b2tex_mrf_params &p = c->mrf_params;
+    const uint32_t window = p.window ? p.window : 1u;
+    if (!mg_active(c)) {
+        {
+            ScopedTimer te(c, "mrf.k_energy", 12.0 * (double)(m.ne - m.nb));
+            B2_TRY(launch_energy(c, m, t));
+        }
+        if (stop_rule) B2_LAUNCH k_stop<<<1, 1, 0, s>>>(m, t, window, p.ratio, p.max_iterations);
+        B2_KERNEL_CHECK();
+        return B2TEX_OK;
+    }
+    MrfMgState *g = c->mrf_mg;
+    MrfPeers pr = make_peers(c);
+    {
+        ScopedTimer th(c, "mrf.halo_exchange");
+        B2_LAUNCH k_halo_push<<<std::max(1, c->num_sms), 256, 0, s>>>(m, pr, g->halo_list.p, g->halo_mask.p, g->halo_cnt.p);
+        B2_LAUNCH k_mg_sync<<<1, 32, 0, s>>>(m, pr, mg_epoch(c, t, 0), 0, t, window, p.ratio, p.max_iterations, g->elocal.p);
+    }
+    {
+        ScopedTimer te(c, "mrf.k_energy", 12.0 * (double)(m.ne - m.nb));
+        B2_TRY(launch_energy(c, m, t));
+    }
+    ScopedTimer ta(c, "mrf.energy_allreduce");
+    B2_LAUNCH k_mg_sync<<<1, 32, 0, s>>>(m, pr, mg_epoch(c, t, 1), 1, t, stop_rule ? window : 0xFFFFFFFFu, p.ratio,
+                                 stop_rule ? p.max_iterations : 0xFFFFFFFFu, g->elocal.p);
+    B2_KERNEL_CHECK();
+    return B2TEX_OK;
+}
+
+int enqueue_iteration(b2tex_ctx *c, Mrf &m, bool stop_rule)
+{
+    if (m.ne <= m.nb && !mg_active(c)) return B2TEX_OK;
     {
         ScopedTimer tf(c, "mrf.k_forest", 20.0 * (double)(m.ne - m.nb));
         B2_TRY(launch_forest(c, m, 1));
@@ -945,10 +1166,7 @@ int enqueue_iteration(b2tex_ctx *c, Mrf &m)
             default: B2_TRY(launch_tree<32>(c, m)); break;
         }
     }
-    ScopedTimer te(c, "mrf.k_energy", 12.0 * (double)(m.ne - m.nb));
-    k_energy<<<std::max(1, c->num_sms * 8), 256, 0, s>>>(m, m.iter);
-    B2_KERNEL_CHECK();
-    return B2TEX_OK;
+    return enqueue_exchange_and_energy(c, m, m.iter, stop_rule);
 }
 
 int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
@@ -956,8 +1174,21 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
     if (!c->have_costs) { set_error("view selection: data costs missing"); return B2TEX_ERR_ARG; }
     if (!c->have_adj) { set_error("view selection: adjacency missing"); return B2TEX_ERR_ARG; }
     if (p->rounds + 2 > (uint32_t)MAX_LEVELS) { set_error("mrf rounds too large"); return B2TEX_ERR_ARG; }
+    if (p->max_iterations + 4 > MRF_SLOTS) { set_error("view selection: at most %u iterations", MRF_SLOTS - 4); return B2TEX_ERR_ARG; }
     c->mrf_params = *p;
     const size_t F = c->F;
+    if (mg_active(c)) {
+        MrfMgState *g = c->mrf_mg;
+        const uint32_t P = g->nranks, psz = (uint32_t)((F + P - 1) / P);
+        if (g->F != F || (p->num_parts ? p->num_parts : 1) != P || c->face_begin != std::min<size_t>(F, (size_t)g->rank * psz) ||
+            c->face_end != std::min<size_t>(F, (size_t)(g->rank + 1) * psz)) {
+            set_error("multi-GPU view selection: the face range must be [rank * ceil(F / P), (rank + 1) * ceil(F / P)) and "
+                      "num_parts = P (F %zu, P %u, range %u..%u, num_parts %u)", F, P, c->face_begin, c->face_end, p->num_parts);
+            return B2TEX_ERR_ARG;
+        }
+        for (uint32_t k = 0; k < P; ++k)
+            if (!g->peer[k]) { set_error("multi-GPU view selection: peer %u not imported", k); return B2TEX_ERR_ARG; }
+    }
     B2_TRY(c->mrf_H.alloc(c->nnz));
     B2_TRY(c->mrf_hminp1.alloc(F));
     B2_TRY(c->mrf_amin.alloc(F));
@@ -974,10 +1205,12 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
     B2_TRY(c->mrf_ctl.alloc(CTL_WORDS));
     B2_TRY(c->mrf_state.alloc(ST_WORDS));
     B2_TRY(c->mrf_state.zero(c->stream));
-    B2_TRY(c->mrf_energy.alloc((size_t)p->max_iterations + 2));
+    B2_TRY(c->mrf_energy.alloc(MRF_SLOTS));
     B2_TRY(c->mrf_energy.zero(c->stream));
+    static const bool forest_timing = getenv("B2TEX_FOREST_TIMING") != nullptr;
+    if (forest_timing) { B2_TRY(c->mrf_dbg.alloc(16)); B2_TRY(c->mrf_dbg.zero(c->stream)); }
     B2_TRY(c->mrf_adj4.alloc(F));
-    if (F) k_build_adj4<<<(unsigned)((F + 255) / 256), 256, 0, c->stream>>>((uint32_t)F, c->adj_ptr.p, c->adj_idx.p, c->mrf_adj4.p);
+    if (F) B2_LAUNCH k_build_adj4<<<(unsigned)((F + 255) / 256), 256, 0, c->stream>>>((uint32_t)F, c->adj_ptr.p, c->adj_idx.p, c->mrf_adj4.p);
     if (!c->have_labels || c->labels.n != F) { B2_TRY(c->labels.alloc(F)); B2_TRY(c->labels.zero(c->stream)); }
     uint32_t nodes = c->face_end - c->face_begin;
     double rho = nodes ? (double)c->nnz / nodes : 0.0;
@@ -1009,50 +1242,66 @@ int read_energy(b2tex_ctx *c, const Mrf &m, uint32_t slot, int64_t *efix)
 
 }  // namespace
 
+// init: arg-min labels of the owned faces, (multi-GPU: boundary labels to the peers,) energy of the initial labeling
 int mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *efix)
 {
     B2_TRY(alloc_mrf(c, p));
     Mrf m = make_mrf(c, 0);
     cudaStream_t s = c->stream;
     const int grid = std::max(1, c->num_sms * 8);
+    if (mg_active(c)) {
+        MrfMgState *g = c->mrf_mg;
+        MrfPeers pr = make_peers(c);
+        B2_TRY(g->elocal.alloc(MRF_SLOTS));
+        B2_TRY(g->elocal.zero(s));
+        const uint32_t n = m.ne - m.nb;
+        B2_TRY(g->halo_list.alloc(n)); B2_TRY(g->halo_mask.alloc(n)); B2_TRY(g->halo_cnt.alloc(1));
+        B2_TRY(g->halo_cnt.zero(s));
+        if (n) B2_LAUNCH k_halo_build<<<(n + 255) / 256, 256, 0, s>>>(m, g->halo_cnt.p, g->halo_list.p, g->halo_mask.p);
+        // entry barrier: every rank is done with the labels of the previous run before anybody overwrites them
+        B2_LAUNCH k_mg_sync<<<1, 32, 0, s>>>(m, pr, g->epoch + 1u, 0, 0u, 1u, 0.0f, 0xFFFFFFFFu, g->elocal.p);
+        B2_KERNEL_CHECK();
+    }
     if (m.ne > m.nb) {
         ScopedTimer tm(c, "mrf_init");
         switch (c->mrf_group) {
-            case 4: k_init_labels<4><<<grid, 256, 0, s>>>(m); break;
-            case 8: k_init_labels<8><<<grid, 256, 0, s>>>(m); break;
-            case 16: k_init_labels<16><<<grid, 256, 0, s>>>(m); break;
-            default: k_init_labels<32><<<grid, 256, 0, s>>>(m); break;
+            case 4: B2_LAUNCH k_init_labels<4><<<grid, 256, 0, s>>>(m); break;
+            case 8: B2_LAUNCH k_init_labels<8><<<grid, 256, 0, s>>>(m); break;
+            case 16: B2_LAUNCH k_init_labels<16><<<grid, 256, 0, s>>>(m); break;
+            default: B2_LAUNCH k_init_labels<32><<<grid, 256, 0, s>>>(m); break;
         }
         B2_KERNEL_CHECK();
     }
     c->have_labels = true;
     c->mrf_ready = true;
-    if (m.ne > m.nb) k_energy<<<grid, 256, 0, s>>>(m, 0u);
-    B2_KERNEL_CHECK();
+    if (m.ne > m.nb || mg_active(c)) B2_TRY(enqueue_exchange_and_energy(c, m, 0u, false));
     return read_energy(c, m, 0u, efix);
 }
 
-// one iteration, energy read back (the building block a host-driven sharded loop uses)
+// one iteration, energy read back (single GPU, or the building block of a host-driven sharded loop over NCCL)
 int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *efix)
 {
     if (!c->mrf_ready) { set_error("mrf_iterate before mrf_init"); return B2TEX_ERR_ARG; }
     if (t == 0 || t > c->mrf_params.max_iterations) { set_error("mrf_iterate: iterations are numbered from 1 to max_iterations"); return B2TEX_ERR_ARG; }
     Mrf m = make_mrf(c, t);
     B2_CUDA(cudaMemsetAsync(m.efix + t, 0, sizeof(unsigned long long), c->stream));
-    B2_TRY(enqueue_iteration(c, m));
+    if (mg_active(c)) B2_CUDA(cudaMemsetAsync(c->mrf_mg->elocal.p + t, 0, sizeof(unsigned long long), c->stream));
+    B2_TRY(enqueue_iteration(c, m, false));
     return read_energy(c, m, t, efix);
 }
 
-// The whole run without a host round trip per iteration: the host queues iterations ahead of the device; k_stop
-// evaluates the stop rule on the device and turns the launches that are already queued behind it into no-ops.
+// The whole run without a host round trip per iteration: the host queues iterations ahead of the device; the stop rule
+// is evaluated on the device and turns the launches that are already queued behind it into no-ops.  With peers attached
+// (mrf_mg_export / mrf_mg_import) every rank runs this same loop; the ranks meet inside the kernels.
 int mrf_run(b2tex_ctx *c, const b2tex_mrf_params *p, b2tex_mrf_info *info, double *trace)
 {
     int64_t e0 = 0;
     B2_TRY(mrf_init(c, p, &e0));
     cudaStream_t s = c->stream;
     const uint32_t max_it = p->max_iterations, window = p->window ? p->window : 1u;
+    const bool mg = mg_active(c);
     info->sweep_bytes = 14ull * c->nnz + 20ull * c->F;
-    if (c->face_end <= c->face_begin) {   // nothing owned: the energy is constant, the stop rule fires at `window`
+    if (c->face_end <= c->face_begin && !mg) {   // nothing owned: the energy is constant, the stop rule fires at `window`
         const uint32_t t_end = std::min(window, max_it);
         info->iterations = t_end; info->unseen = 0;
         info->energy_initial = info->energy_final = (double)e0 / 4294967296.0;
@@ -1067,9 +1316,8 @@ int mrf_run(b2tex_ctx *c, const b2tex_mrf_params *p, b2tex_mrf_info *info, doubl
     int rc = B2TEX_OK;
     for (uint32_t t = 1; t <= max_it; ++t) {
         Mrf m = make_mrf(c, t);
-        rc = enqueue_iteration(c, m);
+        rc = enqueue_iteration(c, m, true);
         if (rc != B2TEX_OK) break;
-        k_stop<<<1, 1, 0, s>>>(m, t, window, p->ratio, max_it);
         const int slot = (int)(t % (LAG + 1));
         if (cudaMemcpyAsync((void *)&hf[slot], m.state + ST_STOP, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
             cudaEventRecord(ev[slot], s) != cudaSuccess) {
@@ -1090,13 +1338,22 @@ int mrf_run(b2tex_ctx *c, const b2tex_mrf_params *p, b2tex_mrf_info *info, doubl
     for (auto &e : ev) cudaEventDestroy(e);
     B2_TRY(rc);
     Mrf m = make_mrf(c, 0);
-    k_label_check<<<std::max(1, c->num_sms * 4), 256, 0, s>>>(m);
+    if (mg) {   // one all-gather of the final labels by peer stores: seam leveling assembles its system on every rank
+        MrfPeers pr = make_peers(c);
+        ScopedTimer tg(c, "mrf.label_allgather", 4.0 * (double)(m.ne - m.nb) * (pr.nranks - 1));
+        B2_LAUNCH k_range_push<<<std::max(1, c->num_sms * 2), 256, 0, s>>>(m, pr);
+        B2_LAUNCH k_mg_sync<<<1, 32, 0, s>>>(m, pr, c->mrf_mg->epoch + 2u * MRF_SLOTS + 4u, 2, max_it, 1u, 0.0f, 0xFFFFFFFFu, c->mrf_mg->elocal.p);
+        B2_KERNEL_CHECK();
+        c->mrf_mg->epoch += 2u * MRF_SLOTS + 8u;   // the same step on every rank, however many launches were queued
+    }
+    B2_LAUNCH k_label_check<<<std::max(1, c->num_sms * 4), 256, 0, s>>>(m);
     B2_KERNEL_CHECK();
     uint32_t st[ST_WORDS];
     B2_TRY(c->mrf_state.download(st, ST_WORDS, s));
     std::vector<unsigned long long> efix((size_t)max_it + 2, 0ull);
     B2_TRY(c->mrf_energy.download(efix.data(), (size_t)max_it + 1, s));
     B2_CUDA(cudaStreamSynchronize(s));
+    if (st[ST_ERR]) { set_error("multi-GPU view selection: %u cross-GPU barrier timeouts (a peer did not arrive)", st[ST_ERR]); return B2TEX_ERR_CUDA; }
     const uint32_t t_end = st[ST_STOP] ? st[ST_STOP] : st[ST_DONE];   // ST_STOP == 0 only for max_iterations == 0
     info->iterations = t_end;
     info->energy_initial = (double)(int64_t)efix[0] / 4294967296.0;
@@ -1111,19 +1368,26 @@ int mrf_run(b2tex_ctx *c, const b2tex_mrf_params *p, b2tex_mrf_info *info, doubl
         const double per = (14.0 * (double)fz + 20.0 * (double)fn) / (double)t_end;
         for (auto &k : c->timers) if (!strcmp(k.name, "mrf.k_tree") && k.bytes == 0.0) k.bytes = per;
     }
+    if (c->mrf_dbg.n) {
+        unsigned long long d[16];
+        B2_TRY(c->mrf_dbg.download(d, 16, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        fprintf(stderr, "k_forest phases over %u iterations [us]: round0 %.1f seed %.1f growth %.1f alloc %.1f scatter %.1f\n", t_end,
+                d[1] / 1e3, d[2] / 1e3, d[3] / 1e3, d[4] / 1e3, d[5] / 1e3);
+    }
     if (st[ST_BAD]) { set_error("Incorrect labeling"); return B2TEX_ERR_LABELING; }
     return B2TEX_OK;
 }
 
-// fixed-point energy of the owned nodes with the labels currently in the context (a sharded run calls
-// this after the boundary-label exchange, so that cut edges see the neighbours' NEW labels)
+// fixed-point energy of the owned nodes with the labels currently in the context (a host-driven sharded run calls
+// this after its own label exchange, so that cut edges see the neighbours' NEW labels)
 int mrf_energy_only(b2tex_ctx *c, int64_t *efix)
 {
     if (!c->mrf_ready) { set_error("mrf_energy before mrf_init"); return B2TEX_ERR_ARG; }
     Mrf m = make_mrf(c, 1);
-    const uint32_t slot = c->mrf_params.max_iterations + 1;   // scratch slot
+    const uint32_t slot = MRF_SLOTS - 1;   // scratch slot
     B2_CUDA(cudaMemsetAsync(m.efix + slot, 0, sizeof(unsigned long long), c->stream));
-    if (m.ne > m.nb) k_energy<<<std::max(1, c->num_sms * 8), 256, 0, c->stream>>>(m, slot);
+    if (m.ne > m.nb) B2_LAUNCH k_energy<<<std::max(1, c->num_sms * 8), 256, 0, c->stream>>>(m, m.efix + slot);
     B2_KERNEL_CHECK();
     return read_energy(c, m, slot, efix);
 }
@@ -1139,5 +1403,65 @@ int mrf_sample_only(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t, uint32_
     B2_CUDA(cudaStreamSynchronize(c->stream));
     return B2TEX_OK;
 }
+
+// ---- peer block management (one process per GPU; the 64-byte cudaIpc handles travel through the caller) ----
+void mrf_mg_free(b2tex_ctx *c)
+{
+    MrfMgState *g = c->mrf_mg;
+    if (!g) return;
+    if (c->labels.borrowed) { c->labels.release(); c->have_labels = false; }
+    for (uint32_t k = 0; k < (uint32_t)MRF_MAX_RANKS; ++k)
+        if (g->opened[k] && g->peer[k]) cudaIpcCloseMemHandle(g->peer[k]);
+    if (g->block) cudaFree(g->block);
+    delete g;
+    c->mrf_mg = nullptr;
+}
+
+// needs the mesh (F); from here on c->labels lives inside the peer-visible block
+int mrf_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t nranks, void *handle64)
+{
+    if (!c->F) { set_error("mrf_mg_export: set the mesh first"); return B2TEX_ERR_ARG; }
+    if (nranks < 1 || nranks > (uint32_t)MRF_MAX_RANKS || rank >= nranks) { set_error("mrf_mg_export: at most %d ranks", MRF_MAX_RANKS); return B2TEX_ERR_ARG; }
+    mrf_mg_free(c);
+    MrfMgState *g = new MrfMgState();
+    c->mrf_mg = g;
+    g->F = c->F; g->rank = rank; g->nranks = nranks;
+    const size_t bytes = mrf_block_bytes(c->F);
+    B2_CUDA(cudaMalloc(&g->block, bytes));
+    B2_CUDA(cudaMemsetAsync(g->block, 0, bytes, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    g->peer[rank] = g->block;
+    c->labels.borrow((uint32_t *)g->block, c->F);
+    c->have_labels = false;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    if (nranks > 1) B2_CUDA(cudaIpcGetMemHandle(&h, g->block));
+    memcpy(handle64, &h, 64);
+    return B2TEX_OK;
+}
+
+int mrf_mg_import(b2tex_ctx *c, uint32_t peer_rank, const void *handle64)
+{
+    MrfMgState *g = c->mrf_mg;
+    if (!g || peer_rank >= g->nranks) { set_error("mrf_mg_import: export first"); return B2TEX_ERR_ARG; }
+    if (peer_rank == g->rank) return B2TEX_OK;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    B2_CUDA(cudaIpcOpenMemHandle(&g->peer[peer_rank], h, cudaIpcMemLazyEnablePeerAccess));
+    g->opened[peer_rank] = true;
+    return B2TEX_OK;
+}
+
+// Peers inside ONE process (two contexts, e.g. two devices driven by threads, or two contexts on one device in the
+// tests): no IPC handle is needed, the raw device pointer of the peer's block is attached instead.
+int mrf_mg_attach(b2tex_ctx *c, uint32_t peer_rank, void *peer_block)
+{
+    MrfMgState *g = c->mrf_mg;
+    if (!g || peer_rank >= g->nranks || !peer_block) { set_error("mrf_mg_attach: export first"); return B2TEX_ERR_ARG; }
+    if (peer_rank != g->rank) g->peer[peer_rank] = peer_block;
+    return B2TEX_OK;
+}
+void *mrf_mg_block(b2tex_ctx *c) { return c->mrf_mg ? c->mrf_mg->block : nullptr; }
 
 }  // namespace b2

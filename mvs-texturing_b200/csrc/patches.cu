@@ -298,8 +298,8 @@ int patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info)
     B2_TRY(ps.comp_wh.upload(comp_wh.data(), 2 * (size_t)C, s));
     B2_TRY(ps.comp_bbox.alloc(4 * (size_t)C));
     B2_TRY(ps.px.alloc(6 * (size_t)T));
-    if (C) k_bbox_init<<<(C + 255) / 256, 256, 0, s>>>(C, ps.comp_wh.p, ps.comp_bbox.p);
-    if (T) k_project<<<(T + 255) / 256, 256, 0, s>>>(T, ps.comp_faces.p, ps.slot_comp0.p, c->labels.p, c->verts.p, c->faces.p,
+    if (C) B2_LAUNCH k_bbox_init<<<(C + 255) / 256, 256, 0, s>>>(C, ps.comp_wh.p, ps.comp_bbox.p);
+    if (T) B2_LAUNCH k_project<<<(T + 255) / 256, 256, 0, s>>>(T, ps.comp_faces.p, ps.slot_comp0.p, c->labels.p, c->verts.p, c->faces.p,
                                                      c->views_dev.p, ps.px.p, ps.comp_bbox.p);
     B2_KERNEL_CHECK();
     std::vector<int32_t> bbox(4 * (size_t)(C ? C : 1));
@@ -330,17 +330,17 @@ int patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info)
     B2_TRY(ps.valid.alloc(P));
     B2_TRY(ps.blend.alloc(P));
     if (T) {
-        k_texcoords<<<(T + 255) / 256, 256, 0, s>>>(T, ps.slot_src.p, ps.slot_comp.p, ps.comp_min.p, ps.comp_chain.p, ps.chain.p,
+        B2_LAUNCH k_texcoords<<<(T + 255) / 256, 256, 0, s>>>(T, ps.slot_src.p, ps.slot_comp.p, ps.comp_min.p, ps.comp_chain.p, ps.chain.p,
                                                     ps.px.p, ps.tex.p);
-        k_adjust_values<<<(T + 255) / 256, 256, 0, s>>>(T, ps.slot_face.p, ps.slot_patch.p, ps.desc.p, c->faces.p,
+        B2_LAUNCH k_adjust_values<<<(T + 255) / 256, 256, 0, s>>>(T, ps.slot_face.p, ps.slot_patch.p, ps.desc.p, c->faces.p,
                                                         apply_adjust ? c->row_ptr.p : nullptr, apply_adjust ? c->row_label.p : nullptr,
                                                         apply_adjust ? c->seam_x.p : nullptr, c->R, ps.adj.p);
     }
     if (P) {
         const unsigned pb = (unsigned)((P + 255) / 256);
-        k_crop<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, c->views_dev.p, ps.img.p, ps.key.p);
-        if (T) k_raster_keys<<<(T + 255) / 256, 256, 0, s>>>(T, ps.slot_patch.p, ps.desc.p, ps.pix_off.p, ps.tex.p, ps.key.p);
-        k_apply<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.tex.p, ps.adj.p, ps.key.p, ps.img.p, ps.valid.p, ps.blend.p);
+        B2_LAUNCH k_crop<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, c->views_dev.p, ps.img.p, ps.key.p);
+        if (T) B2_LAUNCH k_raster_keys<<<(T + 255) / 256, 256, 0, s>>>(T, ps.slot_patch.p, ps.desc.p, ps.pix_off.p, ps.tex.p, ps.key.p);
+        B2_LAUNCH k_apply<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.tex.p, ps.adj.p, ps.key.p, ps.img.p, ps.valid.p, ps.blend.p);
     }
     B2_KERNEL_CHECK();
     B2_CUDA(cudaStreamSynchronize(s));

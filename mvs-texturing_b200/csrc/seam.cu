@@ -425,7 +425,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
     B2_TRY(cnt.zero(s));
     B2_TRY(c->row_ptr.alloc((size_t)Vn + 1));
     const uint32_t vb = (Vn + 127) / 128;
-    k_vertex_labels<false><<<vb, 128, 0, s>>>(Vn, c->vf_ptr.p, c->vf_idx.p, c->labels.p, cnt.p, nullptr, nullptr, nullptr);
+    B2_LAUNCH k_vertex_labels<false><<<vb, 128, 0, s>>>(Vn, c->vf_ptr.p, c->vf_idx.p, c->labels.p, cnt.p, nullptr, nullptr, nullptr);
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u32(c, cnt.p, c->row_ptr.p, (size_t)Vn + 1));
     uint32_t R = 0;
@@ -434,7 +434,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
     c->R = R;
     B2_TRY(c->row_label.alloc(R));
     B2_TRY(row_vertex.alloc(R));
-    k_vertex_labels<true><<<vb, 128, 0, s>>>(Vn, c->vf_ptr.p, c->vf_idx.p, c->labels.p, nullptr, c->row_ptr.p,
+    B2_LAUNCH k_vertex_labels<true><<<vb, 128, 0, s>>>(Vn, c->vf_ptr.p, c->vf_idx.p, c->labels.p, nullptr, c->row_ptr.p,
                                              c->row_label.p, row_vertex.p);
     B2_KERNEL_CHECK();
 
@@ -442,7 +442,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
                c->row_ptr.p, c->row_label.p, c->views_dev.p};
     B2_TRY(c->arow_ptr.alloc((size_t)Vn + 1));
     B2_TRY(cnt.zero(s));
-    k_arows<false><<<vb, 128, 0, s>>>(Vn, m, cnt.p, nullptr, nullptr, nullptr);
+    B2_LAUNCH k_arows<false><<<vb, 128, 0, s>>>(Vn, m, cnt.p, nullptr, nullptr, nullptr);
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u32(c, cnt.p, c->arow_ptr.p, (size_t)Vn + 1));
     uint32_t A = 0;
@@ -451,7 +451,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
     c->A_rows = A;
     B2_TRY(c->arow_rows.alloc(2 * (size_t)A));
     B2_TRY(c->arow_b.alloc(3 * (size_t)A));
-    k_arows<true><<<vb, 128, 0, s>>>(Vn, m, nullptr, c->arow_ptr.p, c->arow_rows.p, c->arow_b.p);
+    B2_LAUNCH k_arows<true><<<vb, 128, 0, s>>>(Vn, m, nullptr, c->arow_ptr.p, c->arow_rows.p, c->arow_b.p);
     B2_KERNEL_CHECK();
 
     DevBuf<uint32_t> &rcnt = c->s_rcnt;
@@ -460,7 +460,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
     B2_TRY(c->csr_ptr.alloc((size_t)R + 1));
     const uint32_t rb = (R + 127) / 128;
     if (R)
-        k_matrix<false><<<rb, 128, 0, s>>>(R, m, row_vertex.p, c->arow_ptr.p, c->arow_rows.p, c->arow_b.p, rcnt.p,
+        B2_LAUNCH k_matrix<false><<<rb, 128, 0, s>>>(R, m, row_vertex.p, c->arow_ptr.p, c->arow_rows.p, c->arow_b.p, rcnt.p,
                                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u32(c, rcnt.p, c->csr_ptr.p, (size_t)R + 1));
@@ -479,7 +479,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
     B2_TRY(c->seam_t.alloc(3 * (size_t)R));
     B2_TRY(c->seam_p.alloc(R));
     if (R)
-        k_matrix<true><<<rb, 128, 0, s>>>(R, m, row_vertex.p, c->arow_ptr.p, c->arow_rows.p, c->arow_b.p, nullptr,
+        B2_LAUNCH k_matrix<true><<<rb, 128, 0, s>>>(R, m, row_vertex.p, c->arow_ptr.p, c->arow_rows.p, c->arow_b.p, nullptr,
                                           c->csr_ptr.p, c->csr_col.p, c->csr_val.p, c->seam_diag.p, c->seam_rhs.p, c->csr_enc.p,
                                           c->seam_dval.p);
     B2_KERNEL_CHECK();
@@ -511,6 +511,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
         B2_CUDA(cudaEventCreate(&e0));
         B2_CUDA(cudaEventCreate(&e1));
         B2_CUDA(cudaEventRecord(e0, s));
+        count_launch();
         B2_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg, dim3(grid), dim3(PCG_THREADS), args, 0, s));
         B2_CUDA(cudaEventRecord(e1, s));
         uint32_t st[8];

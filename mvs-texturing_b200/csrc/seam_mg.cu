@@ -338,6 +338,16 @@ int seam_mg_import(b2tex_ctx *c, uint32_t peer_rank, const void *handle64)
     return B2TEX_OK;
 }
 
+// peers inside one process: attach the raw device pointer of the peer's block instead of an IPC handle
+int seam_mg_attach(b2tex_ctx *c, uint32_t peer_rank, void *peer_block)
+{
+    MgState *m = c->seam_mg;
+    if (!m || peer_rank >= m->nranks || !peer_block) { set_error("seam_mg_attach: export first"); return B2TEX_ERR_ARG; }
+    if (peer_rank != m->rank) m->peer[peer_rank] = peer_block;
+    return B2TEX_OK;
+}
+void *seam_mg_block(b2tex_ctx *c) { return c->seam_mg ? c->seam_mg->block : nullptr; }
+
 int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info)
 {
     MgState *m = c->seam_mg;
@@ -366,6 +376,7 @@ int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info)
     cudaEvent_t e0, e1;
     B2_CUDA(cudaEventCreate(&e0)); B2_CUDA(cudaEventCreate(&e1));
     B2_CUDA(cudaEventRecord(e0, s));
+    count_launch();
     B2_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg_mg, dim3(grid), dim3(MG_THREADS), args, 0, s));
     B2_CUDA(cudaEventRecord(e1, s));
     uint32_t st[16];

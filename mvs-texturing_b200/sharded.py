@@ -45,15 +45,39 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
+def describe_parallelism(world):
+    if world == 1:
+        return "1 GPU, whole scene resident"
+    return (f"{world} GPUs, one process each: faces split in {world} contiguous ranges; data costs: NCCL all-reduce of the "
+            f"maximum and of the 10 000 histogram bins; view selection: boundary-label halo + energy all-reduce through "
+            f"NVLink peer memory inside the device loop (no host round trip per iteration); seam leveling: assembly "
+            f"replicated, PCG rows split, search direction halo + dot products through peer memory inside one "
+            f"persistent kernel per GPU")
+
+
+def _exchange_handles(torch, dist, dev, world, rank, mine: bytes):
+    """All-gather of one 64-byte cudaIpc handle per rank."""
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    allh = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(allh, t)
+    return [bytes(h.cpu().numpy().tobytes()) for h in allh]
+
+
 class ShardedPipeline:
-    def __init__(self, b2, scene, adj, rings, rank=0, world=1, local_rank=0, upload=True):
+    def __init__(self, b2, scene, adj, rings, rank=0, world=1, local_rank=0, upload=True, settings=None):
         self.b2, self.scene, self.adj, self.rings = b2, scene, adj, rings
         self.rank, self.world = rank, world
+        # tex::Settings fields the data-cost stage reads: dict(data_term=, visibility=, outlier_removal=); None = reference defaults
+        self.settings = settings
         self.F = scene.num_faces
         self.psz = (self.F + world - 1) // world
         self.fb = min(self.F, rank * self.psz)
         self.fe = min(self.F, (rank + 1) * self.psz)
         self.ctx = b2.Context(local_rank)
+        # B2TEX_MRF_NCCL=1 / B2TEX_SEAM_P2P=0: the round-1 host-driven paths (label all-gather over NCCL, replicated solve)
+        self.mrf_peer = world > 1 and world <= 8 and os.environ.get("B2TEX_MRF_NCCL", "0") != "1"
+        self.seam_peer = world > 1 and world <= 8 and os.environ.get("B2TEX_SEAM_P2P", "1") != "0"
+        self._mrf_peers_ready = False
         if upload:
             self.upload()
 
@@ -64,13 +88,23 @@ class ShardedPipeline:
         c.set_vertex_rings(*self.rings)
         if self.world > 1:
             c.set_face_range(self.fb, self.fe)
+            if self.mrf_peer and not self._mrf_peers_ready:
+                self._attach_mrf_peers()
+
+    def _attach_mrf_peers(self):
+        """One-time: every rank allocates the peer-visible label block and maps those of its peers (cudaIpc)."""
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", torch.cuda.current_device())
+        handles = _exchange_handles(torch, dist, dev, self.world, self.rank, self.ctx.mrf_mg_export(self.rank, self.world))
+        for k in range(self.world):
+            if k != self.rank:
+                self.ctx.mrf_mg_import(k, handles[k])
+        dist.barrier()      # every block is mapped before the first store into it
+        self._mrf_peers_ready = True
 
     def describe(self):
-        if self.world == 1:
-            return "1 GPU, whole scene resident"
-        return (f"{self.world} GPUs: faces split in {self.world} contiguous ranges for data costs (NCCL max + "
-                f"histogram all-reduce) and MRF (label all-gather + energy all-reduce per iteration); seam "
-                f"leveling replicated")
+        return describe_parallelism(self.world)
 
     # ---- one pass of the hot path ---------------------------------------------------------------
     def step(self):
@@ -81,7 +115,7 @@ class ShardedPipeline:
     def _step_single(self):
         c = self.ctx
         t0 = time.perf_counter()
-        dc = c.data_costs_run()
+        dc = c.data_costs_run(**(self.settings or {}))
         t1 = time.perf_counter()
         mrf, trace = c.view_selection_run()
         t2 = time.perf_counter()
@@ -96,7 +130,7 @@ class ShardedPipeline:
         c, b2 = self.ctx, self.b2
         dev = torch.device("cuda", torch.cuda.current_device())
         t0 = time.perf_counter()
-        info = c.data_costs_qualities()
+        info = c.data_costs_qualities(**(self.settings or {}))
         gmax = torch.tensor([info.max_quality], dtype=torch.float32, device=dev)
         dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
         gmax_f = float(gmax.item())
@@ -109,12 +143,37 @@ class ShardedPipeline:
         cand, rays = info.candidates, info.rays
         info = c.data_costs_normalize(gmax_f, bins)
         info.candidates, info.rays = cand, rays
-        counts = torch.tensor([info.nnz], dtype=torch.int64, device=dev)
-        dist.all_reduce(counts)
-        total_nnz = int(counts.item())
+        self._own_nnz = int(info.nnz)
         t1 = time.perf_counter()
 
-        # ---- MRF with boundary-label exchange ----
+        P, F = self.world, self.F
+        if self.mrf_peer:
+            # the whole loop runs on the device; the ranks meet inside the kernels (csrc/mrf.cu: k_halo_push, k_mg_sync)
+            mrf, trace = c.view_selection_run(num_parts=P)
+        else:
+            mrf, trace = self._mrf_nccl(torch, dist, dev)
+        t2 = time.perf_counter()
+        if self.seam_peer:
+            seam = self._seam_p2p(torch, dist, dev)
+        else:
+            seam = c.seam_run()
+        t3 = time.perf_counter()
+        return dict(dc=info, mrf=mrf, seam=seam, trace=trace,
+                    stage_s=dict(data_costs=t1 - t0, view_selection=t2 - t1, seam_leveling=t3 - t2))
+
+    def total_nnz(self):
+        """DataCosts entries over all ranks (one all-reduce; outside the timed step)."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return None
+        counts = torch.tensor([self._own_nnz], dtype=torch.int64, device="cuda")
+        dist.all_reduce(counts)
+        return int(counts.item())
+
+    def _mrf_nccl(self, torch, dist, dev):
+        """Round-1 path (B2TEX_MRF_NCCL=1): host-driven loop, the whole label array all-gathered every iteration."""
+        c, b2 = self.ctx, self.b2
         P, psz, F = self.world, self.psz, self.F
         p = b2.mrf_params(num_parts=P)
         ratio = float(np.float32(p.ratio))
@@ -144,35 +203,23 @@ class ShardedPipeline:
         mrf.iterations = t
         mrf.energy_initial = efix[0] / 4294967296.0
         mrf.energy_final = efix[t] / 4294967296.0
-        mrf.sweep_bytes = 14 * total_nnz + 20 * F
-        t2 = time.perf_counter()
-        if os.environ.get("B2TEX_SEAM_P2P", "0") == "1" and P <= 8:
-            seam = self._seam_p2p(torch, dist, dev)
-        else:
-            seam = c.seam_run()
-        t3 = time.perf_counter()
-        info.nnz = total_nnz
-        return dict(dc=info, mrf=mrf, seam=seam, trace=np.array(efix) / 4294967296.0,
-                    stage_s=dict(data_costs=t1 - t0, view_selection=t2 - t1, seam_leveling=t3 - t2))
+        mrf.sweep_bytes = 14 * self._own_nnz + 20 * F
+        return mrf, np.array(efix) / 4294967296.0
 
     def _seam_p2p(self, torch, dist, dev):
-        """Row-partitioned PCG with the exchange inside the kernel (csrc/seam_mg.cu) instead of the replicated solve:
-        every rank assembles, the cudaIpc handles of the peer blocks go round once (all-gather of 64 bytes), then each
-        GPU runs one fused compute + exchange kernel.  Opt-in (B2TEX_SEAM_P2P=1) until it has run on hardware."""
+        """Row-partitioned PCG with the exchange inside the kernel (csrc/seam_mg.cu): every rank assembles, the cudaIpc
+        handles of the peer blocks go round once per system size (all-gather of 64 bytes), then each GPU runs one fused
+        compute + exchange kernel."""
         c = self.ctx
         seam = c.seam_assemble()
         if getattr(self, "_mg_rows", None) != int(seam.num_rows):   # peer blocks are kept while the system size stays
-            handle = c.seam_mg_export(self.rank, self.world)
-            mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
-            allh = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(self.world)]
-            dist.all_gather(allh, mine)
+            handles = _exchange_handles(torch, dist, dev, self.world, self.rank, c.seam_mg_export(self.rank, self.world))
             for k in range(self.world):
                 if k != self.rank:
-                    c.seam_mg_import(k, bytes(allh[k].cpu().numpy().tobytes()))
+                    c.seam_mg_import(k, handles[k])
             self._mg_rows = int(seam.num_rows)
-        dist.barrier()           # every peer block is mapped (and the previous solve left) before anybody stores into it
+            dist.barrier()       # every peer block is mapped before anybody stores into it
         c.seam_mg_solve(seam)
-        dist.barrier()           # nobody frees / reuses its block while a peer may still be inside the kernel
         return seam
 
     def _allreduce_energy(self, e):

@@ -35,8 +35,8 @@ def _kernel_part(cu_file, host_entry, drop=None, remove_line=None, close=1):
     PTX) and one line (`extern __shared__`).  `close` = number of namespaces still open at the cut."""
     src = open(os.path.join(CSRC, cu_file)).read()
     head = src.split(host_entry)[0].replace("#include <cub/cub.cuh>", "")
-    if drop:
-        a, b = head.index(drop[0]), head.index(drop[1])
+    for span in ([drop] if drop and isinstance(drop[0], str) else (drop or [])):
+        a, b = head.index(span[0]), head.index(span[1])
         head = head[:a] + head[b:]
     if remove_line:
         assert remove_line in head
@@ -53,7 +53,8 @@ def emul():
         f.write(_kernel_part("datacosts.cu", "int data_costs_qualities(", ("int cub_exclusive_sum_u64", "namespace {")))
     with open(os.path.join(OUT, "mrf_kernels.inc"), "w") as f:
         f.write(_kernel_part("mrf.cu", "Mrf make_mrf(b2tex_ctx",
-                             ("// ---- shared-memory / async-copy primitives", "// ---- end of primitives ----"),
+                             [("// ---- shared-memory / async-copy primitives", "// ---- end of primitives ----"),
+                              ("// ---- system-scope flag primitives", "// ---- end of flag primitives ----")],
                              "    extern __shared__ __align__(16) unsigned char tree_dyn[];\n", close=2))
     with open(os.path.join(OUT, "seam_kernels.inc"), "w") as f:
         f.write(_kernel_part("seam.cu", "int seam_run(b2tex_ctx"))
@@ -177,6 +178,33 @@ def test_device_view_selection_kernels(emul, orc, scene_mod, get_scene, name, kw
         assert stats[0] > 0          # trees that do not fit the pool took the global-memory recursion
     elif name != "messy" and "smem" not in kw:
         assert stats[0] == 0, stats  # default pool: every tree of these scenes is solved in shared memory
+
+
+@pytest.mark.parametrize("name,ranks,kw", [("occ", 2, {}), ("occ", 3, dict(smem=4096)), ("C2s", 4, {}), ("tiny", 8, {}), ("messy", 2, {})])
+def test_device_multi_gpu_view_selection(emul, orc, scene_mod, get_scene, name, ranks, kw):
+    """The multi-GPU view selection on `ranks` emulated devices: every rank owns a contiguous face range, runs k_forest /
+    k_tree on it, stores the labels of its boundary faces into the label arrays of the ranks that own a neighbour
+    (k_halo_push) and meets the others at epoch-flag barriers (k_mg_sync, all ranks alive at once under
+    emul::launch_ranks, epochs crossing the 32-bit wrap); partial energies travel through per-rank slots and are summed in
+    rank order.  Result: the labels, iteration count and energy of the oracle run with num_parts = ranks, identical stop
+    decisions and energy traces on every rank, and every halo copy equal to its owner's label."""
+    s = get_scene(name)
+    adj = scene_mod.face_adjacency(s.faces)
+    dc = orc.data_costs(s)
+    P = dict(orc.DEFAULT_MRF)
+    o = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1, num_parts=ranks)
+    F = s.num_faces
+    params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], ranks, 0, kw.get("smem", 0), ranks], np.uint32)
+    stats = np.zeros(4, np.uint64)
+    labels = np.zeros(F, np.uint32)
+    trace = np.full(P["max_iterations"] + 1, np.nan)
+    it = emul["emul_mrf"].emul_view_selection(C.c_uint32(F), C.c_uint32(s.num_views), orc._p(adj[0]), orc._p(adj[1]), orc._p(dc["face_ptr"]),
+                                              orc._p(dc["view"]), orc._p(dc["cost"]), orc._p(params), C.c_float(P["ratio"]), orc._p(labels),
+                                              orc._p(trace), None, orc._p(stats))
+    assert it >= 0, {-1: "a launch hung (barrier protocol)", -4: "the ranks disagree", -5: "barrier timeout"}.get(it, it)
+    assert it == o["iterations"] and np.array_equal(labels, o["labels"])
+    assert abs(trace[it] - o["energy"]) <= 1e-6 * max(1.0, o["energy"])
+    assert 0 < stats[3] < F / 2 or name == "tiny"      # only boundary faces travel
 
 
 @pytest.mark.parametrize("name", ["tiny", "occ", "messy"])
@@ -519,7 +547,7 @@ def test_device_view_selection_generic_paths(emul, orc, case):
     ap, ai, ptr, view, cost = _random_mrf_problem(rng, n, extra, K, maxl)
     o = orc.view_selection(ap, ai, ptr, view, cost, threads=1)
     P = dict(orc.DEFAULT_MRF)
-    params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], P["num_parts"], group, 2, 2], np.uint32)
+    params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], P["num_parts"], group, 0, 0], np.uint32)
     labels = np.zeros(n, np.uint32)
     trace = np.full(P["max_iterations"] + 1, np.nan)
     it = emul["emul_mrf"].emul_view_selection(C.c_uint32(n), C.c_uint32(Kdev), orc._p(ap), orc._p(ai), orc._p(ptr), orc._p(view), orc._p(cost),
@@ -608,7 +636,7 @@ def test_protocols_do_not_depend_on_the_thread_schedule(emul, orc, scene_mod, ge
         emul[lib].emul_set_schedule(C.c_uint64(seed))
     try:
         P = dict(orc.DEFAULT_MRF)
-        params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], P["num_parts"], 0, 2, 2], np.uint32)
+        params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], P["num_parts"], 0, 0, 0], np.uint32)
         labels = np.zeros(F, np.uint32)
         trace = np.full(P["max_iterations"] + 1, np.nan)
         it = emul["emul_mrf"].emul_view_selection(C.c_uint32(F), C.c_uint32(s.num_views), orc._p(adj[0]), orc._p(adj[1]), orc._p(dc["face_ptr"]),
