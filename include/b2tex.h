@@ -148,6 +148,10 @@ int b2tex_data_costs_download(b2tex_ctx *ctx, uint64_t *face_ptr, uint16_t *view
 
 int b2tex_view_selection_run(b2tex_ctx *ctx, const b2tex_mrf_params *params, b2tex_mrf_info *info,
                              double *energy_trace_or_null);
+/* optional: performs every device allocation b2tex_view_selection_run(params) will need and nothing else.  Only a caller
+ * that drives several peer ranks from ONE process needs it (all ranks prepare before the first one runs: cudaMalloc waits
+ * for the whole device, which a rank already spinning in a cross-rank barrier kernel would block for good). */
+int b2tex_view_selection_prepare(b2tex_ctx *ctx, const b2tex_mrf_params *params);
 int b2tex_labels_download(b2tex_ctx *ctx, uint32_t *labels);
 /* Multi-GPU view selection (one process per GPU, at most 8): rank r owns the faces [r * ceil(F / P), (r + 1) * ceil(F / P))
  * (b2tex_set_face_range) and runs b2tex_view_selection_run with params->num_parts = P like a single GPU would.  Before

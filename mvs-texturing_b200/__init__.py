@@ -26,7 +26,7 @@ EXPORTS = [
     "b2tex_default_mrf_params", "b2tex_set_mesh", "b2tex_set_views", "b2tex_set_adjacency",
     "b2tex_set_vertex_rings", "b2tex_set_data_costs", "b2tex_set_labels", "b2tex_set_face_range",
     "b2tex_data_costs_run", "b2tex_data_costs_qualities", "b2tex_data_costs_histogram",
-    "b2tex_data_costs_normalize", "b2tex_data_costs_download", "b2tex_view_selection_run",
+    "b2tex_data_costs_normalize", "b2tex_data_costs_download", "b2tex_view_selection_run", "b2tex_view_selection_prepare",
     "b2tex_labels_download", "b2tex_mrf_init", "b2tex_mrf_iterate", "b2tex_mrf_energy", "b2tex_mrf_sample_forest",
     "b2tex_seam_run", "b2tex_seam_download", "b2tex_seam_matrix_download", "b2tex_device_ptr",
     "b2tex_texture_patches_run", "b2tex_texture_patches_download", "b2tex_local_seam_leveling_run", "b2tex_seam_assemble", "b2tex_seam_mg_export", "b2tex_seam_mg_import",
@@ -255,6 +255,10 @@ class Context:
         q = np.zeros(nnz, np.float32) if quality else None
         _check(lib().b2tex_data_costs_download(self._h, _p(face_ptr), _p(view), _p(cost), _p(q)))
         return dict(face_ptr=face_ptr, view=view, cost=cost, quality=q)
+
+    def view_selection_prepare(self, **kw):
+        p = mrf_params(**kw)
+        _check(lib().b2tex_view_selection_prepare(self._h, C.byref(p)))
 
     def view_selection_run(self, **kw):
         p = mrf_params(**kw)

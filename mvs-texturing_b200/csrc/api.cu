@@ -300,6 +300,16 @@ int b2tex_peer_attach(b2tex_ctx *c, int which, uint32_t peer_rank, uint64_t peer
     return which == 0 ? mrf_mg_attach(c, peer_rank, p) : seam_mg_attach(c, peer_rank, p);
 }
 
+int b2tex_view_selection_prepare(b2tex_ctx *c, const b2tex_mrf_params *params)
+{
+    B2_CUDA(cudaSetDevice(c->device));
+    b2tex_mrf_params p;
+    if (params) p = *params; else b2tex_default_mrf_params(&p);
+    B2_TRY(mrf_prepare(c, &p));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2TEX_OK;
+}
+
 int b2tex_view_selection_run(b2tex_ctx *c, const b2tex_mrf_params *params, b2tex_mrf_info *info, double *trace)
 {
     B2_CUDA(cudaSetDevice(c->device));

@@ -264,6 +264,7 @@ int data_costs_normalize(b2tex_ctx *c, float gmax, const uint32_t *bins_host, b2
 int mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *energy_fixed);
 int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *energy_fixed);
 int mrf_run(b2tex_ctx *c, const b2tex_mrf_params *p, b2tex_mrf_info *info, double *trace);
+int mrf_prepare(b2tex_ctx *c, const b2tex_mrf_params *p);
 int mrf_energy_only(b2tex_ctx *c, int64_t *energy_fixed);
 int mrf_sample_only(b2tex_ctx *c, const b2tex_mrf_params *p, uint32_t t, uint32_t *level_host);
 int mrf_energy_double(b2tex_ctx *c, double *e, uint64_t *unseen);

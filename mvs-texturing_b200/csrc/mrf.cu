@@ -314,66 +314,87 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
     // itself.  The evaluated set equals the set a full scan would act on, so levels are identical to
     // oracle/mrf.c; list order is irrelevant.  qstamp de-duplicates pushes (unique per iteration+round).
     const uint32_t stamp_base = m.iter * 2048u;
-    auto push = [&](uint32_t w, uint32_t round) {
-        if (atomicExch(m.qstamp + w, stamp_base + round) == stamp_base + round) return;
-        cg::coalesced_group g = cg::coalesced_threads();
-        uint32_t base = 0;
-        if (g.thread_rank() == 0) base = atomicAdd(&m.ctl[CTL_QN + round], g.size());
-        base = g.shfl(base, 0);
-        m.queue[(size_t)(round & 1u) * m.F + base + g.thread_rank()] = w;
+    // Appending to the next frontier: one global atomic per BLOCK and pass (all pushes of a round go to the same
+    // counter; one atomic per push ran at ~2 ns each, i.e. 30 us per round).  A thread collects its pushes first.
+    constexpr int PEND = 4;
+    uint32_t pend[PEND], np = 0;
+    auto push_direct = [&](uint32_t w, uint32_t round) {
+        const uint32_t at = atomicAdd(&m.ctl[CTL_QN + round], 1u);
+        m.queue[(size_t)(round & 1u) * m.F + at] = w;
     };
-    for (uint32_t v = m.nb + tid; v < m.ne; v += nth) {  // seed: undecided neighbours of the roots
-        if (__ldcg(m.level + v) != 0u) continue;
-        const Nb nb = load_nb(m, v);
-        for (uint32_t i = 0; i < nb.deg; ++i) {
-            uint32_t w = nb_at(m, nb, i);
-            if (local_pair(m, v, w) && __ldcg(m.level + w) == LVL_NONE) push(w, 1u);
+    auto push = [&](uint32_t w, uint32_t round) {
+        if (atomicExch(m.qstamp + w, stamp_base + round) == stamp_base + round) return;   // already queued
+        if (np < (uint32_t)PEND) pend[np++] = w; else push_direct(w, round);
+    };
+    auto flush = [&](uint32_t round) {   // block-wide: every thread of the block calls it the same number of times
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const uint32_t off = np ? atomicAdd(&s_cnt, np) : 0u;
+        __syncthreads();
+        if (threadIdx.x == 0 && s_cnt) s_base = atomicAdd(&m.ctl[CTL_QN + round], s_cnt);
+        __syncthreads();
+        for (uint32_t i = 0; i < np; ++i) m.queue[(size_t)(round & 1u) * m.F + s_base + off + i] = pend[i];
+        np = 0;
+    };
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_own; base += nth) {  // seed: undecided neighbours of the roots
+        const uint32_t v = m.nb + base + threadIdx.x;
+        if (v < m.ne && __ldcg(m.level + v) == 0u) {
+            const Nb nb = load_nb(m, v);
+            for (uint32_t i = 0; i < nb.deg; ++i) {
+                uint32_t w = nb_at(m, nb, i);
+                if (local_pair(m, v, w) && __ldcg(m.level + w) == LVL_NONE) push(w, 1u);
+            }
         }
+        flush(1u);
     }
     grid.sync();
     stamp(2);   // frontier seeding
     for (uint32_t r = 1; r <= m.rounds; ++r) {
         const uint32_t n = __ldcg(m.ctl + CTL_QN + r);
         const uint32_t *q = m.queue + (size_t)(r & 1u) * m.F;
-        for (uint32_t qi = tid; qi < n; qi += nth) {
-            const uint32_t v = __ldcg(q + qi);
-            if (__ldcg(m.level + v) != LVL_NONE) continue;
-            const Nb nb = load_nb(m, v);
-            uint32_t c = 0, parent = NO_NODE;
-            for (uint32_t i = 0; i < nb.deg; ++i) {
-                uint32_t w = nb_at(m, nb, i);
-                if (local_pair(m, v, w) && __ldcg(m.level + w) < r) { ++c; parent = w; }
-            }
-            if (c >= 2) { m.level[v] = LVL_DEAD; continue; }
-            if (c != 1) continue;
-            const uint32_t pv = prio(v, seed_t);
-            bool win = true;
-            for (uint32_t i = 0; i < nb.deg && win; ++i) {
-                uint32_t w = nb_at(m, nb, i);
-                if (!local_pair(m, v, w)) continue;
-                uint32_t lw = __ldcg(m.level + w);
-                if (!(lw == LVL_NONE || lw == r)) continue;
-                if (prio(w, seed_t) < pv) continue;
-                if (count_in_forest(m, w, r) == 1) win = false;  // a stronger adjacent candidate: wait
-            }
-            if (win) {
-                m.level[v] = r;
-                if (build_trees) {   // the parent joined in an earlier round: its (tree, slot) is final
-                    const uint2 pj = __ldcg(m.tjoin + parent);
-                    uint4 *te = m.ttab + pj.x;
-                    const uint32_t slot = atomicAdd(&te->x, 1u);
-                    atomicAdd(&te->y, (uint32_t)(m.ptr[v + 1] - m.ptr[v]));
-                    if (nb.deg > 3) atomicOr(&te->w, 1u);
-                    m.tjoin[v] = make_uint2(pj.x, slot);
+        for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += nth) {   // block-uniform trip count
+            const uint32_t qi = base + threadIdx.x;
+            const uint32_t v = qi < n ? __ldcg(q + qi) : NO_NODE;
+            if (v != NO_NODE && __ldcg(m.level + v) == LVL_NONE) {
+                const Nb nb = load_nb(m, v);
+                uint32_t c = 0, parent = NO_NODE;
+                for (uint32_t i = 0; i < nb.deg; ++i) {
+                    uint32_t w = nb_at(m, nb, i);
+                    if (local_pair(m, v, w) && __ldcg(m.level + w) < r) { ++c; parent = w; }
                 }
-                if (r < m.rounds)
-                    for (uint32_t i = 0; i < nb.deg; ++i) {
+                if (c >= 2) m.level[v] = LVL_DEAD;
+                else if (c == 1) {
+                    const uint32_t pv = prio(v, seed_t);
+                    bool win = true;
+                    for (uint32_t i = 0; i < nb.deg && win; ++i) {
                         uint32_t w = nb_at(m, nb, i);
-                        if (local_pair(m, v, w) && __ldcg(m.level + w) == LVL_NONE) push(w, r + 1u);
+                        if (!local_pair(m, v, w)) continue;
+                        uint32_t lw = __ldcg(m.level + w);
+                        if (!(lw == LVL_NONE || lw == r)) continue;
+                        if (prio(w, seed_t) < pv) continue;
+                        if (count_in_forest(m, w, r) == 1) win = false;  // a stronger adjacent candidate: wait
                     }
-            } else if (r < m.rounds) {
-                push(v, r + 1u);
+                    if (win) {
+                        m.level[v] = r;
+                        if (build_trees) {   // the parent joined in an earlier round: its (tree, slot) is final
+                            const uint2 pj = __ldcg(m.tjoin + parent);
+                            uint4 *te = m.ttab + pj.x;
+                            const uint32_t slot = atomicAdd(&te->x, 1u);
+                            atomicAdd(&te->y, (uint32_t)(m.ptr[v + 1] - m.ptr[v]));
+                            if (nb.deg > 3) atomicOr(&te->w, 1u);
+                            m.tjoin[v] = make_uint2(pj.x, slot);
+                        }
+                        if (r < m.rounds)
+                            for (uint32_t i = 0; i < nb.deg; ++i) {
+                                uint32_t w = nb_at(m, nb, i);
+                                if (local_pair(m, v, w) && __ldcg(m.level + w) == LVL_NONE) push(w, r + 1u);
+                            }
+                    } else if (r < m.rounds) {
+                        push(v, r + 1u);
+                    }
+                }
             }
+            if (r < m.rounds) flush(r + 1u);
         }
         grid.sync();
     }
@@ -428,10 +449,10 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
     stamp(5);   // scatter (thread 0's share)
 }
 
-// ---- min-sum DP of whole trees inside one warp ---------------------------------------------------------------
-constexpr int TREE_THREADS = 128;
+// ---- min-sum DP of whole trees in shared memory ------------------------------------------------------------------
+constexpr int TREE_THREADS = 256;
 constexpr int TREE_WARPS = TREE_THREADS / 32;
-constexpr int TREE_CHUNK = 16;       // trees claimed per global atomic (<= 8 per warp: cp_async_wait_pending)
+constexpr int TREE_CHUNK = 32;       // trees claimed per global atomic (<= 8 staged per warp: cp_async_wait_pending)
 constexpr uint32_t NBR_SKIP = 0u, NBR_CHILD = 1u << 30, NBR_FIXED = 2u << 30, NBR_PARENT = 3u << 30;
 constexpr uint32_t NBR_KIND = 3u << 30, NBR_ARG = ~NBR_KIND;
 
@@ -439,12 +460,15 @@ constexpr uint32_t NBR_KIND = 3u << 30, NBR_ARG = ~NBR_KIND;
 // copies: <= 6 extra floats and <= 14 extra u16 per node)
 __host__ __device__ __forceinline__ uint32_t tree_hcap(uint32_t cnt, uint32_t nnz) { return (nnz + 6u * cnt + 3u) & ~3u; }
 __host__ __device__ __forceinline__ uint32_t tree_vcap(uint32_t cnt, uint32_t nnz) { return (nnz + 14u * cnt + 7u) & ~7u; }
-__host__ __device__ __forceinline__ uint32_t tree_node_bytes(uint32_t W) { return 40u + 6u * W; }
+__host__ __device__ __forceinline__ uint32_t tree_node_bytes(uint32_t W) { return 42u + 6u * W; }
 
 struct TreeStatic {
     uint32_t t_cnt[TREE_CHUNK], t_nnz[TREE_CHUNK], t_start[TREE_CHUNK], t_flags[TREE_CHUNK];
     uint32_t t_node0[TREE_CHUNK], t_h0[TREE_CHUNK], t_v0[TREE_CHUNK], t_slow[TREE_CHUNK];
     uint32_t chunk_first, sb_n, sb_nodes, sb_hcap, sb_vcap;
+    uint32_t scan_carry;
+    uint16_t lstart[MAX_LEVELS + 2];   // first slot of every level in lnode (sub-batch wide level buckets)
+    uint16_t lfill[MAX_LEVELS + 2];
 };
 
 // pointers into the dynamic shared memory of one sub-batch
@@ -454,6 +478,7 @@ struct TreePool {
     uint32_t *gid, *hoff, *voff, *nbr, *am, *lab, *mask;
     float *hm;
     uint16_t *nlab, *lev, *mpre;
+    uint16_t *lnode;   // the nodes of the sub-batch bucketed by level
 };
 __device__ __forceinline__ TreePool carve_pool(unsigned char *base, uint32_t nodes, uint32_t hcap, uint32_t vcap, uint32_t W)
 {
@@ -470,7 +495,8 @@ __device__ __forceinline__ TreePool carve_pool(unsigned char *base, uint32_t nod
     p.mask = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4 * W;
     p.nlab = reinterpret_cast<uint16_t *>(base); base += (size_t)nodes * 2;
     p.lev = reinterpret_cast<uint16_t *>(base); base += (size_t)nodes * 2;
-    p.mpre = reinterpret_cast<uint16_t *>(base);
+    p.mpre = reinterpret_cast<uint16_t *>(base); base += (size_t)nodes * 2 * W;
+    p.lnode = reinterpret_cast<uint16_t *>(base);
     return p;
 }
 
@@ -595,19 +621,24 @@ __device__ void tree_stage(const Mrf &m, const TreePool &p, uint32_t start, uint
     cp_async_commit();
 }
 
-// the DP of one staged tree: nodes [a, b) of the pool, sorted by level
+// The DP of ALL staged trees of a sub-batch at once, by the whole CTA: the trees are independent, so one level of all of
+// them is one parallel step (a single tree has only ~3 nodes per level: solved alone it would leave its warp idle in
+// a chain of dependent shared-memory round trips).  Nodes are bucketed by level across the sub-batch; the bottom-up
+// sweep gives every node G lanes (min / arg-min by shuffles inside the group), the top-down sweep one thread.
 template <int G>
-__device__ void tree_solve_smem(const Mrf &m, const TreePool &p, uint32_t a, uint32_t b, uint32_t W, uint32_t lane)
+__device__ void batch_solve(const Mrf &m, const TreePool &p, TreeStatic &ts, uint32_t N, uint32_t W)
 {
-    constexpr uint32_t GPW = 32 / G;
-    const uint32_t glane = lane & (G - 1), sub = lane / G;
-    // label bitmasks of this tree's rows
-    if (W) {
-        for (uint32_t i = a * W + lane; i < b * W; i += 32) p.mask[i] = 0u;
-        __syncwarp();
-        for (uint32_t base = a; base < b; base += GPW) {
-            const uint32_t li = base + sub;
-            if (li < b) {
+    constexpr uint32_t NG = TREE_THREADS / G;   // nodes in flight per step
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, glane = tid & (G - 1), group = tid / G;
+    const uint32_t nlev = m.rounds + 1u;
+    // ---- label bitmasks of every row + level histogram ----
+    for (uint32_t i = tid; i < N * W; i += TREE_THREADS) p.mask[i] = 0u;
+    for (uint32_t i = tid; i <= nlev; i += TREE_THREADS) ts.lfill[i] = 0;
+    __syncthreads();
+    if (W)
+        for (uint32_t base = 0; base < N; base += NG) {
+            const uint32_t li = base + group;
+            if (li < N) {
                 const uint16_t *row = p.V + p.voff[li];
                 const uint32_t n = p.nlab[li];
                 for (uint32_t k = glane; k < n; k += G) {
@@ -616,25 +647,53 @@ __device__ void tree_solve_smem(const Mrf &m, const TreePool &p, uint32_t a, uin
                 }
             }
         }
-        __syncwarp();
-        for (uint32_t li = a + lane; li < b; li += 32) {
-            uint32_t seen = 0;
-            for (uint32_t w = 0; w < W; ++w) {
-                p.mpre[(size_t)li * W + w] = (uint16_t)seen;
-                seen += __popc(p.mask[(size_t)li * W + w]);
-            }
-        }
-        __syncwarp();
+    for (uint32_t li = tid; li < N; li += TREE_THREADS) {   // counts as uint32 pairs would race: 16-bit atomics via CAS-free trick
+        const uint32_t l = p.lev[li];
+        atomicAdd(reinterpret_cast<uint32_t *>(ts.lfill) + (l >> 1), (l & 1u) ? 0x10000u : 1u);   // two 16-bit counters per word
     }
-    // bottom-up: deepest level first
-    for (uint32_t end = b; end > a;) {
-        const uint32_t s = level_run_begin(p.lev, a, end, lane);
-        for (uint32_t base = s; base < end; base += GPW) {
-            const uint32_t li = base + sub;
-            const bool act = li < end;
+    __syncthreads();
+    for (uint32_t li = tid; li < N; li += TREE_THREADS) {
+        uint32_t seen = 0;
+        for (uint32_t w = 0; w < W; ++w) {
+            p.mpre[(size_t)li * W + w] = (uint16_t)seen;
+            seen += __popc(p.mask[(size_t)li * W + w]);
+        }
+    }
+    if (tid < 32) {   // exclusive scan of the level counts -> lstart; lfill restarts at lstart
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base <= nlev; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t c = i <= nlev ? ts.lfill[i] : 0u;
+            uint32_t incl = c;
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, sft);
+                if ((int)lane >= sft) incl += o;
+            }
+            if (i <= nlev) ts.lstart[i] = (uint16_t)(carry + incl - c);
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) ts.lstart[nlev + 1] = (uint16_t)carry;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i <= nlev; i += TREE_THREADS) ts.lfill[i] = ts.lstart[i];
+    __syncthreads();
+    for (uint32_t li = tid; li < N; li += TREE_THREADS) {
+        const uint32_t l = p.lev[li];
+        const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(ts.lfill) + (l >> 1), (l & 1u) ? 0x10000u : 1u);
+        p.lnode[(l & 1u) ? (old >> 16) : (old & 0xFFFFu)] = (uint16_t)li;
+    }
+    __syncthreads();
+    // ---- bottom-up: deepest level first ----
+    for (uint32_t L = nlev; L-- > 0;) {
+        const uint32_t s = ts.lstart[L], e = ts.lstart[L + 1];
+        if (s == e) continue;
+        for (uint32_t base = s; base < e; base += NG) {
+            const uint32_t idx = base + group;
+            const bool act = idx < e;
             float bh = INFINITY;
-            uint32_t bk = 0xFFFFFFFFu;
+            uint32_t bk = 0xFFFFFFFFu, li = 0;
             if (act) {
+                li = p.lnode[idx];
                 const uint32_t n = p.nlab[li];
                 float *Hv = p.H + p.hoff[li];
                 const uint16_t *viewv = p.V + p.voff[li];
@@ -642,10 +701,11 @@ __device__ void tree_solve_smem(const Mrf &m, const TreePool &p, uint32_t a, uin
                 float chm[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    const uint32_t e = p.nbr[3 * (size_t)li + i];
-                    kind[i] = e & NBR_KIND; arg[i] = e & NBR_ARG;
+                    const uint32_t en = p.nbr[3 * (size_t)li + i];
+                    kind[i] = en & NBR_KIND; arg[i] = en & NBR_ARG;
                     if (kind[i] == NBR_CHILD) { chm[i] = p.hm[arg[i]]; cho[i] = p.hoff[arg[i]]; }
                 }
+#pragma unroll 2
                 for (uint32_t k = glane; k < n; k += G) {
                     const uint32_t lab = (uint32_t)viewv[k] + 1u;
                     float h = Hv[k];
@@ -671,13 +731,14 @@ __device__ void tree_solve_smem(const Mrf &m, const TreePool &p, uint32_t a, uin
             }
             if (act && glane == 0) { p.hm[li] = bh + 1.0f; p.am[li] = bk; }
         }
-        __syncwarp();
-        end = s;
+        __syncthreads();
     }
-    // top-down: shallowest level first, one lane per node
-    for (uint32_t s = a; s < b;) {
-        const uint32_t e = level_run_end(p.lev, s, b, lane);
-        for (uint32_t li = s + lane; li < e; li += 32) {
+    // ---- top-down: shallowest level first, one thread per node ----
+    for (uint32_t L = 0; L < nlev; ++L) {
+        const uint32_t s = ts.lstart[L], e = ts.lstart[L + 1];
+        if (s == e) continue;
+        for (uint32_t idx = s + tid; idx < e; idx += TREE_THREADS) {
+            const uint32_t li = p.lnode[idx];
             uint32_t bk = p.am[li];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -691,10 +752,9 @@ __device__ void tree_solve_smem(const Mrf &m, const TreePool &p, uint32_t a, uin
             p.am[li] = bk;
             p.lab[li] = (uint32_t)p.V[p.voff[li] + bk] + 1u;
         }
-        __syncwarp();
-        s = e;
+        __syncthreads();
     }
-    for (uint32_t li = a + lane; li < b; li += 32) {
+    for (uint32_t li = tid; li < N; li += TREE_THREADS) {
         const uint32_t v = p.gid[li];
         m.labels[v] = p.lab[li];
         m.lidx[v] = p.am[li];
@@ -813,20 +873,15 @@ __global__ void __launch_bounds__(TREE_THREADS) k_tree(Mrf m)
             __syncthreads();
             const uint32_t sb_n = ts.sb_n;
             const TreePool pool = carve_pool(tree_dyn, ts.sb_nodes, ts.sb_hcap, ts.sb_vcap, W);
-            // every warp first stages all of its trees (one commit group each; the copies of the later trees overlap the
-            // DP of the earlier ones), then solves them in the same order
-            uint32_t staged = 0;
-            for (uint32_t i = done + warp; i < done + sb_n; i += TREE_WARPS)
-                if (!ts.t_slow[i]) {
-                    tree_stage(m, pool, ts.t_start[i], ts.t_cnt[i], ts.t_node0[i], ts.t_h0[i], ts.t_v0[i], lane);
-                    ++staged;
-                }
+            // trees that do not fit (or hold a node of degree > 3) go through global memory, one warp each; the others
+            // are staged warp by warp (asynchronous copies) and then solved together by the whole CTA
             for (uint32_t i = done + warp; i < done + sb_n; i += TREE_WARPS) {
-                if (ts.t_slow[i]) { tree_solve_global(m, ts.t_start[i], ts.t_cnt[i], lane); continue; }
-                cp_async_wait_pending(--staged);   // this tree's group and all earlier ones have landed
-                __syncwarp();
-                tree_solve_smem<G>(m, pool, ts.t_node0[i], ts.t_node0[i] + ts.t_cnt[i], W, lane);
+                if (ts.t_slow[i]) tree_solve_global(m, ts.t_start[i], ts.t_cnt[i], lane);
+                else tree_stage(m, pool, ts.t_start[i], ts.t_cnt[i], ts.t_node0[i], ts.t_h0[i], ts.t_v0[i], lane);
             }
+            cp_async_wait_pending(0);
+            __syncthreads();
+            if (ts.sb_nodes) batch_solve<G>(m, pool, ts, ts.sb_nodes, W);
             __syncthreads();
             done += sb_n;
         }
@@ -1188,7 +1243,11 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
         }
         for (uint32_t k = 0; k < P; ++k)
             if (!g->peer[k]) { set_error("multi-GPU view selection: peer %u not imported", k); return B2TEX_ERR_ARG; }
+        const size_t n = c->face_end - c->face_begin;
+        B2_TRY(g->elocal.alloc(MRF_SLOTS));
+        B2_TRY(g->halo_list.alloc(n)); B2_TRY(g->halo_mask.alloc(n)); B2_TRY(g->halo_cnt.alloc(1));
     }
+    if (!c->mrf_host_flags) B2_CUDA(cudaHostAlloc((void **)&c->mrf_host_flags, 64 * sizeof(uint32_t), cudaHostAllocDefault));
     B2_TRY(c->mrf_H.alloc(c->nnz));
     B2_TRY(c->mrf_hminp1.alloc(F));
     B2_TRY(c->mrf_amin.alloc(F));
@@ -1225,7 +1284,7 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
     static const bool no_masks = getenv("B2TEX_NO_MASKS") != nullptr;
     c->mrf_mask_words = (c->K == 0 || words > (uint32_t)MAX_MASK_WORDS || no_masks) ? 0 : words;
     // shared-memory pool of k_tree: room for a few average trees (~ rounds * 2.7 nodes) per CTA
-    uint32_t smem = 72 * 1024;
+    uint32_t smem = 100 * 1024;
     if (const char *e = getenv("B2TEX_TREE_SMEM_KB")) smem = (uint32_t)std::max(8, std::min(200, atoi(e))) * 1024u;
     c->mrf_tree_smem = smem;
     return B2TEX_OK;
@@ -1252,10 +1311,8 @@ int mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *efix)
     if (mg_active(c)) {
         MrfMgState *g = c->mrf_mg;
         MrfPeers pr = make_peers(c);
-        B2_TRY(g->elocal.alloc(MRF_SLOTS));
         B2_TRY(g->elocal.zero(s));
         const uint32_t n = m.ne - m.nb;
-        B2_TRY(g->halo_list.alloc(n)); B2_TRY(g->halo_mask.alloc(n)); B2_TRY(g->halo_cnt.alloc(1));
         B2_TRY(g->halo_cnt.zero(s));
         if (n) B2_LAUNCH k_halo_build<<<(n + 255) / 256, 256, 0, s>>>(m, g->halo_cnt.p, g->halo_list.p, g->halo_mask.p);
         // entry barrier: every rank is done with the labels of the previous run before anybody overwrites them
@@ -1277,6 +1334,11 @@ int mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *efix)
     if (m.ne > m.nb || mg_active(c)) B2_TRY(enqueue_exchange_and_energy(c, m, 0u, false));
     return read_energy(c, m, 0u, efix);
 }
+
+// every allocation of a run, nothing else: a caller that drives several ranks from ONE process (threads) prepares all of
+// them before the first rank starts, because cudaMalloc waits for the whole device and a rank that already spins in a
+// cross-rank barrier kernel would never be released (separate processes / devices do not have that problem)
+int mrf_prepare(b2tex_ctx *c, const b2tex_mrf_params *p) { return alloc_mrf(c, p); }
 
 // one iteration, energy read back (single GPU, or the building block of a host-driven sharded loop over NCCL)
 int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *efix)
@@ -1309,7 +1371,6 @@ int mrf_run(b2tex_ctx *c, const b2tex_mrf_params *p, b2tex_mrf_info *info, doubl
         return B2TEX_OK;
     }
     constexpr int LAG = 3;   // iterations queued beyond the last one whose stop flag the host has seen
-    if (!c->mrf_host_flags) B2_CUDA(cudaHostAlloc((void **)&c->mrf_host_flags, 64 * sizeof(uint32_t), cudaHostAllocDefault));
     cudaEvent_t ev[LAG + 1];
     for (auto &e : ev) B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     volatile uint32_t *hf = c->mrf_host_flags;

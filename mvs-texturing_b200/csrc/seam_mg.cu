@@ -318,6 +318,8 @@ int seam_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t nranks, void *handle64)
     B2_CUDA(cudaMemsetAsync(m->block, 0, bytes, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     m->peer[rank] = m->block;
+    B2_TRY(m->blockpart.alloc(4096 * 8));   // every allocation happens here: nothing inside the solve waits for the device
+    B2_TRY(m->status.alloc(16));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
     memset(&h, 0, sizeof(h));
@@ -363,8 +365,7 @@ int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info)
     int grid = c->num_sms * per_sm;
     const int need = (int)((r1 - r0 + MG_THREADS - 1) / MG_THREADS);
     if (grid > need) grid = std::max(1, need);
-    B2_TRY(m->blockpart.alloc((size_t)grid * 8));
-    B2_TRY(m->status.alloc(16));
+    if (grid > 4096) grid = 4096;
     B2_TRY(m->status.zero(s));
     PcgMg q;
     q.R = R; q.r0 = r0; q.r1 = r1; q.rank = m->rank; q.nranks = m->nranks;

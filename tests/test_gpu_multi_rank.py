@@ -69,6 +69,8 @@ def test_sharded_pipeline_on_one_gpu(b2, orc, scene_mod, get_scene, name, ranks)
             for k in range(ranks):
                 if k != r:
                     c.peer_attach(0, k, blocks[k])
+        for c in ctxs:      # all device allocations before any rank can sit in a barrier kernel (one process, one device)
+            c.view_selection_prepare(num_parts=ranks)
         res = _run_threads([(lambda c=c: c.view_selection_run(num_parts=ranks)) for c in ctxs])
         for (info, trace), c in zip(res, ctxs):
             assert info.iterations == om["iterations"]
