@@ -234,6 +234,14 @@ int b2tex_calculate_data_costs_into(const float *verts, uint32_t num_verts, cons
                                     const b2tex_view *views, uint32_t num_views,
                                     const b2tex_settings *settings, uint64_t *face_ptr, uint16_t *view,
                                     float *cost, uint64_t capacity, b2tex_dc_info *info);
+/* tex::postprocess_face_infos (libs/tex/texturing.h:71-74, calculate_data_costs.cpp:253-306) for qualities the caller
+ * computed: per face (CSR face_ptr[F+1]) the infos in ascending view order -- view[n], quality[n] and, with outlier
+ * removal, the mean YCbCr colour mean_color_ycbcr[n][3] (NULL otherwise).  Photometric outlier removal, quality == 0
+ * entries dropped, 99.5 % percentile of the 10 000-bin histogram, cost = 1 - min(1, quality / percentile).  Out arrays are
+ * caller allocated: face_ptr_out[F+1], view_out / cost_out with room for n entries. */
+int b2tex_postprocess_face_infos(uint32_t num_faces, const uint64_t *face_ptr, const uint16_t *view, const float *quality,
+                                 const float *mean_color_ycbcr, const b2tex_settings *settings, uint64_t *face_ptr_out,
+                                 uint16_t *view_out, float *cost_out, b2tex_dc_info *info);
 /* tex::view_selection: labels_out[F] (0 = unseen, else view index + 1) */
 int b2tex_view_selection(uint32_t num_faces, const uint32_t *adj_ptr, const uint32_t *adj_idx,
                          const uint64_t *face_ptr, const uint16_t *view, const float *cost,

@@ -31,7 +31,7 @@ EXPORTS = [
     "b2tex_seam_run", "b2tex_seam_download", "b2tex_seam_matrix_download", "b2tex_device_ptr",
     "b2tex_texture_patches_run", "b2tex_texture_patches_download", "b2tex_local_seam_leveling_run", "b2tex_seam_assemble", "b2tex_seam_mg_export", "b2tex_seam_mg_import",
     "b2tex_seam_mg_solve", "b2tex_mrf_mg_export", "b2tex_mrf_mg_import", "b2tex_peer_block", "b2tex_peer_attach",
-    "b2tex_calculate_data_costs", "b2tex_calculate_data_costs_into", "b2tex_view_selection",
+    "b2tex_calculate_data_costs", "b2tex_calculate_data_costs_into", "b2tex_postprocess_face_infos", "b2tex_view_selection",
     "b2tex_global_seam_leveling", "b2tex_texture_hot_path", "b2tex_seam_leveling_patches", "b2tex_release_cached_contexts",
 ]
 

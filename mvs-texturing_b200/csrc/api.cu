@@ -523,6 +523,31 @@ int b2tex_calculate_data_costs_into(const float *verts, uint32_t nv, const uint3
     return rc;
 }
 
+int b2tex_postprocess_face_infos(uint32_t nf, const uint64_t *face_ptr, const uint16_t *view, const float *quality,
+                                 const float *mean_color_ycbcr, const b2tex_settings *st, uint64_t *face_ptr_out,
+                                 uint16_t *view_out, float *cost_out, b2tex_dc_info *info)
+{
+    b2tex_ctx *c = nullptr;
+    B2_TRY(acquire_ctx(&c));
+    b2tex_dc_info local;
+    if (!info) info = &local;
+    int rc = data_costs_postprocess(c, st, nf, face_ptr, view, quality, mean_color_ycbcr, info);
+    if (rc == B2TEX_OK) {
+        const float gmax = info->max_quality;
+        uint32_t *bins = (uint32_t *)malloc(10000 * sizeof(uint32_t));
+        rc = b2tex_data_costs_histogram(c, gmax, bins, 1);
+        if (rc == B2TEX_OK) {
+            const uint64_t cand = info->candidates;
+            rc = data_costs_normalize(c, gmax, bins, info);
+            info->candidates = cand; info->rays = 0;
+        }
+        free(bins);
+    }
+    if (rc == B2TEX_OK) rc = b2tex_data_costs_download(c, face_ptr_out, view_out, cost_out, nullptr);
+    release_ctx(c, rc);
+    return rc;
+}
+
 int b2tex_view_selection(uint32_t nf, const uint32_t *adj_ptr, const uint32_t *adj_idx, const uint64_t *face_ptr,
                          const uint16_t *view, const float *cost, const b2tex_mrf_params *params,
                          uint32_t *labels_out, b2tex_mrf_info *info)

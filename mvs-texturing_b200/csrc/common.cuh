@@ -260,6 +260,8 @@ int prepare_images(b2tex_ctx *c, int data_term, bool force = false);
 int build_bvh(b2tex_ctx *c, bool force = false);
 int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *info);
 int data_costs_histogram(b2tex_ctx *c, float gmax);
+int data_costs_postprocess(b2tex_ctx *c, const b2tex_settings *st, uint32_t F, const uint64_t *face_ptr, const uint16_t *view,
+                           const float *quality, const float *mean_ycbcr, b2tex_dc_info *info);
 int data_costs_normalize(b2tex_ctx *c, float gmax, const uint32_t *bins_host, b2tex_dc_info *info);
 int mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *energy_fixed);
 int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *energy_fixed);

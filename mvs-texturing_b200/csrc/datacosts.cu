@@ -585,6 +585,56 @@ float cos75_threshold()
 
 }  // namespace
 
+// qualities of all candidates are known: photometric outlier removal (optional), drop quality 0, compact to the
+// DataCosts layout, maximum (calculate_data_costs.cpp:222,265-281)
+static int finish_candidates(b2tex_ctx *c, const b2tex_settings *st, uint64_t num_cand, b2tex_dc_info *info)
+{
+    cudaStream_t s = c->stream;
+    const uint32_t F = c->F, fb = c->face_begin, fe = c->face_end, nf = fe - fb;
+    const uint32_t blocks = (nf + 255) / 256;
+    const bool outlier = st->outlier_removal != 0;
+    DevBuf<uint64_t> &cnt = c->s_cnt64;
+    unsigned long long *ray_count = reinterpret_cast<unsigned long long *>(c->scalars.p + 2);
+    if (outlier && nf) {
+        ScopedTimer tm(c, "k_outlier", 16.0 * (double)num_cand);
+        B2_LAUNCH k_outlier<<<(nf + 127) / 128, 128, 0, s>>>(c->cand_ptr.p, c->cand_q.p, c->cand_ycc.p, c->cand_flag.p, fb, fe,
+                                                   st->outlier_removal, c->scalars.p);
+        B2_KERNEL_CHECK();
+    }
+    {
+        ScopedTimer tm(c, "k_count_survivors", 4.0 * (double)num_cand + 16.0 * F);
+        B2_LAUNCH k_count_survivors<<<(F + 1 + 255) / 256, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, fb, fe, F, cnt.p);
+    }
+    B2_KERNEL_CHECK();
+    B2_TRY(cub_exclusive_sum_u64(c, cnt.p, c->dc_ptr.p, (size_t)F + 1));
+    uint64_t nnz = 0;
+    uint32_t maxbits = 0;
+    unsigned long long rays = 0;
+    B2_CUDA(cudaMemcpyAsync(&nnz, c->dc_ptr.p + F, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaMemcpyAsync(&maxbits, c->scalars.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaMemcpyAsync(&rays, ray_count, sizeof(rays), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    c->nnz = nnz;
+    B2_TRY(c->dc_view.alloc(nnz));
+    B2_TRY(c->dc_quality.alloc(nnz));
+    B2_TRY(c->dc_cost.alloc(nnz));
+    if (nf) {
+        ScopedTimer tm(c, "k_compact", 6.0 * (double)num_cand + 6.0 * (double)nnz + 16.0 * nf);
+        B2_LAUNCH k_compact<<<blocks, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, c->cand_view.p, c->dc_ptr.p, fb, fe,
+                                         c->dc_view.p, c->dc_quality.p);
+    }
+    B2_KERNEL_CHECK();
+    float maxq;
+    memcpy(&maxq, &maxbits, 4);
+    info->nnz = nnz;
+    info->candidates = num_cand;
+    info->rays = rays;
+    info->max_quality = maxq;
+    info->percentile = 0.0f;
+    c->have_costs = false;
+    return B2TEX_OK;
+}
+
 int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *info)
 {
     if (!c->F || !c->K) { set_error("data costs: mesh and views must be set first"); return B2TEX_ERR_ARG; }
@@ -661,44 +711,44 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
                                                     outlier ? c->cand_ycc.p : nullptr);
         B2_KERNEL_CHECK();
     }
-    if (outlier && nf) {
-        ScopedTimer tm(c, "k_outlier", 16.0 * (double)num_cand);
-        B2_LAUNCH k_outlier<<<(nf + 127) / 128, 128, 0, s>>>(c->cand_ptr.p, c->cand_q.p, c->cand_ycc.p, c->cand_flag.p, fb, fe,
-                                                   st->outlier_removal, c->scalars.p);
-        B2_KERNEL_CHECK();
+    return finish_candidates(c, st, num_cand, info);
+}
+
+// maximum of the uploaded qualities (without outlier removal nothing else computes it on this path)
+__global__ void __launch_bounds__(256) k_max_quality(const float *__restrict__ q, uint64_t n, uint32_t *max_q_bits)
+{
+    uint32_t qb = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float v = q[i];
+        if (v == v && v > 0.0f) qb = max(qb, __float_as_uint(v));
     }
-    {
-        ScopedTimer tm(c, "k_count_survivors", 4.0 * (double)num_cand + 16.0 * F);
-        B2_LAUNCH k_count_survivors<<<(F + 1 + 255) / 256, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, fb, fe, F, cnt.p);
-    }
+    for (int s = 16; s; s >>= 1) qb = max(qb, __shfl_xor_sync(0xffffffffu, qb, s));
+    if ((threadIdx.x & 31) == 0 && qb) atomicMax(max_q_bits, qb);
+}
+
+// tex::postprocess_face_infos (calculate_data_costs.cpp:253-306) on candidates the CALLER computed: per face the
+// (view, quality[, mean YCbCr colour]) infos in ascending view order
+int data_costs_postprocess(b2tex_ctx *c, const b2tex_settings *st, uint32_t F, const uint64_t *face_ptr, const uint16_t *view,
+                           const float *quality, const float *mean_ycbcr, b2tex_dc_info *info)
+{
+    if (st->outlier_removal < 0 || st->outlier_removal > 2) { set_error("unknown outlier removal mode"); return B2TEX_ERR_UNSUPPORTED; }
+    const bool outlier = st->outlier_removal != 0;
+    if (outlier && !mean_ycbcr) { set_error("postprocess_face_infos: outlier removal needs the mean colours"); return B2TEX_ERR_ARG; }
+    cudaStream_t s = c->stream;
+    c->F = F; c->face_begin = 0; c->face_end = F;
+    const uint64_t n = face_ptr[F];
+    B2_TRY(c->cand_ptr.upload(face_ptr, (size_t)F + 1, s));
+    B2_TRY(c->cand_view.upload(view, n, s));
+    B2_TRY(c->cand_q.upload(quality, n, s));
+    if (outlier) { B2_TRY(c->cand_ycc.upload(mean_ycbcr, 3 * n, s)); B2_TRY(c->cand_flag.alloc(n)); }
+    B2_TRY(c->dc_ptr.alloc((size_t)F + 1));
+    B2_TRY(c->s_cnt64.alloc((size_t)F + 1));
+    B2_TRY(c->scalars.alloc(std::max<size_t>(c->scalars.n, 256)));
+    B2_CUDA(cudaMemsetAsync(c->scalars.p, 0, 64 * sizeof(uint32_t), s));
+    c->num_cand = n;
+    if (!outlier && n) B2_LAUNCH k_max_quality<<<std::max(1, c->num_sms * 4), 256, 0, s>>>(c->cand_q.p, n, c->scalars.p);
     B2_KERNEL_CHECK();
-    B2_TRY(cub_exclusive_sum_u64(c, cnt.p, c->dc_ptr.p, (size_t)F + 1));
-    uint64_t nnz = 0;
-    uint32_t maxbits = 0;
-    unsigned long long rays = 0;
-    B2_CUDA(cudaMemcpyAsync(&nnz, c->dc_ptr.p + F, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    B2_CUDA(cudaMemcpyAsync(&maxbits, c->scalars.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    B2_CUDA(cudaMemcpyAsync(&rays, ray_count, sizeof(rays), cudaMemcpyDeviceToHost, s));
-    B2_CUDA(cudaStreamSynchronize(s));
-    c->nnz = nnz;
-    B2_TRY(c->dc_view.alloc(nnz));
-    B2_TRY(c->dc_quality.alloc(nnz));
-    B2_TRY(c->dc_cost.alloc(nnz));
-    if (nf) {
-        ScopedTimer tm(c, "k_compact", 6.0 * (double)num_cand + 6.0 * (double)nnz + 16.0 * nf);
-        B2_LAUNCH k_compact<<<blocks, 256, 0, s>>>(c->cand_ptr.p, c->cand_q.p, c->cand_view.p, c->dc_ptr.p, fb, fe,
-                                         c->dc_view.p, c->dc_quality.p);
-    }
-    B2_KERNEL_CHECK();
-    float maxq;
-    memcpy(&maxq, &maxbits, 4);
-    info->nnz = nnz;
-    info->candidates = num_cand;
-    info->rays = rays;
-    info->max_quality = maxq;
-    info->percentile = 0.0f;
-    c->have_costs = false;
-    return B2TEX_OK;
+    return finish_candidates(c, st, n, info);
 }
 
 int data_costs_histogram(b2tex_ctx *c, float gmax)
