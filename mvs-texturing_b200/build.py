@@ -51,8 +51,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 f.write(r.stderr)
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(OUT, objs):
-        subprocess.check_call([nvcc, "-shared", "-o", OUT, *objs, "-ccbin", "/usr/bin/g++",
+        subprocess.check_call([nvcc, "-shared", "-o", OUT + ".tmp", *objs, "-ccbin", "/usr/bin/g++",
                                "-gencode", "arch=compute_100a,code=sm_100a"])
+        os.replace(OUT + ".tmp", OUT)   # atomic: a snapshot of the tree never sees a half-written library
+        import hashlib
+        import time
+        h = hashlib.sha256()
+        for f in sorted(os.listdir(CSRC)):
+            h.update(open(os.path.join(CSRC, f), "rb").read())
+        with open(os.path.join(objdir, "STAMP"), "w") as f:
+            f.write(f"{time.strftime('%Y-%m-%d %H:%M:%S')} csrc {h.hexdigest()[:12]}\n")
     return OUT
 
 

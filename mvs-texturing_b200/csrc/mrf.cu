@@ -80,7 +80,7 @@ struct Mrf {
     uint16_t *olev;              // level of order[i]
     uint32_t *pos;               // index of a node in order, NO_NODE outside the forest
     uint2 *tjoin;                // per node: (tree, arrival number in the tree)
-    uint4 *ttab;                 // per tree: (nodes, labels, first order index, flags: 1 = has a node of degree > 3)
+    uint4 *ttab;                 // per tree: (nodes | has a node of degree > 3 << 31, labels, first order index, message-row entries)
     uint32_t *ctl;               // per-iteration control block (zeroed before k_forest), see CTL_*
     uint32_t *state;             // per-run state, see ST_*
     uint32_t *queue, *qstamp;    // frontier lists [2][F] and push de-duplication stamps [F]
@@ -164,6 +164,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ long long sm_clock() { return clock64(); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // wait until at most `pending` of this thread's committed groups are still in flight
 __device__ __forceinline__ void cp_async_wait_pending(uint32_t pending)
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
             if (is_root) {
                 const uint32_t j = s_base + my;
                 const uint32_t nl = (uint32_t)(m.ptr[v + 1] - m.ptr[v]);
-                m.ttab[j] = make_uint4(1u, nl, 0u, __ldg(&m.adj4[v].w) > 3u ? 1u : 0u);
+                m.ttab[j] = make_uint4(1u | (__ldg(&m.adj4[v].w) > 3u ? 0x80000000u : 0u), nl, 0u, 0u);
                 m.tjoin[v] = make_uint2(j, 0u);
             }
         }
@@ -358,30 +359,74 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
             if (v != NO_NODE && __ldcg(m.level + v) == LVL_NONE) {
                 const Nb nb = load_nb(m, v);
                 uint32_t c = 0, parent = NO_NODE;
-                for (uint32_t i = 0; i < nb.deg; ++i) {
-                    uint32_t w = nb_at(m, nb, i);
-                    if (local_pair(m, v, w) && __ldcg(m.level + w) < r) { ++c; parent = w; }
+                bool win = true;
+                if (nb.deg <= 3) {
+                    // manifold degree: every load of a hop is issued before the first one is used (the round is a chain of
+                    // dependent loads; two hops instead of up to eight round trips)
+                    const uint32_t wn[3] = {nb.x, nb.y, nb.z};
+                    uint32_t lw[3];
+                    bool loc[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        loc[i] = (uint32_t)i < nb.deg && local_pair(m, v, wn[i]);
+                        lw[i] = loc[i] ? __ldcg(m.level + wn[i]) : LVL_DEAD;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (loc[i] && lw[i] < r) { ++c; parent = wn[i]; }
+                    if (c == 1) {
+                        const uint32_t pv = prio(v, seed_t);
+                        bool cont[3];
+                        uint4 a4[3];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {   // undecided (or just joined) local neighbours that are not weaker
+                            cont[i] = loc[i] && (lw[i] == LVL_NONE || lw[i] == r) && !(prio(wn[i], seed_t) < pv);
+                            a4[i] = cont[i] ? __ldg(m.adj4 + wn[i]) : make_uint4(NO_NODE, NO_NODE, NO_NODE, 0u);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            if (!cont[i]) continue;
+                            uint32_t cw = 0;
+                            if (a4[i].w <= 3) {
+                                const uint32_t xn[3] = {a4[i].x, a4[i].y, a4[i].z};
+                                uint32_t lx[3];
+#pragma unroll
+                                for (int j = 0; j < 3; ++j)
+                                    lx[j] = ((uint32_t)j < a4[i].w && local_pair(m, wn[i], xn[j])) ? __ldcg(m.level + xn[j]) : LVL_DEAD;
+#pragma unroll
+                                for (int j = 0; j < 3; ++j) cw += lx[j] < r ? 1u : 0u;
+                            } else cw = count_in_forest(m, wn[i], r);
+                            if (cw == 1) win = false;  // a stronger adjacent candidate: wait
+                        }
+                    }
+                } else {
+                    for (uint32_t i = 0; i < nb.deg; ++i) {
+                        uint32_t w = nb_at(m, nb, i);
+                        if (local_pair(m, v, w) && __ldcg(m.level + w) < r) { ++c; parent = w; }
+                    }
+                    if (c == 1) {
+                        const uint32_t pv = prio(v, seed_t);
+                        for (uint32_t i = 0; i < nb.deg && win; ++i) {
+                            uint32_t w = nb_at(m, nb, i);
+                            if (!local_pair(m, v, w)) continue;
+                            uint32_t lw = __ldcg(m.level + w);
+                            if (!(lw == LVL_NONE || lw == r)) continue;
+                            if (prio(w, seed_t) < pv) continue;
+                            if (count_in_forest(m, w, r) == 1) win = false;  // a stronger adjacent candidate: wait
+                        }
+                    }
                 }
                 if (c >= 2) m.level[v] = LVL_DEAD;
                 else if (c == 1) {
-                    const uint32_t pv = prio(v, seed_t);
-                    bool win = true;
-                    for (uint32_t i = 0; i < nb.deg && win; ++i) {
-                        uint32_t w = nb_at(m, nb, i);
-                        if (!local_pair(m, v, w)) continue;
-                        uint32_t lw = __ldcg(m.level + w);
-                        if (!(lw == LVL_NONE || lw == r)) continue;
-                        if (prio(w, seed_t) < pv) continue;
-                        if (count_in_forest(m, w, r) == 1) win = false;  // a stronger adjacent candidate: wait
-                    }
                     if (win) {
                         m.level[v] = r;
                         if (build_trees) {   // the parent joined in an earlier round: its (tree, slot) is final
                             const uint2 pj = __ldcg(m.tjoin + parent);
                             uint4 *te = m.ttab + pj.x;
-                            const uint32_t slot = atomicAdd(&te->x, 1u);
+                            const uint32_t slot = atomicAdd(&te->x, 1u) & 0x7FFFFFFFu;
                             atomicAdd(&te->y, (uint32_t)(m.ptr[v + 1] - m.ptr[v]));
-                            if (nb.deg > 3) atomicOr(&te->w, 1u);
+                            atomicAdd(&te->w, (uint32_t)(m.ptr[parent + 1] - m.ptr[parent]));   // its message row: one entry per label of the parent
+                            if (nb.deg > 3) atomicOr(&te->x, 0x80000000u);
                             m.tjoin[v] = make_uint2(pj.x, slot);
                         }
                         if (r < m.rounds)
@@ -406,7 +451,7 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
     const uint32_t nroots = __ldcg(m.ctl + CTL_NROOTS);
     for (uint32_t base = blockIdx.x * blockDim.x; base < nroots; base += nth) {
         const uint32_t j = base + threadIdx.x;
-        const uint32_t cnt = j < nroots ? __ldcg(&m.ttab[j].x) : 0u;
+        const uint32_t cnt = j < nroots ? (__ldcg(&m.ttab[j].x) & 0x7FFFFFFFu) : 0u;
         uint32_t incl = cnt;
         for (int s = 1; s < 32; s <<= 1) {
             uint32_t o = __shfl_up_sync(0xffffffffu, incl, s);
@@ -450,52 +495,61 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
 }
 
 // ---- min-sum DP of whole trees in shared memory ------------------------------------------------------------------
-constexpr int TREE_THREADS = 256;
+constexpr int TREE_THREADS = 512;
 constexpr int TREE_WARPS = TREE_THREADS / 32;
 constexpr int TREE_CHUNK = 32;       // trees claimed per global atomic (<= 8 staged per warp: cp_async_wait_pending)
 constexpr uint32_t NBR_SKIP = 0u, NBR_CHILD = 1u << 30, NBR_FIXED = 2u << 30, NBR_PARENT = 3u << 30;
 constexpr uint32_t NBR_KIND = 3u << 30, NBR_ARG = ~NBR_KIND;
 
-// upper bound of the shared memory one tree needs (the exact rows are padded to the 16-byte granules of the async
-// copies: <= 6 extra floats and <= 14 extra u16 per node)
+// upper bound of the shared memory one tree needs (cost / view rows are padded to the 16-byte granules of the async
+// copies: <= 6 extra floats and <= 14 extra u16 per node; index rows have one entry per label of the PARENT:
+// `msum` = sum over the non-root nodes of the parent's label count, accumulated by k_forest)
 __host__ __device__ __forceinline__ uint32_t tree_hcap(uint32_t cnt, uint32_t nnz) { return (nnz + 6u * cnt + 3u) & ~3u; }
 __host__ __device__ __forceinline__ uint32_t tree_vcap(uint32_t cnt, uint32_t nnz) { return (nnz + 14u * cnt + 7u) & ~7u; }
-__host__ __device__ __forceinline__ uint32_t tree_node_bytes(uint32_t W) { return 42u + 6u * W; }
+__host__ __device__ __forceinline__ uint32_t tree_mcap(uint32_t msum) { return (msum + 7u) & ~7u; }   // keeps the view rows behind it 16-byte aligned
+constexpr uint32_t TREE_NODE_BYTES = 56u;   // per-node tables below
+__host__ __device__ __forceinline__ uint64_t tree_bytes(uint32_t cnt, uint32_t hcap, uint32_t vcap, uint32_t mcap)
+{
+    return 4ull * hcap + 2ull * vcap + 2ull * mcap + (uint64_t)cnt * TREE_NODE_BYTES;
+}
 
 struct TreeStatic {
-    uint32_t t_cnt[TREE_CHUNK], t_nnz[TREE_CHUNK], t_start[TREE_CHUNK], t_flags[TREE_CHUNK];
-    uint32_t t_node0[TREE_CHUNK], t_h0[TREE_CHUNK], t_v0[TREE_CHUNK], t_slow[TREE_CHUNK];
-    uint32_t chunk_first, sb_n, sb_nodes, sb_hcap, sb_vcap;
-    uint32_t scan_carry;
+    uint32_t t_cnt[TREE_CHUNK], t_nnz[TREE_CHUNK], t_start[TREE_CHUNK], t_msum[TREE_CHUNK];
+    uint32_t t_node0[TREE_CHUNK], t_h0[TREE_CHUNK], t_v0[TREE_CHUNK], t_m0[TREE_CHUNK], t_slow[TREE_CHUNK];
+    uint32_t chunk_first, sb_n, sb_nodes, sb_hcap, sb_vcap, sb_mcap;
+    long long c_prep, c_up, c_down;   // diagnostic cycle counters (thread 0)
     uint16_t lstart[MAX_LEVELS + 2];   // first slot of every level in lnode (sub-batch wide level buckets)
     uint16_t lfill[MAX_LEVELS + 2];
 };
 
 // pointers into the dynamic shared memory of one sub-batch
 struct TreePool {
-    float *H;          // [hcap]   cost rows, turned into the min-sum tables in place
-    uint16_t *V;       // [vcap]   view rows
-    uint32_t *gid, *hoff, *voff, *nbr, *am, *lab, *mask;
+    float *H;          // [hcap]  cost rows, turned into the min-sum tables in place
+    uint16_t *V;       // [vcap]  view rows
+    uint16_t *J;       // [mcap]  per non-root node: position of every label of the PARENT in the node's own row, 0xFFFF = absent
+    uint32_t *gid, *hoff, *voff, *moff, *nbr, *am, *plo, *phi;   // plo / phi: first entry of the node's rows in the global arrays
     float *hm;
-    uint16_t *nlab, *lev, *mpre;
+    uint16_t *nlab, *lev, *np;
     uint16_t *lnode;   // the nodes of the sub-batch bucketed by level
 };
-__device__ __forceinline__ TreePool carve_pool(unsigned char *base, uint32_t nodes, uint32_t hcap, uint32_t vcap, uint32_t W)
+__device__ __forceinline__ TreePool carve_pool(unsigned char *base, uint32_t nodes, uint32_t hcap, uint32_t vcap, uint32_t mcap)
 {
     TreePool p;
     p.H = reinterpret_cast<float *>(base); base += (size_t)hcap * 4;
     p.V = reinterpret_cast<uint16_t *>(base); base += (size_t)vcap * 2;
+    p.J = reinterpret_cast<uint16_t *>(base); base += (size_t)mcap * 2;
     p.gid = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
     p.hoff = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
     p.voff = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
+    p.moff = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
     p.nbr = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 12;
     p.am = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
-    p.lab = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
+    p.plo = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
+    p.phi = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
     p.hm = reinterpret_cast<float *>(base); base += (size_t)nodes * 4;
-    p.mask = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4 * W;
     p.nlab = reinterpret_cast<uint16_t *>(base); base += (size_t)nodes * 2;
     p.lev = reinterpret_cast<uint16_t *>(base); base += (size_t)nodes * 2;
-    p.mpre = reinterpret_cast<uint16_t *>(base); base += (size_t)nodes * 2 * W;
+    p.np = reinterpret_cast<uint16_t *>(base); base += (size_t)nodes * 2;
     p.lnode = reinterpret_cast<uint16_t *>(base);
     return p;
 }
@@ -531,55 +585,85 @@ __device__ __forceinline__ uint32_t level_run_end(LevPtr lev, uint32_t s, uint32
     return e;
 }
 
-// position of label `lab` in a shared-memory row: bitmask + prefix popcount, or binary search without masks
-__device__ __forceinline__ int row_find(const TreePool &p, uint32_t W, uint32_t li, uint32_t lab)
+// Staging, phase 1 -- one THREAD per node of the sub-batch: everything that needs global memory round trips (node id ->
+// row extents, adjacency -> labels and forest positions of the three neighbours), all nodes at once.
+__device__ void batch_load_nodes(const Mrf &m, const TreePool &p, const TreeStatic &ts, uint32_t done, uint32_t sb_n, uint32_t N)
 {
-    if (W) {
-        const uint32_t word = lab >> 5, bit = lab & 31u;
-        if (word >= W) return -1;
-        const uint32_t bits = p.mask[(size_t)li * W + word];
-        if (!((bits >> bit) & 1u)) return -1;
-        return (int)((uint32_t)p.mpre[(size_t)li * W + word] + __popc(bits & ((1u << bit) - 1u)));
+    for (uint32_t li = threadIdx.x; li < N; li += TREE_THREADS) {
+        uint32_t t = done;
+        for (uint32_t i = done; i < done + sb_n; ++i)   // node0 ascends over the staged trees of the sub-batch
+            if (!ts.t_slow[i] && ts.t_node0[i] <= li) t = i;
+        const uint32_t node0 = ts.t_node0[t], start = ts.t_start[t], i = li - node0;
+        const uint32_t v = m.order[start + i];
+        const uint32_t lv = m.olev[start + i];
+        const uint64_t p0 = m.ptr[v];
+        const uint32_t n = (uint32_t)(m.ptr[v + 1] - p0);
+        const uint4 a4 = __ldg(m.adj4 + v);
+        // all six neighbour loads first (independent), classification afterwards
+        uint32_t xl[3] = {0u, 0u, 0u}, pl[3] = {NO_NODE, NO_NODE, NO_NODE};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const uint32_t w = a == 0 ? a4.x : (a == 1 ? a4.y : a4.z);
+            if ((uint32_t)a < a4.w && w != NO_NODE) { xl[a] = m.labels[w]; pl[a] = m.pos[w]; }
+        }
+        p.gid[li] = v;
+        p.nlab[li] = (uint16_t)n;
+        p.lev[li] = (uint16_t)lv;
+        p.plo[li] = (uint32_t)p0;
+        p.phi[li] = (uint32_t)(p0 >> 32);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            uint32_t enc = NBR_SKIP;
+            if (xl[a] != 0u) {   // unseen faces carry no edges (view_selection.cpp:30,35)
+                if (pl[a] != NO_NODE) {   // a forest neighbour is in the same tree: deeper = child
+                    const uint32_t lj = pl[a] - start;
+                    enc = (lj > i ? NBR_CHILD : NBR_PARENT) | (node0 + lj);
+                } else enc = NBR_FIXED | xl[a];
+            }
+            p.nbr[3 * li + a] = enc;
+        }
     }
-    const uint16_t *row = p.V + p.voff[li];
-    int lo = 0, n = (int)p.nlab[li], hi = n;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if ((uint32_t)row[mid] + 1u < lab) lo = mid + 1; else hi = mid;
-    }
-    return (lo < n && (uint32_t)row[lo] + 1u == lab) ? lo : -1;
 }
 
-// stage one tree: node tables + asynchronous 16-byte copies of its cost and view rows (one commit group per tree)
-__device__ void tree_stage(const Mrf &m, const TreePool &p, uint32_t start, uint32_t cnt, uint32_t node0, uint32_t h0,
-                           uint32_t v0, uint32_t lane)
+// Staging, phase 2 -- one WARP per tree, shared memory only: row offsets by prefix sums, asynchronous 16-byte copies of the
+// cost and view rows (from the aligned-down start of every row), offsets of the index rows
+__device__ void tree_layout(const Mrf &m, const TreePool &p, uint32_t cnt, uint32_t node0, uint32_t h0, uint32_t v0, uint32_t m0,
+                            uint32_t lane)
 {
-    uint32_t hcarry = h0, vcarry = v0;
+    uint32_t hcarry = h0, vcarry = v0, mcarry = m0;
     const uint32_t half = lane >> 4, sl = lane & 15u;   // two rows per step, 16 lanes (= 16 chunks of 16 bytes) each
     for (uint32_t c = 0; c < cnt; c += 32) {
-        const uint32_t i = c + lane;
+        const uint32_t i = c + lane, li = node0 + i;
         const bool valid = i < cnt;
-        uint32_t v = 0, lv = 0, n = 0, hsz = 0, vsz = 0;
+        uint32_t n = 0, hsz = 0, vsz = 0, npar = 0;
         uint64_t p0 = 0;
-        uint4 a4 = make_uint4(NO_NODE, NO_NODE, NO_NODE, 0u);
         if (valid) {
-            v = m.order[start + i];
-            lv = m.olev[start + i];
-            p0 = m.ptr[v];
-            n = (uint32_t)(m.ptr[v + 1] - p0);
-            a4 = __ldg(m.adj4 + v);
+            n = p.nlab[li];
+            p0 = ((uint64_t)p.phi[li] << 32) | p.plo[li];
             hsz = ((uint32_t)(p0 & 3u) + n + 3u) & ~3u;
             vsz = ((uint32_t)(p0 & 7u) + n + 7u) & ~7u;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const uint32_t en = p.nbr[3 * li + a];
+                if ((en & NBR_KIND) == NBR_PARENT) npar = p.nlab[en & NBR_ARG];
+            }
         }
-        uint32_t hi = hsz, vi = vsz;
+        uint32_t hi = hsz, vi = vsz, mi = npar;
         for (int s = 1; s < 32; s <<= 1) {
-            const uint32_t oh = __shfl_up_sync(0xffffffffu, hi, s), ov = __shfl_up_sync(0xffffffffu, vi, s);
-            if ((int)lane >= s) { hi += oh; vi += ov; }
+            const uint32_t oh = __shfl_up_sync(0xffffffffu, hi, s), ov = __shfl_up_sync(0xffffffffu, vi, s),
+                           om = __shfl_up_sync(0xffffffffu, mi, s);
+            if ((int)lane >= s) { hi += oh; vi += ov; mi += om; }
         }
         const uint32_t ho = hcarry + hi - hsz, vo = vcarry + vi - vsz;
+        if (valid) {
+            p.hoff[li] = ho + (uint32_t)(p0 & 3u);
+            p.voff[li] = vo + (uint32_t)(p0 & 7u);
+            p.moff[li] = mcarry + mi - npar;
+            p.np[li] = (uint16_t)npar;
+        }
         hcarry += __shfl_sync(0xffffffffu, hi, 31);
         vcarry += __shfl_sync(0xffffffffu, vi, 31);
-        // the rows of this group of <= 32 nodes: 16-byte chunks from the aligned-down start of every row
+        mcarry += __shfl_sync(0xffffffffu, mi, 31);
         const uint32_t rows = min(32u, cnt - c);
         const unsigned long long src_c = (unsigned long long)(m.cost + (p0 & ~(uint64_t)3));
         const unsigned long long src_v = (unsigned long long)(m.view + (p0 & ~(uint64_t)7));
@@ -593,73 +677,53 @@ __device__ void tree_stage(const Mrf &m, const TreePool &p, uint32_t start, uint
                 for (uint32_t q = sl; q < vch; q += 16) cp_async16(p.V + rvo + 8u * q, (const uint16_t *)sv + 8u * q);
             }
         }
-        if (valid) {
-            const uint32_t li = node0 + i;
-            p.gid[li] = v;
-            p.hoff[li] = ho + (uint32_t)(p0 & 3u);
-            p.voff[li] = vo + (uint32_t)(p0 & 7u);
-            p.nlab[li] = (uint16_t)n;
-            p.lev[li] = (uint16_t)lv;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const uint32_t w = a == 0 ? a4.x : (a == 1 ? a4.y : a4.z);
-                uint32_t enc = NBR_SKIP;
-                if ((uint32_t)a < a4.w && w != NO_NODE) {
-                    const uint32_t x = m.labels[w];
-                    if (x != 0u) {  // unseen faces carry no edges (view_selection.cpp:30,35)
-                        const uint32_t pw = m.pos[w];
-                        if (pw != NO_NODE) {   // a forest neighbour is in the same tree: deeper = child
-                            const uint32_t lj = pw - start;
-                            enc = (lj > i ? NBR_CHILD : NBR_PARENT) | (node0 + lj);
-                        } else enc = NBR_FIXED | x;
-                    }
-                }
-                p.nbr[3 * (size_t)li + a] = enc;
-            }
-        }
     }
     cp_async_commit();
 }
 
 // The DP of ALL staged trees of a sub-batch at once, by the whole CTA: the trees are independent, so one level of all of
-// them is one parallel step (a single tree has only ~3 nodes per level: solved alone it would leave its warp idle in
-// a chain of dependent shared-memory round trips).  Nodes are bucketed by level across the sub-batch; the bottom-up
-// sweep gives every node G lanes (min / arg-min by shuffles inside the group), the top-down sweep one thread.
+// them is one parallel step (a single tree has only ~3 nodes per level).  Nodes are bucketed by level across the
+// sub-batch.  Bottom-up, a node gets G lanes: h(l) = cost(l) + the terms of its neighbours in adjacency order -- a child c
+// contributes the Potts message min(h_c(l), hmin_c + 1), found through the child's index row J_c (where each label of
+// THIS node sits in the child's row; built once per sub-batch by merging the two sorted label lists, so the inner loop
+// has no search), a fixed neighbour 0 or 1 -- then min / arg-min by shuffles.  Top-down one thread per node.
 template <int G>
-__device__ void batch_solve(const Mrf &m, const TreePool &p, TreeStatic &ts, uint32_t N, uint32_t W)
+__device__ void batch_solve(const Mrf &m, const TreePool &p, TreeStatic &ts, uint32_t N)
 {
     constexpr uint32_t NG = TREE_THREADS / G;   // nodes in flight per step
     const uint32_t tid = threadIdx.x, lane = tid & 31u, glane = tid & (G - 1), group = tid / G;
     const uint32_t nlev = m.rounds + 1u;
-    // ---- label bitmasks of every row + level histogram ----
-    for (uint32_t i = tid; i < N * W; i += TREE_THREADS) p.mask[i] = 0u;
+    const bool prof = m.dbg != nullptr && tid == 0;
+    long long tc = prof ? sm_clock() : 0;
+    // ---- level histogram (two 16-bit counters per word) ----
     for (uint32_t i = tid; i <= nlev; i += TREE_THREADS) ts.lfill[i] = 0;
     __syncthreads();
-    if (W)
-        for (uint32_t base = 0; base < N; base += NG) {
-            const uint32_t li = base + group;
-            if (li < N) {
-                const uint16_t *row = p.V + p.voff[li];
-                const uint32_t n = p.nlab[li];
-                for (uint32_t k = glane; k < n; k += G) {
-                    const uint32_t lab = (uint32_t)row[k] + 1u;
-                    atomicOr(&p.mask[(size_t)li * W + (lab >> 5)], 1u << (lab & 31u));
-                }
-            }
-        }
-    for (uint32_t li = tid; li < N; li += TREE_THREADS) {   // counts as uint32 pairs would race: 16-bit atomics via CAS-free trick
+    for (uint32_t li = tid; li < N; li += TREE_THREADS) {
         const uint32_t l = p.lev[li];
-        atomicAdd(reinterpret_cast<uint32_t *>(ts.lfill) + (l >> 1), (l & 1u) ? 0x10000u : 1u);   // two 16-bit counters per word
+        atomicAdd(reinterpret_cast<uint32_t *>(ts.lfill) + (l >> 1), (l & 1u) ? 0x10000u : 1u);
+    }
+    // ---- index rows: merge of the parent's and the node's sorted label lists (one thread per non-root node) ----
+    for (uint32_t li = tid; li < N; li += TREE_THREADS) {
+        const uint32_t npar = p.np[li];
+        if (!npar) continue;
+        uint32_t par = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const uint32_t en = p.nbr[3 * li + a];
+            if ((en & NBR_KIND) == NBR_PARENT) par = en & NBR_ARG;
+        }
+        const uint16_t *pv = p.V + p.voff[par], *cv = p.V + p.voff[li];
+        uint16_t *J = p.J + p.moff[li];
+        const uint32_t n = p.nlab[li];
+        uint32_t j = 0;
+        for (uint32_t k = 0; k < npar; ++k) {
+            const uint32_t want = pv[k];
+            while (j < n && cv[j] < want) ++j;
+            J[k] = (j < n && cv[j] == want) ? (uint16_t)j : (uint16_t)0xFFFFu;
+        }
     }
     __syncthreads();
-    for (uint32_t li = tid; li < N; li += TREE_THREADS) {
-        uint32_t seen = 0;
-        for (uint32_t w = 0; w < W; ++w) {
-            p.mpre[(size_t)li * W + w] = (uint16_t)seen;
-            seen += __popc(p.mask[(size_t)li * W + w]);
-        }
-    }
-    if (tid < 32) {   // exclusive scan of the level counts -> lstart; lfill restarts at lstart
+    if (tid < 32) {   // exclusive scan of the level counts -> lstart
         uint32_t carry = 0;
         for (uint32_t base = 0; base <= nlev; base += 32) {
             const uint32_t i = base + lane;
@@ -683,6 +747,7 @@ __device__ void batch_solve(const Mrf &m, const TreePool &p, TreeStatic &ts, uin
         p.lnode[(l & 1u) ? (old >> 16) : (old & 0xFFFFu)] = (uint16_t)li;
     }
     __syncthreads();
+    if (prof) { const long long t = sm_clock(); ts.c_prep += t - tc; tc = t; }
     // ---- bottom-up: deepest level first ----
     for (uint32_t L = nlev; L-- > 0;) {
         const uint32_t s = ts.lstart[L], e = ts.lstart[L + 1];
@@ -691,35 +756,36 @@ __device__ void batch_solve(const Mrf &m, const TreePool &p, TreeStatic &ts, uin
             const uint32_t idx = base + group;
             const bool act = idx < e;
             float bh = INFINITY;
-            uint32_t bk = 0xFFFFFFFFu, li = 0;
+            uint32_t bk = 0xFFFFFFFFu, li = 0, n = 0;
+            float *Hv = p.H;
             if (act) {
                 li = p.lnode[idx];
-                const uint32_t n = p.nlab[li];
-                float *Hv = p.H + p.hoff[li];
+                n = p.nlab[li];
+                Hv = p.H + p.hoff[li];
                 const uint16_t *viewv = p.V + p.voff[li];
-                uint32_t kind[3], arg[3], cho[3] = {0, 0, 0};
-                float chm[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const uint32_t en = p.nbr[3 * (size_t)li + i];
-                    kind[i] = en & NBR_KIND; arg[i] = en & NBR_ARG;
-                    if (kind[i] == NBR_CHILD) { chm[i] = p.hm[arg[i]]; cho[i] = p.hoff[arg[i]]; }
-                }
+                const uint32_t e0 = p.nbr[3 * li], e1 = p.nbr[3 * li + 1], e2 = p.nbr[3 * li + 2];
+                // per neighbour slot: a child (its index row, table and hmin + 1), a fixed label (0 = none: labels start
+                // at 1), or nothing
+                const bool c0 = (e0 & NBR_KIND) == NBR_CHILD, c1 = (e1 & NBR_KIND) == NBR_CHILD, c2 = (e2 & NBR_KIND) == NBR_CHILD;
+                const uint32_t a0 = e0 & NBR_ARG, a1 = e1 & NBR_ARG, a2 = e2 & NBR_ARG;
+                const uint16_t *j0 = c0 ? p.J + p.moff[a0] : nullptr, *j1 = c1 ? p.J + p.moff[a1] : nullptr,
+                               *j2 = c2 ? p.J + p.moff[a2] : nullptr;
+                const float *h0 = c0 ? p.H + p.hoff[a0] : nullptr, *h1 = c1 ? p.H + p.hoff[a1] : nullptr,
+                            *h2 = c2 ? p.H + p.hoff[a2] : nullptr;
+                const float g0 = c0 ? p.hm[a0] : 0.0f, g1 = c1 ? p.hm[a1] : 0.0f, g2 = c2 ? p.hm[a2] : 0.0f;
+                const uint32_t x0 = (e0 & NBR_KIND) == NBR_FIXED ? a0 : 0u;
+                const uint32_t x1 = (e1 & NBR_KIND) == NBR_FIXED ? a1 : 0u;
+                const uint32_t x2 = (e2 & NBR_KIND) == NBR_FIXED ? a2 : 0u;
 #pragma unroll 2
                 for (uint32_t k = glane; k < n; k += G) {
                     const uint32_t lab = (uint32_t)viewv[k] + 1u;
                     float h = Hv[k];
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        if (kind[i] == NBR_CHILD) {  // Potts message min(h_w(lab), hmin_w + 1)
-                            float msg = chm[i];
-                            const int j = row_find(p, W, arg[i], lab);
-                            if (j >= 0) { const float hw = p.H[cho[i] + (uint32_t)j]; if (hw < msg) msg = hw; }
-                            h = h + msg;
-                        } else if (kind[i] == NBR_FIXED) {
-                            h = h + (lab != arg[i] ? 1.0f : 0.0f);
-                        }
-                    }
+                    if (c0) { float msg = g0; const uint32_t j = j0[k]; if (j != 0xFFFFu) { const float hw = h0[j]; if (hw < msg) msg = hw; } h = h + msg; }
+                    else if (x0) h = h + (lab != x0 ? 1.0f : 0.0f);
+                    if (c1) { float msg = g1; const uint32_t j = j1[k]; if (j != 0xFFFFu) { const float hw = h1[j]; if (hw < msg) msg = hw; } h = h + msg; }
+                    else if (x1) h = h + (lab != x1 ? 1.0f : 0.0f);
+                    if (c2) { float msg = g2; const uint32_t j = j2[k]; if (j != 0xFFFFu) { const float hw = h2[j]; if (hw < msg) msg = hw; } h = h + msg; }
+                    else if (x2) h = h + (lab != x2 ? 1.0f : 0.0f);
                     Hv[k] = h;
                     if (h < bh) { bh = h; bk = k; }
                 }
@@ -733,31 +799,33 @@ __device__ void batch_solve(const Mrf &m, const TreePool &p, TreeStatic &ts, uin
         }
         __syncthreads();
     }
-    // ---- top-down: shallowest level first, one thread per node ----
+    if (prof) { const long long t = sm_clock(); ts.c_up += t - tc; tc = t; }
+    // ---- top-down: shallowest level first, one thread per node; am becomes the position of the chosen label ----
     for (uint32_t L = 0; L < nlev; ++L) {
         const uint32_t s = ts.lstart[L], e = ts.lstart[L + 1];
         if (s == e) continue;
         for (uint32_t idx = s + tid; idx < e; idx += TREE_THREADS) {
             const uint32_t li = p.lnode[idx];
             uint32_t bk = p.am[li];
+            if (p.np[li]) {
+                uint32_t par = 0;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const uint32_t en = p.nbr[3 * (size_t)li + i];
-                if ((en & NBR_KIND) == NBR_PARENT) {
-                    const uint32_t xp = p.lab[en & NBR_ARG];
-                    const int j = row_find(p, W, li, xp);
-                    if (j >= 0 && p.H[p.hoff[li] + (uint32_t)j] <= p.hm[li]) bk = (uint32_t)j;
+                for (int a = 0; a < 3; ++a) {
+                    const uint32_t en = p.nbr[3 * li + a];
+                    if ((en & NBR_KIND) == NBR_PARENT) par = en & NBR_ARG;
                 }
+                const uint32_t j = p.J[p.moff[li] + p.am[par]];   // the parent's label in this node's row
+                if (j != 0xFFFFu && p.H[p.hoff[li] + j] <= p.hm[li]) bk = j;
             }
             p.am[li] = bk;
-            p.lab[li] = (uint32_t)p.V[p.voff[li] + bk] + 1u;
         }
         __syncthreads();
     }
+    if (prof) { const long long t = sm_clock(); ts.c_down += t - tc; tc = t; }
     for (uint32_t li = tid; li < N; li += TREE_THREADS) {
-        const uint32_t v = p.gid[li];
-        m.labels[v] = p.lab[li];
-        m.lidx[v] = p.am[li];
+        const uint32_t v = p.gid[li], bk = p.am[li];
+        m.labels[v] = (uint32_t)p.V[p.voff[li] + bk] + 1u;
+        m.lidx[v] = bk;
     }
 }
 
@@ -836,8 +904,13 @@ __global__ void __launch_bounds__(TREE_THREADS) k_tree(Mrf m)
     extern __shared__ __align__(16) unsigned char tree_dyn[];
     __shared__ TreeStatic ts;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t W = m.mask_words;
     const uint32_t nroots = m.ctl[CTL_NROOTS];
+    // diagnostic (B2TEX_FOREST_TIMING): cycles thread 0 of every CTA spends per phase, summed over CTAs and launches
+    const bool prof = m.dbg != nullptr && threadIdx.x == 0;
+    long long tc = prof ? sm_clock() : 0, c_claim = 0, c_stage = 0, c_solve = 0;
+    unsigned long long n_sb = 0, max_nodes = 0;
+    auto lap = [&](long long &acc) { if (prof) { const long long t = sm_clock(); acc += t - tc; tc = t; } };
+    if (threadIdx.x == 0) { ts.c_prep = 0; ts.c_up = 0; ts.c_down = 0; }
     for (;;) {
         if (threadIdx.x == 0) ts.chunk_first = atomicAdd(&m.ctl[CTL_CLAIM], (uint32_t)TREE_CHUNK);
         __syncthreads();
@@ -846,45 +919,63 @@ __global__ void __launch_bounds__(TREE_THREADS) k_tree(Mrf m)
         const uint32_t nchunk = min((uint32_t)TREE_CHUNK, nroots - first);
         if (threadIdx.x < nchunk) {
             const uint4 t = m.ttab[first + threadIdx.x];
-            ts.t_cnt[threadIdx.x] = t.x; ts.t_nnz[threadIdx.x] = t.y; ts.t_start[threadIdx.x] = t.z; ts.t_flags[threadIdx.x] = t.w;
+            ts.t_cnt[threadIdx.x] = t.x; ts.t_nnz[threadIdx.x] = t.y; ts.t_start[threadIdx.x] = t.z; ts.t_msum[threadIdx.x] = t.w;
         }
         __syncthreads();
         for (uint32_t done = 0; done < nchunk;) {
             if (threadIdx.x == 0) {   // pack the next trees of the chunk into the pool, in order
-                uint32_t n = 0, nodes = 0, hcap = 0, vcap = 0, slow = 0;
+                uint32_t n = 0, nodes = 0, hcap = 0, vcap = 0, mcap = 0, slow = 0;
                 while (done + n < nchunk) {
-                    const uint32_t i = done + n, cnt = ts.t_cnt[i], nnz = ts.t_nnz[i];
-                    const uint32_t hc = tree_hcap(cnt, nnz), vc = tree_vcap(cnt, nnz);
-                    const uint64_t alone = 4ull * hc + 2ull * vc + (uint64_t)cnt * tree_node_bytes(W);
-                    if ((ts.t_flags[i] & 1u) || alone > m.tree_smem || cnt > 16384u) {   // through global memory
-                        ts.t_slow[i] = 1u; ts.t_node0[i] = 0; ts.t_h0[i] = 0; ts.t_v0[i] = 0;
+                    const uint32_t i = done + n, cnt = ts.t_cnt[i] & 0x7FFFFFFFu, nnz = ts.t_nnz[i];
+                    const uint32_t hc = tree_hcap(cnt, nnz), vc = tree_vcap(cnt, nnz), mc = tree_mcap(ts.t_msum[i]);
+                    if ((ts.t_cnt[i] >> 31) || tree_bytes(cnt, hc, vc, mc) > m.tree_smem || cnt > 16384u) {   // through global memory
+                        ts.t_slow[i] = 1u; ts.t_node0[i] = 0; ts.t_h0[i] = 0; ts.t_v0[i] = 0; ts.t_m0[i] = 0;
                         ++n; ++slow;
                         continue;
                     }
-                    const uint64_t bytes = 4ull * (hcap + hc) + 2ull * (vcap + vc) + (uint64_t)(nodes + cnt) * tree_node_bytes(W);
-                    if (bytes > m.tree_smem) break;
-                    ts.t_slow[i] = 0u; ts.t_node0[i] = nodes; ts.t_h0[i] = hcap; ts.t_v0[i] = vcap;
-                    nodes += cnt; hcap += hc; vcap += vc;
+                    if (tree_bytes(nodes + cnt, hcap + hc, vcap + vc, mcap + mc) > m.tree_smem) break;
+                    ts.t_slow[i] = 0u; ts.t_node0[i] = nodes; ts.t_h0[i] = hcap; ts.t_v0[i] = vcap; ts.t_m0[i] = mcap;
+                    nodes += cnt; hcap += hc; vcap += vc; mcap += mc;
                     ++n;
                 }
-                ts.sb_n = n; ts.sb_nodes = nodes; ts.sb_hcap = hcap; ts.sb_vcap = vcap;
+                ts.sb_n = n; ts.sb_nodes = nodes; ts.sb_hcap = hcap; ts.sb_vcap = vcap; ts.sb_mcap = mcap;
                 if (slow) atomicAdd(m.state + ST_SLOW, slow);
             }
             __syncthreads();
+            lap(c_claim);
             const uint32_t sb_n = ts.sb_n;
-            const TreePool pool = carve_pool(tree_dyn, ts.sb_nodes, ts.sb_hcap, ts.sb_vcap, W);
+            const TreePool pool = carve_pool(tree_dyn, ts.sb_nodes, ts.sb_hcap, ts.sb_vcap, ts.sb_mcap);
             // trees that do not fit (or hold a node of degree > 3) go through global memory, one warp each; the others
-            // are staged warp by warp (asynchronous copies) and then solved together by the whole CTA
+            // are staged (global round trips by one thread per node, row copies by one warp per tree) and then solved
+            // together by the whole CTA
+            batch_load_nodes(m, pool, ts, done, sb_n, ts.sb_nodes);
+            __syncthreads();
             for (uint32_t i = done + warp; i < done + sb_n; i += TREE_WARPS) {
-                if (ts.t_slow[i]) tree_solve_global(m, ts.t_start[i], ts.t_cnt[i], lane);
-                else tree_stage(m, pool, ts.t_start[i], ts.t_cnt[i], ts.t_node0[i], ts.t_h0[i], ts.t_v0[i], lane);
+                const uint32_t cnt = ts.t_cnt[i] & 0x7FFFFFFFu;
+                if (ts.t_slow[i]) tree_solve_global(m, ts.t_start[i], cnt, lane);
+                else tree_layout(m, pool, cnt, ts.t_node0[i], ts.t_h0[i], ts.t_v0[i], ts.t_m0[i], lane);
             }
             cp_async_wait_pending(0);
             __syncthreads();
-            if (ts.sb_nodes) batch_solve<G>(m, pool, ts, ts.sb_nodes, W);
+            lap(c_stage);
+            if (ts.sb_nodes) batch_solve<G>(m, pool, ts, ts.sb_nodes);
             __syncthreads();
+            lap(c_solve);
+            ++n_sb;
+            if (ts.sb_nodes > max_nodes) max_nodes = ts.sb_nodes;
             done += sb_n;
         }
+    }
+    if (prof) {
+        atomicAdd(m.dbg + 8, (unsigned long long)c_claim);
+        atomicAdd(m.dbg + 9, (unsigned long long)c_stage);
+        atomicAdd(m.dbg + 10, (unsigned long long)c_solve);
+        atomicAdd(m.dbg + 11, n_sb);
+        atomicMax(m.dbg + 12, max_nodes);
+        atomicAdd(m.dbg + 13, 1ull);
+        atomicAdd(m.dbg + 14, (unsigned long long)ts.c_prep);
+        atomicAdd(m.dbg + 15, (unsigned long long)ts.c_up);
+        atomicAdd(m.dbg + 7, (unsigned long long)ts.c_down);
     }
 }
 
@@ -1247,7 +1338,9 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
         B2_TRY(g->elocal.alloc(MRF_SLOTS));
         B2_TRY(g->halo_list.alloc(n)); B2_TRY(g->halo_mask.alloc(n)); B2_TRY(g->halo_cnt.alloc(1));
     }
-    if (!c->mrf_host_flags) B2_CUDA(cudaHostAlloc((void **)&c->mrf_host_flags, 64 * sizeof(uint32_t), cudaHostAllocDefault));
+    // pinned: [0, 64) stop flags the host polls, then a read-back area (a cudaMemcpyAsync to PAGEABLE memory waits for the
+    // stream inside the driver; with several ranks driven from one process that blocks the peers' launches)
+    if (!c->mrf_host_flags) B2_CUDA(cudaHostAlloc((void **)&c->mrf_host_flags, (64 + 2 * MRF_SLOTS + 64) * sizeof(uint32_t), cudaHostAllocDefault));
     B2_TRY(c->mrf_H.alloc(c->nnz));
     B2_TRY(c->mrf_hminp1.alloc(F));
     B2_TRY(c->mrf_amin.alloc(F));
@@ -1292,10 +1385,10 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
 
 int read_energy(b2tex_ctx *c, const Mrf &m, uint32_t slot, int64_t *efix)
 {
-    unsigned long long e = 0;
-    B2_CUDA(cudaMemcpyAsync(&e, m.efix + slot, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long *pin = reinterpret_cast<unsigned long long *>(c->mrf_host_flags + 64);
+    B2_CUDA(cudaMemcpyAsync(pin, m.efix + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
-    *efix = (int64_t)e;
+    *efix = (int64_t)pin[0];
     return B2TEX_OK;
 }
 
@@ -1338,7 +1431,20 @@ int mrf_init(b2tex_ctx *c, const b2tex_mrf_params *p, int64_t *efix)
 // every allocation of a run, nothing else: a caller that drives several ranks from ONE process (threads) prepares all of
 // them before the first rank starts, because cudaMalloc waits for the whole device and a rank that already spins in a
 // cross-rank barrier kernel would never be released (separate processes / devices do not have that problem)
-int mrf_prepare(b2tex_ctx *c, const b2tex_mrf_params *p) { return alloc_mrf(c, p); }
+int mrf_prepare(b2tex_ctx *c, const b2tex_mrf_params *p)
+{
+    B2_TRY(alloc_mrf(c, p));
+    // ... and every kernel of the run is loaded now: with lazy module loading the FIRST launch of a kernel synchronises
+    // the context, which would also wait for a peer rank's spinning barrier kernel
+    cudaFuncAttributes fa;
+    const void *fns[] = {(const void *)k_forest, (const void *)k_energy, (const void *)k_stop, (const void *)k_label_check,
+                         (const void *)k_build_adj4, (const void *)k_halo_build, (const void *)k_halo_push, (const void *)k_range_push,
+                         (const void *)k_mg_sync, (const void *)k_tree<4>, (const void *)k_tree<8>, (const void *)k_tree<16>,
+                         (const void *)k_tree<32>, (const void *)k_init_labels<4>, (const void *)k_init_labels<8>,
+                         (const void *)k_init_labels<16>, (const void *)k_init_labels<32>};
+    for (const void *f : fns) B2_CUDA(cudaFuncGetAttributes(&fa, f));
+    return B2TEX_OK;
+}
 
 // one iteration, energy read back (single GPU, or the building block of a host-driven sharded loop over NCCL)
 int mrf_iterate(b2tex_ctx *c, uint32_t t, int64_t *efix)
@@ -1410,10 +1516,16 @@ int mrf_run(b2tex_ctx *c, const b2tex_mrf_params *p, b2tex_mrf_info *info, doubl
     B2_LAUNCH k_label_check<<<std::max(1, c->num_sms * 4), 256, 0, s>>>(m);
     B2_KERNEL_CHECK();
     uint32_t st[ST_WORDS];
-    B2_TRY(c->mrf_state.download(st, ST_WORDS, s));
     std::vector<unsigned long long> efix((size_t)max_it + 2, 0ull);
-    B2_TRY(c->mrf_energy.download(efix.data(), (size_t)max_it + 1, s));
-    B2_CUDA(cudaStreamSynchronize(s));
+    {   // through the pinned read-back area
+        unsigned long long *pin_e = reinterpret_cast<unsigned long long *>(c->mrf_host_flags + 64);
+        uint32_t *pin_s = c->mrf_host_flags + 64 + 2 * MRF_SLOTS;
+        B2_CUDA(cudaMemcpyAsync(pin_s, c->mrf_state.p, ST_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaMemcpyAsync(pin_e, c->mrf_energy.p, ((size_t)max_it + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        memcpy(st, pin_s, sizeof(st));
+        memcpy(efix.data(), pin_e, ((size_t)max_it + 1) * sizeof(unsigned long long));
+    }
     if (st[ST_ERR]) { set_error("multi-GPU view selection: %u cross-GPU barrier timeouts (a peer did not arrive)", st[ST_ERR]); return B2TEX_ERR_CUDA; }
     const uint32_t t_end = st[ST_STOP] ? st[ST_STOP] : st[ST_DONE];   // ST_STOP == 0 only for max_iterations == 0
     info->iterations = t_end;
@@ -1435,6 +1547,11 @@ int mrf_run(b2tex_ctx *c, const b2tex_mrf_params *p, b2tex_mrf_info *info, doubl
         B2_CUDA(cudaStreamSynchronize(s));
         fprintf(stderr, "k_forest phases over %u iterations [us]: round0 %.1f seed %.1f growth %.1f alloc %.1f scatter %.1f\n", t_end,
                 d[1] / 1e3, d[2] / 1e3, d[3] / 1e3, d[4] / 1e3, d[5] / 1e3);
+        const double ctas = d[13] ? (double)d[13] : 1.0;
+        fprintf(stderr, "k_tree solve split per CTA-launch [kcycles]: masks+buckets %.1f up %.1f down %.1f\n", d[14] / ctas / 1e3, d[15] / ctas / 1e3, d[7] / ctas / 1e3);
+        fprintf(stderr, "k_tree per CTA-launch [kcycles]: claim+pack %.1f stage %.1f solve %.1f; sub-batches/CTA-launch %.1f, largest sub-batch %llu nodes, "
+                        "trees through global memory %u, forest nodes %llu in %llu labels\n", d[8] / ctas / 1e3, d[9] / ctas / 1e3, d[10] / ctas / 1e3,
+                (double)d[11] / ctas, d[12], st[ST_SLOW], fn, fz);
     }
     if (st[ST_BAD]) { set_error("Incorrect labeling"); return B2TEX_ERR_LABELING; }
     return B2TEX_OK;

@@ -314,22 +314,37 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg(Pcg q)
     uint32_t loops = 0;
     grid.sync();  // partA is rewritten below
     while (active[0] || active[1] || active[2]) {
-        // phase 1: t = A p, p.t
+        // phase 1: t = A p, p.t.  Two rows per thread in flight: the row loop is a chain of dependent loads
+        // (row extent -> column -> p[column]) and the solve is latency bound, so the second chain is free.
+        // Per row the edges are still added in storage order and the rows of a thread in ascending order: bit-identical.
         for (int k = 0; k < 6; ++k) acc[k] = 0.0;
-        for (uint32_t i = tid; i < R; i += nth) {
-            const uint32_t e1 = q.csr_ptr[i + 1];
-            const float4 pi = q.p[i];
-            const float dv = q.diag_val[i];
-            float s0 = 0.0f + dv * pi.x, s1 = 0.0f + dv * pi.y, s2 = 0.0f + dv * pi.z;  // diagonal first
-            const float lam2 = 0.1f * 0.1f;
-            for (uint32_t e = q.csr_ptr[i] + 1; e < e1; ++e) {
-                const uint32_t enc = q.csr_enc[e];
-                const float a = (enc >> 31) ? -1.0f : -lam2;
-                const float4 pv = q.p[enc & 0x7FFFFFFFu];
-                s0 += a * pv.x; s1 += a * pv.y; s2 += a * pv.z;
+        const float lam2 = 0.1f * 0.1f;
+        for (uint32_t i0 = tid; i0 < R; i0 += 2 * nth) {
+            const uint32_t i1 = i0 + nth;
+            const bool h1 = i1 < R;
+            uint32_t a = q.csr_ptr[i0] + 1, ae = q.csr_ptr[i0 + 1];
+            uint32_t b = h1 ? q.csr_ptr[i1] + 1 : 0u, be = h1 ? q.csr_ptr[i1 + 1] : 0u;
+            const float4 pa = q.p[i0];
+            const float4 pb = h1 ? q.p[i1] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const float da = q.diag_val[i0], db = h1 ? q.diag_val[i1] : 0.0f;
+            float a0 = 0.0f + da * pa.x, a1 = 0.0f + da * pa.y, a2 = 0.0f + da * pa.z;  // diagonal first
+            float b0 = 0.0f + db * pb.x, b1 = 0.0f + db * pb.y, b2 = 0.0f + db * pb.z;
+            while (a < ae || b < be) {
+                uint32_t ea = 0, eb = 0;
+                if (a < ae) ea = q.csr_enc[a];
+                if (b < be) eb = q.csr_enc[b];
+                float4 va = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vb = va;
+                if (a < ae) va = q.p[ea & 0x7FFFFFFFu];
+                if (b < be) vb = q.p[eb & 0x7FFFFFFFu];
+                if (a < ae) { const float w = (ea >> 31) ? -1.0f : -lam2; a0 += w * va.x; a1 += w * va.y; a2 += w * va.z; ++a; }
+                if (b < be) { const float w = (eb >> 31) ? -1.0f : -lam2; b0 += w * vb.x; b1 += w * vb.y; b2 += w * vb.z; ++b; }
             }
-            q.t[i] = s0; q.t[(size_t)R + i] = s1; q.t[2 * (size_t)R + i] = s2;
-            acc[0] += (double)pi.x * s0; acc[1] += (double)pi.y * s1; acc[2] += (double)pi.z * s2;
+            q.t[i0] = a0; q.t[(size_t)R + i0] = a1; q.t[2 * (size_t)R + i0] = a2;
+            acc[0] += (double)pa.x * a0; acc[1] += (double)pa.y * a1; acc[2] += (double)pa.z * a2;
+            if (h1) {
+                q.t[i1] = b0; q.t[(size_t)R + i1] = b1; q.t[2 * (size_t)R + i1] = b2;
+                acc[0] += (double)pb.x * b0; acc[1] += (double)pb.y * b1; acc[2] += (double)pb.z * b2;
+            }
         }
         block_reduce6(acc, smem);
         if (threadIdx.x == 0) for (int k = 0; k < 6; ++k) partA[(size_t)blockIdx.x * 8 + k] = acc[k];
@@ -338,20 +353,43 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg(Pcg q)
         float alpha[3];
         for (int c = 0; c < 3; ++c) alpha[c] = active[c] ? absNew[c] / (float)tot[c] : 0.0f;
 
-        // phase 2: x += a p, r -= a t, |r|^2, r.z
+        // phase 2: x += a p, r -= a t, |r|^2, r.z (two rows per thread in flight, loads first)
         for (int k = 0; k < 6; ++k) acc[k] = 0.0;
-        for (uint32_t i = tid; i < R; i += nth) {
-            const float4 pi = q.p[i];
-            const float pv[3] = {pi.x, pi.y, pi.z};
-            const float id = q.inv_diag[i];
+        for (uint32_t i0 = tid; i0 < R; i0 += 2 * nth) {
+            const uint32_t i1 = i0 + nth;
+            const bool h1 = i1 < R;
+            const uint32_t j1 = h1 ? i1 : i0;
+            const float4 pa = q.p[i0], pb = q.p[j1];
+            const float ida = q.inv_diag[i0], idb = q.inv_diag[j1];
+            float xa[3], ra[3], ta[3], xb[3], rb[3], tb[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const size_t oa = (size_t)c * R + i0, ob = (size_t)c * R + j1;
+                xa[c] = q.x[oa]; ra[c] = q.r[oa]; ta[c] = q.t[oa];
+                xb[c] = q.x[ob]; rb[c] = q.r[ob]; tb[c] = q.t[ob];
+            }
+            const float pva[3] = {pa.x, pa.y, pa.z}, pvb[3] = {pb.x, pb.y, pb.z};
+#pragma unroll
             for (int c = 0; c < 3; ++c) {
                 if (!active[c]) continue;
-                const size_t o = (size_t)c * R + i;
-                q.x[o] += alpha[c] * pv[c];
-                float rv = q.r[o] - alpha[c] * q.t[o];
-                q.r[o] = rv;
+                const size_t oa = (size_t)c * R + i0;
+                q.x[oa] = xa[c] + alpha[c] * pva[c];
+                const float rv = ra[c] - alpha[c] * ta[c];
+                q.r[oa] = rv;
                 acc[c] += (double)rv * rv;
-                acc[3 + c] += (double)rv * (id * rv);
+                acc[3 + c] += (double)rv * (ida * rv);
+            }
+            if (h1) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (!active[c]) continue;
+                    const size_t ob = (size_t)c * R + i1;
+                    q.x[ob] = xb[c] + alpha[c] * pvb[c];
+                    const float rv = rb[c] - alpha[c] * tb[c];
+                    q.r[ob] = rv;
+                    acc[c] += (double)rv * rv;
+                    acc[3 + c] += (double)rv * (idb * rv);
+                }
             }
         }
         block_reduce6(acc, smem);
@@ -371,15 +409,21 @@ __global__ void __launch_bounds__(PCG_THREADS, 1) k_pcg(Pcg q)
             upd[c] = true;
             if (++iters[c] >= q.max_iters) active[c] = false;  // while (i < maxIters)
         }
-        // phase 3: p = z + beta p
+        // phase 3: p = z + beta p (two rows per thread in flight)
         if (upd[0] || upd[1] || upd[2]) {
-            for (uint32_t i = tid; i < R; i += nth) {
-                float4 pi = q.p[i];
-                const float id = q.inv_diag[i];
-                if (upd[0]) pi.x = id * q.r[i] + beta[0] * pi.x;
-                if (upd[1]) pi.y = id * q.r[(size_t)R + i] + beta[1] * pi.y;
-                if (upd[2]) pi.z = id * q.r[2 * (size_t)R + i] + beta[2] * pi.z;
-                q.p[i] = pi;
+            for (uint32_t i0 = tid; i0 < R; i0 += 2 * nth) {
+                const uint32_t i1 = i0 + nth;
+                const bool h1 = i1 < R;
+                const uint32_t j1 = h1 ? i1 : i0;
+                float4 pa = q.p[i0], pb = q.p[j1];
+                const float ida = q.inv_diag[i0], idb = q.inv_diag[j1];
+                const float ra0 = q.r[i0], ra1 = q.r[(size_t)R + i0], ra2 = q.r[2 * (size_t)R + i0];
+                const float rb0 = q.r[j1], rb1 = q.r[(size_t)R + j1], rb2 = q.r[2 * (size_t)R + j1];
+                if (upd[0]) { pa.x = ida * ra0 + beta[0] * pa.x; pb.x = idb * rb0 + beta[0] * pb.x; }
+                if (upd[1]) { pa.y = ida * ra1 + beta[1] * pa.y; pb.y = idb * rb1 + beta[1] * pb.y; }
+                if (upd[2]) { pa.z = ida * ra2 + beta[2] * pa.z; pb.z = idb * rb2 + beta[2] * pb.z; }
+                q.p[i0] = pa;
+                if (h1) q.p[i1] = pb;
             }
         }
         ++loops;

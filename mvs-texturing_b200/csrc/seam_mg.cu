@@ -291,6 +291,7 @@ struct MgState {
     uint32_t R = 0, rank = 0, nranks = 1, epoch = 0;
     DevBuf<double> blockpart;
     DevBuf<uint32_t> status;
+    uint32_t *pinned = nullptr;
 };
 
 void seam_mg_free(b2tex_ctx *c)
@@ -300,6 +301,7 @@ void seam_mg_free(b2tex_ctx *c)
     for (uint32_t k = 0; k < MG_MAX_RANKS; ++k)
         if (m->opened[k] && m->peer[k]) cudaIpcCloseMemHandle(m->peer[k]);
     if (m->block) cudaFree(m->block);
+    if (m->pinned) cudaFreeHost(m->pinned);
     delete m;
     c->seam_mg = nullptr;
 }
@@ -320,6 +322,9 @@ int seam_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t nranks, void *handle64)
     m->peer[rank] = m->block;
     B2_TRY(m->blockpart.alloc(4096 * 8));   // every allocation happens here: nothing inside the solve waits for the device
     B2_TRY(m->status.alloc(16));
+    B2_CUDA(cudaHostAlloc((void **)&m->pinned, 16 * sizeof(uint32_t), cudaHostAllocDefault));
+    cudaFuncAttributes fa;   // load the kernel now (the first launch of a lazily loaded kernel synchronises the context)
+    B2_CUDA(cudaFuncGetAttributes(&fa, (const void *)k_pcg_mg));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
     memset(&h, 0, sizeof(h));
@@ -381,10 +386,14 @@ int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info)
     B2_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg_mg, dim3(grid), dim3(MG_THREADS), args, 0, s));
     B2_CUDA(cudaEventRecord(e1, s));
     uint32_t st[16];
-    B2_CUDA(cudaMemcpyAsync(st, m->status.p, sizeof(st), cudaMemcpyDeviceToHost, s));
+    // read back through pinned memory: a copy to pageable memory waits for the stream inside the driver, which (ranks driven
+    // from one process) would keep the peers from launching the kernel this one is waiting for
+    if (!m->pinned) B2_CUDA(cudaHostAlloc((void **)&m->pinned, 16 * sizeof(uint32_t), cudaHostAllocDefault));
+    B2_CUDA(cudaMemcpyAsync(m->pinned, m->status.p, sizeof(st), cudaMemcpyDeviceToHost, s));
     // the complete solution sits in the own peer block: copy it where the single-GPU path leaves it
     B2_CUDA(cudaMemcpyAsync(c->seam_x.p, mg_carve(m->block, R).x, 3 * (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, s));
     B2_CUDA(cudaStreamSynchronize(s));
+    memcpy(st, m->pinned, sizeof(st));
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);

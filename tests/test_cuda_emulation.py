@@ -50,7 +50,7 @@ def emul():
     with open(os.path.join(OUT, "bvh_kernels.inc"), "w") as f:
         f.write(_kernel_part("bvh.cu", "int build_bvh("))
     with open(os.path.join(OUT, "datacosts_kernels.inc"), "w") as f:
-        f.write(_kernel_part("datacosts.cu", "int data_costs_qualities(", ("int cub_exclusive_sum_u64", "namespace {")))
+        f.write(_kernel_part("datacosts.cu", "static int finish_candidates(", ("int cub_exclusive_sum_u64", "namespace {")))
     with open(os.path.join(OUT, "mrf_kernels.inc"), "w") as f:
         f.write(_kernel_part("mrf.cu", "Mrf make_mrf(b2tex_ctx",
                              [("// ---- shared-memory / async-copy primitives", "// ---- end of primitives ----"),

@@ -3,7 +3,10 @@ the same peer-memory protocol as one process per GPU does (mvs-texturing_b200/sh
 epoch-flag barriers, energy slots (csrc/mrf.cu) and the fused PCG with the search-direction exchange inside the kernel
 (csrc/seam_mg.cu).  The peers live in one process here, so they attach each other's blocks by raw device pointer
 (b2tex_peer_attach) instead of a cudaIpc handle; everything behind that is identical.  The scenes are small, so the
-persistent kernels of all ranks are co-resident (a spinning kernel never keeps a peer's kernel off the SMs).
+persistent kernels of all ranks are co-resident (a spinning kernel never keeps a peer's kernel off the SMs), and at most
+four ranks, so that every rank's stream has a hardware work queue of its own (CUDA_DEVICE_MAX_CONNECTIONS defaults to 8:
+with eight rank streams plus the framework's own, two ranks share a queue and a barrier kernel at its head keeps the
+peer's kernel behind it from ever starting -- one process per GPU, the real deployment, has no such coupling).
 
 Bars: labels, iteration count and fixed-point energy equal the oracle run with num_parts = ranks (bit exact); every rank
 holds every label after the final all-gather; all ranks end with the bit-identical seam solution, within 5e-3 of the
@@ -37,7 +40,7 @@ def _run_threads(fns):
     return out
 
 
-@pytest.mark.parametrize("name,ranks", [("occ", 2), ("C2s", 4), ("C1d", 3), ("small", 8)])
+@pytest.mark.parametrize("name,ranks", [("occ", 2), ("C2s", 4), ("C1d", 3)])
 def test_sharded_pipeline_on_one_gpu(b2, orc, scene_mod, get_scene, name, ranks):
     s = get_scene(name)
     adj = scene_mod.face_adjacency(s.faces)
