@@ -201,6 +201,9 @@ int b2tex_set_data_costs(b2tex_ctx *c, const uint64_t *face_ptr, const uint16_t 
 int b2tex_set_labels(b2tex_ctx *c, const uint32_t *labels)
 {
     B2_CUDA(cudaSetDevice(c->device));
+    if (c->K)   // texrecon.cpp:141-153 rejects such labelings ("Incorrect labeling"); the seam / patch kernels index views[label - 1]
+        for (uint32_t i = 0; i < c->F; ++i)
+            if (labels[i] > c->K) { set_error("Incorrect labeling (face %u has label %u, %u views)", i, labels[i], c->K); return B2TEX_ERR_LABELING; }
     B2_TRY(c->labels.upload(labels, c->F, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     c->have_labels = true;

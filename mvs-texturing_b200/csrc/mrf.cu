@@ -790,10 +790,13 @@ __device__ void batch_solve(const Mrf &m, const TreePool &p, TreeStatic &ts, uin
                     if (h < bh) { bh = h; bk = k; }
                 }
             }
-            for (int sft = G / 2; sft; sft >>= 1) {
-                const float oh = __shfl_xor_sync(0xffffffffu, bh, sft);
-                const uint32_t ok = __shfl_xor_sync(0xffffffffu, bk, sft);
-                if (oh < bh || (oh == bh && ok < bk)) { bh = oh; bk = ok; }
+            {   // min / arg-min over the G lanes of the node by two integer warp reductions: every h is >= 0 (costs in [0, 1],
+                // messages sums of such), so the unsigned order of the bit patterns is the float order; ties -> smallest index
+                const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(uint32_t)(G - 1)));
+                const uint32_t hb = __float_as_uint(bh);
+                const uint32_t hmin = __reduce_min_sync(gmask, hb);
+                bk = __reduce_min_sync(gmask, hb == hmin ? bk : 0xFFFFFFFFu);
+                bh = __uint_as_float(hmin);
             }
             if (act && glane == 0) { p.hm[li] = bh + 1.0f; p.am[li] = bk; }
         }
@@ -1367,7 +1370,7 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
     uint32_t nodes = c->face_end - c->face_begin;
     double rho = nodes ? (double)c->nnz / nodes : 0.0;
     // lanes per node: a level of one tree holds only a few nodes, so wide groups idle on short label lists
-    c->mrf_group = rho >= 40 ? 32 : rho >= 12 ? 16 : rho >= 6 ? 8 : 4;
+    c->mrf_group = rho >= 64 ? 32 : rho >= 12 ? 16 : rho >= 6 ? 8 : 4;   // C3 (44 labels per node): 16 lanes 28.9 ms, 32 lanes 31.2 ms, 8 lanes 36.9 ms
     if (const char *g = getenv("B2TEX_MRF_GROUP")) {
         int v = atoi(g);
         if (v == 4 || v == 8 || v == 16 || v == 32) c->mrf_group = v;

@@ -29,7 +29,7 @@ template <bool FILL>
 __global__ void k_vertex_labels(uint32_t Vn, const uint32_t *__restrict__ vf_ptr,
                                 const uint32_t *__restrict__ vf_idx, const uint32_t *__restrict__ labels,
                                 uint32_t *cnt, const uint32_t *__restrict__ row_ptr, uint32_t *row_label,
-                                uint32_t *row_vertex)
+                                uint32_t *row_vertex, uint32_t *limit_flags)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Vn) return;
@@ -40,7 +40,8 @@ __global__ void k_vertex_labels(uint32_t Vn, const uint32_t *__restrict__ vf_ptr
         if (l == 0) continue;
         uint32_t k = 0;
         while (k < n && tmp[k] != l) ++k;
-        if (k < n || n >= MAXL) continue;
+        if (k < n) continue;
+        if (n >= MAXL) { atomicOr(limit_flags, 1u); continue; }   // the reference has no such cap: reported, not dropped silently
         uint32_t p = n++;
         while (p > 0 && tmp[p - 1] > l) { tmp[p] = tmp[p - 1]; --p; }
         tmp[p] = l;
@@ -116,7 +117,7 @@ __device__ void sample_edge(const ViewDev &V, const float p1[2], const float p2[
 // A rows of one vertex: label pairs l1<l2 with >= 1 seam edge (:214-237); FILL also computes b.
 template <bool FILL>
 __global__ void k_arows(uint32_t Vn, SeamMesh m, uint32_t *cnt, const uint32_t *__restrict__ arow_ptr,
-                        uint32_t *arow_rows, float *arow_b)
+                        uint32_t *arow_rows, float *arow_b, uint32_t *limit_flags)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Vn) return;
@@ -133,8 +134,11 @@ __global__ void k_arows(uint32_t Vn, SeamMesh m, uint32_t *cnt, const uint32_t *
                     uint32_t adj = m.vv_idx[a];
                     if (adj == i) continue;
                     uint32_t ef[16], nef = 0;
-                    for (uint32_t q = m.vf_ptr[i]; q < m.vf_ptr[i + 1] && nef < 16; ++q)
-                        if (face_has_vertex(m.faces, m.vf_idx[q], adj)) ef[nef++] = m.vf_idx[q];
+                    for (uint32_t q = m.vf_ptr[i]; q < m.vf_ptr[i + 1]; ++q)
+                        if (face_has_vertex(m.faces, m.vf_idx[q], adj)) {
+                            if (nef < 16) ef[nef++] = m.vf_idx[q];
+                            else atomicOr(limit_flags, 2u);   // more than 16 faces on one edge
+                        }
                     for (uint32_t x = 0; x < nef; ++x)
                         for (uint32_t y = x + 1; y < nef; ++y) {
                             uint32_t fl1 = m.labels[ef[x]], fl2 = m.labels[ef[y]];
@@ -479,14 +483,14 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
     B2_TRY(c->row_label.alloc(R));
     B2_TRY(row_vertex.alloc(R));
     B2_LAUNCH k_vertex_labels<true><<<vb, 128, 0, s>>>(Vn, c->vf_ptr.p, c->vf_idx.p, c->labels.p, nullptr, c->row_ptr.p,
-                                             c->row_label.p, row_vertex.p);
+                                             c->row_label.p, row_vertex.p, limit_flags);
     B2_KERNEL_CHECK();
 
     SeamMesh m{c->verts.p, c->faces.p, c->vf_ptr.p, c->vf_idx.p, c->vv_ptr.p, c->vv_idx.p, c->labels.p,
                c->row_ptr.p, c->row_label.p, c->views_dev.p};
     B2_TRY(c->arow_ptr.alloc((size_t)Vn + 1));
     B2_TRY(cnt.zero(s));
-    B2_LAUNCH k_arows<false><<<vb, 128, 0, s>>>(Vn, m, cnt.p, nullptr, nullptr, nullptr);
+    B2_LAUNCH k_arows<false><<<vb, 128, 0, s>>>(Vn, m, cnt.p, nullptr, nullptr, nullptr, limit_flags);
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u32(c, cnt.p, c->arow_ptr.p, (size_t)Vn + 1));
     uint32_t A = 0;
@@ -495,7 +499,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
     c->A_rows = A;
     B2_TRY(c->arow_rows.alloc(2 * (size_t)A));
     B2_TRY(c->arow_b.alloc(3 * (size_t)A));
-    B2_LAUNCH k_arows<true><<<vb, 128, 0, s>>>(Vn, m, nullptr, c->arow_ptr.p, c->arow_rows.p, c->arow_b.p);
+    B2_LAUNCH k_arows<true><<<vb, 128, 0, s>>>(Vn, m, nullptr, c->arow_ptr.p, c->arow_rows.p, c->arow_b.p, limit_flags);
     B2_KERNEL_CHECK();
 
     DevBuf<uint32_t> &rcnt = c->s_rcnt;
@@ -508,9 +512,15 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
                                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u32(c, rcnt.p, c->csr_ptr.p, (size_t)R + 1));
-    uint32_t nnzL = 0;
+    uint32_t nnzL = 0, limits = 0;
     B2_CUDA(cudaMemcpyAsync(&nnzL, c->csr_ptr.p + R, 4, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaMemcpyAsync(&limits, limit_flags, 4, cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
+    if (limits) {
+        set_error("global seam leveling: %s%s", (limits & 1u) ? "a vertex carries more than 64 different labels; " : "",
+                  (limits & 2u) ? "an edge has more than 16 incident faces" : "");
+        return B2TEX_ERR_LIMITS;
+    }
     c->nnz_L = nnzL;
     B2_TRY(c->csr_col.alloc(nnzL));
     B2_TRY(c->csr_val.alloc(nnzL));
@@ -538,7 +548,6 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
     info->cg_ms = 0.0f;
 
     tm_asm.reset();
-    B2_TRY(c->seam_status.alloc(16));
     B2_TRY(c->seam_status.zero(s));
     if (R && solve) {   // solve == false: assembly only, the multi-GPU solver (seam_mg.cu) takes over
         int per_sm = 0;

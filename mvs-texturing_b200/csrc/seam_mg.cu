@@ -4,8 +4,10 @@
 // Lhs x = Rhs (global_seam_leveling.cpp:245-277) are split into contiguous ranges, one per rank.  Every rank runs the
 // same persistent cooperative Jacobi-PCG as k_pcg on ITS rows and, inside the kernel, exchanges with its peers through
 // peer-mapped memory (cudaIpc handles, NVLink / NVSwitch loads and stores) instead of returning to the host for NCCL:
-//   * search direction p: after "p = z + beta p" every rank STORES its slice into every peer's full-length copy of p,
-//     so the SpMV of the next iteration reads only local memory (an all-gather by stores, overlapped with the update);
+//   * search direction p: after "p = z + beta p" every rank STORES the entries of its HALO rows -- the rows some column
+//     of a peer's rows refers to, 0.4 % of the rows at 2 ranks and 2 % at 8 on the C3 system (the Laplacian couples a
+//     vertex only to its 1-ring) -- into the copies of exactly those peers, so the SpMV of the next iteration reads only
+//     local memory; the destination mask of every row is derived from the CSR once per solve;
 //   * dot products: every rank stores its fp64 partial sums into every peer's slot table; after the barrier all ranks
 //     add the P slots in rank order -> bit-identical scalars everywhere, no divergence of the iteration;
 //   * barrier: one epoch counter per (rank, peer) in peer memory, store-release at system scope after a system fence,
@@ -13,8 +15,8 @@
 // Results are deterministic for a given rank count; they differ from the single-GPU kernel only by the summation
 // order of the reductions (per rank, then across ranks).
 //
-// STATUS (end of round 1): the kernel logic runs in the multi-rank fiber emulation (tests/cpp/emul_seam_mg.cpp) and
-// matches the oracle; it has NOT run on hardware.  mvs-texturing_b200/sharded.py keeps the replicated solve as default.
+// Measured (round 2, C3 on 2 B200): a first version that all-gathered the whole slice of p every iteration and let every
+// thread issue a system fence per barrier took 146 us per iteration against 71 us on one GPU; see DESIGN.md section 5.
 #include <cooperative_groups.h>
 #include <math.h>
 
@@ -57,6 +59,7 @@ struct PcgMg {
     const uint32_t *csr_ptr, *csr_enc;
     const float *diag_val, *inv_diag, *rhs;   // replicated assembly (k_matrix), indexed by global row
     float *r, *t;                // [3][R] local scratch (own rows used)
+    const uint8_t *dest;         // [R] for own rows: bit k = rank k reads this row's entry of p (halo destination mask)
     double *blockpart;           // [grid][8] per-block partials of this rank
     uint32_t *status;            // [0..2] iterations, [3..5] residual bits, [6] loops, [7] barrier timeouts
     void *peer[MG_MAX_RANKS];    // base pointers of every rank's MgBlock (peer[rank] = own)
@@ -97,18 +100,21 @@ __device__ __forceinline__ void mg_block_reduce6(double v[6], double *smem)
 }
 
 // Cross-GPU barrier, called by ALL threads of the grid.  Everything every thread of this rank stored to peer memory
-// before the call is visible to every thread of every rank after it.
+// before the call is visible to every thread of every rank after it.  One system-scope fence per BLOCK (after the block's
+// own barrier; the fence of one thread is cumulative over what the block barrier ordered before it), not one per thread.
 __device__ __forceinline__ bool mg_barrier(cg::grid_group &grid, const PcgMg &q, uint32_t epoch)
 {
-    __threadfence_system();   // this thread's peer stores before the rank-wide barrier
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
     grid.sync();
     if (blockIdx.x == 0 && threadIdx.x < q.nranks) {
         const uint32_t k = threadIdx.x;
+        __threadfence_system();
         st_release_sys(mg_carve(q.peer[k], q.R).flag + q.rank, epoch);          // tell peer k: rank `rank` reached `epoch`
         const uint32_t *mine = mg_carve(q.peer[q.rank], q.R).flag + k;          // wait until peer k reached it too
         unsigned long long spins = 0;
         while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-            __nanosleep(64);
+            __nanosleep(32);
             if (++spins > q.spin_limit) { atomicAdd(q.status + 7, 1u); break; }
         }
     }
@@ -118,8 +124,11 @@ __device__ __forceinline__ bool mg_barrier(cg::grid_group &grid, const PcgMg &q,
     return __ldcg(q.status + 7) == 0u;
 }
 
-// sum of the per-block partials of this rank (every thread computes the same value), pushed to all peers by block 0
-__device__ __forceinline__ void mg_push_partials(cg::grid_group &grid, const PcgMg &q, double acc[6], double *smem, int parity)
+// All-reduce of six partial sums across the ranks, fused with the barrier: per-block partials -> grid.sync -> block 0 sums
+// them (fixed order), stores the rank's sums into slot [parity][rank] of every peer, fences, raises its epoch flag at every
+// peer and waits for theirs -> grid.sync -> every thread adds the slots in rank order (identical on every GPU).
+__device__ __forceinline__ bool mg_allreduce6(cg::grid_group &grid, const PcgMg &q, double acc[6], double *smem, int parity,
+                                              uint32_t epoch, double tot[6])
 {
     mg_block_reduce6(acc, smem);
     if (threadIdx.x == 0) for (int k = 0; k < 6; ++k) q.blockpart[(size_t)blockIdx.x * 8 + k] = acc[k];
@@ -129,22 +138,60 @@ __device__ __forceinline__ void mg_push_partials(cg::grid_group &grid, const Pcg
         for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
             for (int k = 0; k < 6; ++k) v[k] += q.blockpart[(size_t)b * 8 + k];
         mg_block_reduce6(v, smem);
-        if (threadIdx.x < q.nranks)
-            for (int k = 0; k < 6; ++k)
-                mg_carve(q.peer[threadIdx.x], q.R).part[((size_t)parity * MG_MAX_RANKS + q.rank) * 8 + k] = v[k];
+        if (threadIdx.x < q.nranks) {
+            const uint32_t k = threadIdx.x;
+            const MgBlock pk = mg_carve(q.peer[k], q.R);
+            for (int j = 0; j < 6; ++j) pk.part[((size_t)parity * MG_MAX_RANKS + q.rank) * 8 + j] = v[j];
+            __threadfence_system();
+            st_release_sys(pk.flag + q.rank, epoch);
+            const uint32_t *mine = mg_carve(q.peer[q.rank], q.R).flag + k;
+            unsigned long long spins = 0;
+            while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+                __nanosleep(32);
+                if (++spins > q.spin_limit) { atomicAdd(q.status + 7, 1u); break; }
+            }
+        }
     }
-}
-__device__ __forceinline__ void mg_totals(const PcgMg &q, int parity, double tot[6])
-{
+    grid.sync();
     const double *part = mg_carve(q.peer[q.rank], q.R).part + (size_t)parity * MG_MAX_RANKS * 8;
     for (int k = 0; k < 6; ++k) {
-        double s = 0.0;
-        for (uint32_t r = 0; r < q.nranks; ++r) s += __ldcg(part + (size_t)r * 8 + k);   // rank order: identical on every GPU
-        tot[k] = s;
+        double sum = 0.0;
+        for (uint32_t r = 0; r < q.nranks; ++r) sum += __ldcg(part + (size_t)r * 8 + k);   // rank order: identical on every GPU
+        tot[k] = sum;
+    }
+    return __ldcg(q.status + 7) == 0u;
+}
+
+// the entry of p of one own row goes to the ranks that read it
+__device__ __forceinline__ void mg_push_p(const PcgMg &q, uint32_t i, const float4 &v)
+{
+    for (uint32_t mk = q.dest[i]; mk; mk &= mk - 1u) {
+        const uint32_t k = (uint32_t)__ffs((int)mk) - 1u;
+        mg_carve(q.peer[k], q.R).p[i] = v;
     }
 }
 
 }  // namespace
+
+// destination mask of every own row: the ranks whose row ranges hold a row with this row among its columns (the matrix is
+// symmetric: those are the ranks of this row's own columns)
+__global__ void __launch_bounds__(256) k_pcg_mg_dest(uint32_t R, uint32_t r0, uint32_t r1, uint32_t rank, uint32_t nranks,
+                                                     const uint32_t *__restrict__ csr_ptr, const uint32_t *__restrict__ csr_enc,
+                                                     uint8_t *dest)
+{
+    const uint32_t i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r1) return;
+    uint32_t mask = 0;
+    for (uint32_t e = csr_ptr[i] + 1; e < csr_ptr[i + 1]; ++e) {
+        const uint32_t col = csr_enc[e] & 0x7FFFFFFFu;
+        // rank k owns [R k / P, R (k + 1) / P): k = floor((col P + P - 1) / R) up to the rounding of the bounds
+        uint32_t k = (uint32_t)(((uint64_t)col * nranks) / R);
+        while (k + 1 < nranks && col >= (uint32_t)((uint64_t)R * (k + 1) / nranks)) ++k;
+        while (k > 0 && col < (uint32_t)((uint64_t)R * k / nranks)) --k;
+        if (k != rank) mask |= 1u << k;
+    }
+    dest[i] = (uint8_t)mask;
+}
 
 constexpr int MG_THREADS = 1024;
 __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
@@ -158,7 +205,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
     uint32_t epoch = q.epoch0;
     bool alive = true;
 
-    // r = rhs, p = M^-1 r on the own rows; p goes to every rank's copy
+    // r = rhs, p = M^-1 r on the own rows; the halo entries of p go to the ranks that read them
     for (int k = 0; k < 6; ++k) acc[k] = 0.0;
     for (uint32_t i = q.r0 + tid; i < q.r1; i += nth) {
         const float id = q.inv_diag[i];
@@ -172,11 +219,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
             acc[3 + c] += (double)rv * pv[c];
         }
         const float4 p4 = make_float4(pv[0], pv[1], pv[2], 0.0f);
-        for (uint32_t k = 0; k < q.nranks; ++k) mg_carve(q.peer[k], R).p[i] = p4;
+        own.p[i] = p4;
+        mg_push_p(q, i, p4);
     }
-    mg_push_partials(grid, q, acc, smem, 0);
-    alive = mg_barrier(grid, q, ++epoch) && alive;
-    mg_totals(q, 0, tot);
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();   // the pushes of this block before the flags of the all-reduce below
+    alive = mg_allreduce6(grid, q, acc, smem, 0, ++epoch, tot) && alive;
     float rhsNorm2[3], threshold[3], absNew[3], resNorm2[3];
     bool active[3];
     uint32_t iters[3] = {0, 0, 0};
@@ -188,27 +236,38 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
         active[c] = rhsNorm2[c] != 0.0f && !(resNorm2[c] < threshold[c]);
     }
     uint32_t loops = 0;
+    const float lam2 = 0.1f * 0.1f;
     while (alive && (active[0] || active[1] || active[2])) {
-        // phase 1: t = A p on the own rows (p is complete locally), p.t
+        // phase 1: t = A p on the own rows (own entries and the halo the peers pushed are local), p.t; two rows in flight
         for (int k = 0; k < 6; ++k) acc[k] = 0.0;
-        for (uint32_t i = q.r0 + tid; i < q.r1; i += nth) {
-            const uint32_t e1 = q.csr_ptr[i + 1];
-            const float4 pi = own.p[i];
-            const float dv = q.diag_val[i];
-            float s0 = 0.0f + dv * pi.x, s1 = 0.0f + dv * pi.y, s2 = 0.0f + dv * pi.z;
-            const float lam2 = 0.1f * 0.1f;
-            for (uint32_t e = q.csr_ptr[i] + 1; e < e1; ++e) {
-                const uint32_t enc = q.csr_enc[e];
-                const float a = (enc >> 31) ? -1.0f : -lam2;
-                const float4 pv = own.p[enc & 0x7FFFFFFFu];
-                s0 += a * pv.x; s1 += a * pv.y; s2 += a * pv.z;
+        for (uint32_t i0 = q.r0 + tid; i0 < q.r1; i0 += 2 * nth) {
+            const uint32_t i1 = i0 + nth;
+            const bool h1 = i1 < q.r1;
+            uint32_t a = q.csr_ptr[i0] + 1, ae = q.csr_ptr[i0 + 1];
+            uint32_t b = h1 ? q.csr_ptr[i1] + 1 : 0u, be = h1 ? q.csr_ptr[i1 + 1] : 0u;
+            const float4 pa = own.p[i0];
+            const float4 pb = h1 ? own.p[i1] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const float da = q.diag_val[i0], db = h1 ? q.diag_val[i1] : 0.0f;
+            float a0 = 0.0f + da * pa.x, a1 = 0.0f + da * pa.y, a2 = 0.0f + da * pa.z;
+            float b0 = 0.0f + db * pb.x, b1 = 0.0f + db * pb.y, b2 = 0.0f + db * pb.z;
+            while (a < ae || b < be) {
+                uint32_t ea = 0, eb = 0;
+                if (a < ae) ea = q.csr_enc[a];
+                if (b < be) eb = q.csr_enc[b];
+                float4 va = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vb = va;
+                if (a < ae) va = own.p[ea & 0x7FFFFFFFu];
+                if (b < be) vb = own.p[eb & 0x7FFFFFFFu];
+                if (a < ae) { const float w = (ea >> 31) ? -1.0f : -lam2; a0 += w * va.x; a1 += w * va.y; a2 += w * va.z; ++a; }
+                if (b < be) { const float w = (eb >> 31) ? -1.0f : -lam2; b0 += w * vb.x; b1 += w * vb.y; b2 += w * vb.z; ++b; }
             }
-            q.t[i] = s0; q.t[(size_t)R + i] = s1; q.t[2 * (size_t)R + i] = s2;
-            acc[0] += (double)pi.x * s0; acc[1] += (double)pi.y * s1; acc[2] += (double)pi.z * s2;
+            q.t[i0] = a0; q.t[(size_t)R + i0] = a1; q.t[2 * (size_t)R + i0] = a2;
+            acc[0] += (double)pa.x * a0; acc[1] += (double)pa.y * a1; acc[2] += (double)pa.z * a2;
+            if (h1) {
+                q.t[i1] = b0; q.t[(size_t)R + i1] = b1; q.t[2 * (size_t)R + i1] = b2;
+                acc[0] += (double)pb.x * b0; acc[1] += (double)pb.y * b1; acc[2] += (double)pb.z * b2;
+            }
         }
-        mg_push_partials(grid, q, acc, smem, 1);
-        alive = mg_barrier(grid, q, ++epoch) && alive;
-        mg_totals(q, 1, tot);
+        alive = mg_allreduce6(grid, q, acc, smem, 1, ++epoch, tot) && alive;
         float alpha[3];
         for (int c = 0; c < 3; ++c) alpha[c] = active[c] ? absNew[c] / (float)tot[c] : 0.0f;
 
@@ -218,19 +277,21 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
             const float4 pi = own.p[i];
             const float pv[3] = {pi.x, pi.y, pi.z};
             const float id = q.inv_diag[i];
+            float xv[3], rv0[3], tv[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const size_t o = (size_t)c * R + i; xv[c] = own.x[o]; rv0[c] = q.r[o]; tv[c] = q.t[o]; }
+#pragma unroll
             for (int c = 0; c < 3; ++c) {
                 if (!active[c]) continue;
                 const size_t o = (size_t)c * R + i;
-                own.x[o] += alpha[c] * pv[c];
-                const float rv = q.r[o] - alpha[c] * q.t[o];
+                own.x[o] = xv[c] + alpha[c] * pv[c];
+                const float rv = rv0[c] - alpha[c] * tv[c];
                 q.r[o] = rv;
                 acc[c] += (double)rv * rv;
                 acc[3 + c] += (double)rv * (id * rv);
             }
         }
-        mg_push_partials(grid, q, acc, smem, 0);
-        alive = mg_barrier(grid, q, ++epoch) && alive;
-        mg_totals(q, 0, tot);
+        alive = mg_allreduce6(grid, q, acc, smem, 0, ++epoch, tot) && alive;
         float beta[3] = {0.0f, 0.0f, 0.0f};
         bool upd[3];
         for (int c = 0; c < 3; ++c) {
@@ -244,15 +305,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
             upd[c] = true;
             if (++iters[c] >= q.max_iters) active[c] = false;
         }
-        // phase 3: p = z + beta p on the own rows, stored into every rank's copy (the all-gather)
+        // phase 3: p = z + beta p on the own rows; halo entries also into the copies of the ranks that read them
         if (upd[0] || upd[1] || upd[2])
             for (uint32_t i = q.r0 + tid; i < q.r1; i += nth) {
                 float4 pi = own.p[i];
                 const float id = q.inv_diag[i];
-                if (upd[0]) pi.x = id * q.r[i] + beta[0] * pi.x;
-                if (upd[1]) pi.y = id * q.r[(size_t)R + i] + beta[1] * pi.y;
-                if (upd[2]) pi.z = id * q.r[2 * (size_t)R + i] + beta[2] * pi.z;
-                for (uint32_t k = 0; k < q.nranks; ++k) mg_carve(q.peer[k], R).p[i] = pi;
+                const float r0v = q.r[i], r1v = q.r[(size_t)R + i], r2v = q.r[2 * (size_t)R + i];
+                if (upd[0]) pi.x = id * r0v + beta[0] * pi.x;
+                if (upd[1]) pi.y = id * r1v + beta[1] * pi.y;
+                if (upd[2]) pi.z = id * r2v + beta[2] * pi.z;
+                own.p[i] = pi;
+                mg_push_p(q, i, pi);
             }
         ++loops;
         alive = mg_barrier(grid, q, ++epoch) && alive;
@@ -261,9 +324,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
     for (int k = 0; k < 6; ++k) acc[k] = 0.0;
     for (uint32_t i = q.r0 + tid; i < q.r1; i += nth)
         for (int c = 0; c < 3; ++c) acc[c] += (double)own.x[(size_t)c * R + i];
-    mg_push_partials(grid, q, acc, smem, 1);
-    alive = mg_barrier(grid, q, ++epoch) && alive;
-    mg_totals(q, 1, tot);
+    alive = mg_allreduce6(grid, q, acc, smem, 1, ++epoch, tot) && alive;
     float mean[3];
     for (int c = 0; c < 3; ++c) mean[c] = R ? (float)(tot[c] / (double)R) : 0.0f;
     for (uint32_t i = q.r0 + tid; i < q.r1; i += nth)
@@ -291,6 +352,7 @@ struct MgState {
     uint32_t R = 0, rank = 0, nranks = 1, epoch = 0;
     DevBuf<double> blockpart;
     DevBuf<uint32_t> status;
+    DevBuf<uint8_t> dest;     // halo destination mask of every row
     uint32_t *pinned = nullptr;
 };
 
@@ -322,9 +384,11 @@ int seam_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t nranks, void *handle64)
     m->peer[rank] = m->block;
     B2_TRY(m->blockpart.alloc(4096 * 8));   // every allocation happens here: nothing inside the solve waits for the device
     B2_TRY(m->status.alloc(16));
+    B2_TRY(m->dest.alloc(c->R));
     B2_CUDA(cudaHostAlloc((void **)&m->pinned, 16 * sizeof(uint32_t), cudaHostAllocDefault));
-    cudaFuncAttributes fa;   // load the kernel now (the first launch of a lazily loaded kernel synchronises the context)
+    cudaFuncAttributes fa;   // load the kernels now (the first launch of a lazily loaded kernel synchronises the context)
     B2_CUDA(cudaFuncGetAttributes(&fa, (const void *)k_pcg_mg));
+    B2_CUDA(cudaFuncGetAttributes(&fa, (const void *)k_pcg_mg_dest));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
     memset(&h, 0, sizeof(h));
@@ -375,7 +439,8 @@ int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info)
     PcgMg q;
     q.R = R; q.r0 = r0; q.r1 = r1; q.rank = m->rank; q.nranks = m->nranks;
     q.csr_ptr = c->csr_ptr.p; q.csr_enc = c->csr_enc.p; q.diag_val = c->seam_dval.p; q.inv_diag = c->seam_diag.p; q.rhs = c->seam_rhs.p;
-    q.r = c->seam_r.p; q.t = c->seam_t.p; q.blockpart = m->blockpart.p; q.status = m->status.p;
+    q.r = c->seam_r.p; q.t = c->seam_t.p; q.blockpart = m->blockpart.p; q.status = m->status.p; q.dest = m->dest.p;
+    if (r1 > r0) B2_LAUNCH k_pcg_mg_dest<<<(r1 - r0 + 255) / 256, 256, 0, s>>>(R, r0, r1, m->rank, m->nranks, c->csr_ptr.p, c->csr_enc.p, m->dest.p);
     for (int k = 0; k < MG_MAX_RANKS; ++k) q.peer[k] = m->peer[k];
     q.max_iters = 1000u; q.tol = 0.0001f; q.epoch0 = m->epoch; q.spin_limit = 50ull * 1000 * 1000;
     void *args[] = {&q};

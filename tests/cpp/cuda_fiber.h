@@ -234,6 +234,17 @@ template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned del
     emul::wait(w->bar);
     return r;
 }
+// redux.sync: every lane of the warp arrives (each with the mask of its own group); minimum over the lanes named in the mask
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v)
+{
+    emul::Warp *w = emul::g_cur->warp;
+    w->slot[threadIdx.x & 31u] = v;
+    emul::wait(w->bar);
+    unsigned r = 0xFFFFFFFFu;
+    for (unsigned l = 0; l < 32; ++l) if ((mask >> l) & 1u) r = std::min(r, (unsigned)w->slot[l]);
+    emul::wait(w->bar);
+    return r;
+}
 static inline unsigned __ballot_sync(unsigned, bool p)
 {
     emul::Warp *w = emul::g_cur->warp;

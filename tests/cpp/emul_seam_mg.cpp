@@ -46,20 +46,21 @@ int emul_seam_mg(const float *verts, uint32_t Vn, const uint32_t *faces, uint32_
     // ---- assembly (seam_run with solve = false), identical on every rank ----
     const uint32_t vb = (Vn + 127) / 128;
     std::vector<uint32_t> cnt((size_t)Vn + 1, 0u), row_ptr((size_t)Vn + 1, 0u);
-    emul::launch_serial(vb, 128, [&] { k_vertex_labels<false>(Vn, vf_ptr, vf_idx, labels, cnt.data(), nullptr, nullptr, nullptr); });
+    uint32_t limit_flags = 0;   // overflow of the fixed per-vertex / per-edge caps (none on these scenes)
+    emul::launch_serial(vb, 128, [&] { k_vertex_labels<false>(Vn, vf_ptr, vf_idx, labels, cnt.data(), nullptr, nullptr, nullptr, &limit_flags); });
     for (uint32_t i = 0; i < Vn; ++i) row_ptr[i + 1] = row_ptr[i] + cnt[i];
     const uint32_t R = row_ptr[Vn];
     std::vector<uint32_t> row_label(R ? R : 1), row_vertex(R ? R : 1);
-    emul::launch_serial(vb, 128, [&] { k_vertex_labels<true>(Vn, vf_ptr, vf_idx, labels, nullptr, row_ptr.data(), row_label.data(), row_vertex.data()); });
+    emul::launch_serial(vb, 128, [&] { k_vertex_labels<true>(Vn, vf_ptr, vf_idx, labels, nullptr, row_ptr.data(), row_label.data(), row_vertex.data(), &limit_flags); });
     SeamMesh m{verts, faces, vf_ptr, vf_idx, vv_ptr, vv_idx, labels, row_ptr.data(), row_label.data(), vd.data()};
     std::fill(cnt.begin(), cnt.end(), 0u);
-    emul::launch_serial(vb, 128, [&] { k_arows<false>(Vn, m, cnt.data(), nullptr, nullptr, nullptr); });
+    emul::launch_serial(vb, 128, [&] { k_arows<false>(Vn, m, cnt.data(), nullptr, nullptr, nullptr, &limit_flags); });
     std::vector<uint32_t> arow_ptr((size_t)Vn + 1, 0u);
     for (uint32_t i = 0; i < Vn; ++i) arow_ptr[i + 1] = arow_ptr[i] + cnt[i];
     const uint32_t A = arow_ptr[Vn];
     std::vector<uint32_t> arow_rows(2 * (size_t)A + 2);
     std::vector<float> arow_b(3 * (size_t)A + 3);
-    emul::launch_serial(vb, 128, [&] { k_arows<true>(Vn, m, nullptr, arow_ptr.data(), arow_rows.data(), arow_b.data()); });
+    emul::launch_serial(vb, 128, [&] { k_arows<true>(Vn, m, nullptr, arow_ptr.data(), arow_rows.data(), arow_b.data(), &limit_flags); });
     std::vector<uint32_t> rcnt((size_t)R + 1, 0u), csr_ptr((size_t)R + 1, 0u);
     const uint32_t rb = (R + 127) / 128;
     if (R) emul::launch_serial(rb, 128, [&] { k_matrix<false>(R, m, row_vertex.data(), arow_ptr.data(), arow_rows.data(), arow_b.data(), rcnt.data(),
@@ -82,6 +83,8 @@ int emul_seam_mg(const float *verts, uint32_t Vn, const uint32_t *faces, uint32_
     std::vector<std::vector<double> > bp(ranks, std::vector<double>((size_t)grid * 8, 0.0));
     std::vector<std::vector<uint32_t> > st(ranks, std::vector<uint32_t>(16, 0u));
     std::vector<PcgMg> q(ranks);
+    std::vector<std::vector<uint8_t> > dest(ranks, std::vector<uint8_t>(R, 0xFF));   // 0xFF outside the own rows: never read
+    uint32_t halo_rows = 0;
     for (uint32_t k = 0; k < ranks; ++k) {
         PcgMg &p = q[k];
         p.R = R; p.r0 = (uint32_t)((uint64_t)R * k / ranks); p.r1 = (uint32_t)((uint64_t)R * (k + 1) / ranks);
@@ -91,7 +94,12 @@ int emul_seam_mg(const float *verts, uint32_t Vn, const uint32_t *faces, uint32_
         for (uint32_t j = 0; j < (uint32_t)MG_MAX_RANKS; ++j) p.peer[j] = j < ranks ? (void *)blocks[j].data() : nullptr;
         p.max_iters = 1000u; p.tol = 0.0001f; p.epoch0 = 0xFFFFFFF0u;   // start close to the wrap-around of the epoch counter
         p.spin_limit = 1000000000ull;
+        if (p.r1 > p.r0)
+            emul::launch_serial((p.r1 - p.r0 + 255) / 256, 256, [&] { k_pcg_mg_dest(R, p.r0, p.r1, k, ranks, csr_ptr.data(), csr_enc.data(), dest[k].data()); });
+        p.dest = dest[k].data();
+        for (uint32_t i = p.r0; i < p.r1; ++i) halo_rows += dest[k][i] != 0;
     }
+    st[0][15] = halo_rows;   // reported through the status words of rank 0
     for (uint32_t k = 0; k < ranks; ++k)      // flags start at epoch0 ("everybody reached the epochs used so far")
         for (uint32_t j = 0; j < (uint32_t)MG_MAX_RANKS; ++j) mg_carve(blocks[k].data(), R).flag[j] = 0xFFFFFFF0u;
     if (!emul::launch_ranks(ranks, grid, MG_THREADS, [&](unsigned rank) { k_pcg_mg(q[rank]); })) return -1;

@@ -584,6 +584,7 @@ def test_device_multi_gpu_seam_solve(emul, orc, scene_mod, get_scene, ranks, gri
     L.emul_seam_mg_free(xp)
     st = status.reshape(ranks, 16)
     assert Rn == len(o["row_label"]) and not st[:, 7].any()
+    assert 0 < st[0, 15] < Rn          # only the halo rows of the search direction travel
     for k in range(ranks):
         assert np.array_equal(x[k].view(np.uint32), x[0].view(np.uint32))
         assert st[k, :3].tolist() == list(o["iterations"])
