@@ -164,7 +164,7 @@ struct b2tex_ctx {
     bool bvh_built = false;
     b2::DevBuf<uint32_t> vrank, vorder;  // Morton rank of every vertex and its inverse
     // persistent scratch (grow only): cudaMalloc/cudaFree inside a stage would serialise the device
-    b2::DevBuf<uint32_t> s_bnd, s_ids_in, s_ids_out, s_counters, s_vi_in, s_cnt32, s_row_vertex, s_rcnt, s_pass_bits;
+    b2::DevBuf<uint32_t> s_bnd, s_ids_in, s_ids_out, s_counters, s_vi_in, s_cnt32, s_row_vertex, s_rcnt, s_pass_bits, s_limits;
     b2::DevBuf<uint64_t> s_keys_in, s_keys_out, s_vk_in, s_vk_out, s_cnt64;
     b2::DevBuf<int> s_parent_internal, s_parent_leaf;
 

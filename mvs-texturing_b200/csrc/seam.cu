@@ -471,9 +471,13 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
     DevBuf<uint32_t> &cnt = c->s_cnt32, &row_vertex = c->s_row_vertex;
     B2_TRY(cnt.alloc((size_t)Vn + 1));
     B2_TRY(cnt.zero(s));
+    B2_TRY(c->s_limits.alloc(1));
+    B2_TRY(c->s_limits.zero(s));
+    uint32_t *limit_flags = c->s_limits.p;   // bit 0: MAXL labels on a vertex, bit 1: > 16 faces on an edge
     B2_TRY(c->row_ptr.alloc((size_t)Vn + 1));
     const uint32_t vb = (Vn + 127) / 128;
-    B2_LAUNCH k_vertex_labels<false><<<vb, 128, 0, s>>>(Vn, c->vf_ptr.p, c->vf_idx.p, c->labels.p, cnt.p, nullptr, nullptr, nullptr);
+    B2_LAUNCH k_vertex_labels<false><<<vb, 128, 0, s>>>(Vn, c->vf_ptr.p, c->vf_idx.p, c->labels.p, cnt.p, nullptr, nullptr, nullptr,
+                                              limit_flags);
     B2_KERNEL_CHECK();
     B2_TRY(cub_exclusive_sum_u32(c, cnt.p, c->row_ptr.p, (size_t)Vn + 1));
     uint32_t R = 0;
@@ -548,6 +552,7 @@ int seam_run(b2tex_ctx *c, b2tex_seam_info *info, bool solve)
     info->cg_ms = 0.0f;
 
     tm_asm.reset();
+    B2_TRY(c->seam_status.alloc(16));
     B2_TRY(c->seam_status.zero(s));
     if (R && solve) {   // solve == false: assembly only, the multi-GPU solver (seam_mg.cu) takes over
         int per_sm = 0;
