@@ -210,11 +210,25 @@ def verify_against_oracle(scene_mod, s, adj, rings, runner, res, world):
     out["mrf_energy_identical"] = out["mrf_energy_fixed"] == out["mrf_energy_fixed_ref"]
     x = c.seam_download(res["seam"])["x"]
     out["seam_rows_equal"] = bool(int(res["seam"].num_rows) == len(og["row_label"]))
+    seam_ok = False
     if out["seam_rows_equal"] and out["labels_bit_exact"]:
+        import scipy.sparse as sp
+        cp, cc, cv = og["csr"]
+        A = sp.csr_matrix((cv.astype(np.float64), cc.astype(np.int64), cp.astype(np.int64)), shape=(len(cp) - 1,) * 2)
+        x64, rhs = x.astype(np.float64), og["rhs"].astype(np.float64)
+        # north_star's bar: the residual of the returned adjust values on the reference system, relative L2, per channel
+        out["seam_true_residual"] = [float(np.linalg.norm(A @ x64[:, ch] - rhs[:, ch]) / max(1e-300, np.linalg.norm(rhs[:, ch])))
+                                     for ch in range(3)]
+        out["seam_true_residual_ref"] = [float(np.linalg.norm(A @ og["x"][:, ch].astype(np.float64) - rhs[:, ch]) /
+                                               max(1e-300, np.linalg.norm(rhs[:, ch]))) for ch in range(3)]
         out["seam_rel_l2_vs_ref"] = float(np.linalg.norm(x - og["x"]) / max(1e-30, np.linalg.norm(og["x"])))
         out["cg_iterations_ref"] = [int(v) for v in og["iterations"]]
-    out["ok"] = bool(out["labels_bit_exact"] and out["mrf_energy_identical"] and out.get("data_costs_bit_exact", True)
-                     and out.get("seam_rel_l2_vs_ref", 1.0) < 5e-3)
+        same_stop = list(res["seam"].iterations) == out["cg_iterations_ref"]
+        # the system is singular and the residual hovers around 1e-4 for ~20 iterations while x still moves ~0.25 % per
+        # iteration (measured on C3, NOTES.md): the distance of the solutions is only meaningful for equal stop iterations
+        out["seam_same_stop_iterations"] = bool(same_stop)
+        seam_ok = max(out["seam_true_residual"]) < 2e-4 and out["seam_rel_l2_vs_ref"] < (5e-3 if same_stop else 5e-2)
+    out["ok"] = bool(out["labels_bit_exact"] and out["mrf_energy_identical"] and out.get("data_costs_bit_exact", True) and seam_ok)
     out["cpu_full_workload"] = {"value": s.num_faces / (t3 - t0), "unit": UNIT, "seconds": round(t3 - t0, 2)}
     return out
 
