@@ -2,51 +2,54 @@
 //
 // Replaces the replicated k_pcg (seam.cu) when the job runs on several GPUs (one process per GPU): the rows of
 // Lhs x = Rhs (global_seam_leveling.cpp:245-277) are split into contiguous ranges, one per rank.  Every rank runs the
-// same persistent cooperative Jacobi-PCG as k_pcg on ITS rows and, inside the kernel, exchanges with its peers through
-// peer-mapped memory (cudaIpc handles, NVLink / NVSwitch loads and stores) instead of returning to the host for NCCL:
-//   * search direction p: after "p = z + beta p" every rank STORES the entries of its HALO rows -- the rows some column
-//     of a peer's rows refers to, 0.4 % of the rows at 2 ranks and 2 % at 8 on the C3 system (the Laplacian couples a
-//     vertex only to its 1-ring) -- into the copies of exactly those peers, so the SpMV of the next iteration reads only
-//     local memory; the destination mask of every row is derived from the CSR once per solve;
-//   * dot products: every rank stores its fp64 partial sums into every peer's slot table; after the barrier all ranks
-//     add the P slots in rank order -> bit-identical scalars everywhere, no divergence of the iteration;
-//   * barrier: one epoch counter per (rank, peer) in peer memory, store-release at system scope after a system fence,
-//     polled with load-acquire; three per iteration (p.t, |r|^2 & r.z, p exchange), each bracketed by grid.sync().
-// Results are deterministic for a given rank count; they differ from the single-GPU kernel only by the summation
-// order of the reductions (per rank, then across ranks).
+// same persistent Jacobi-PCG as k_pcg on ITS rows and, inside the kernel, exchanges with its peers through peer-mapped
+// memory (cudaIpc handles, NVLink / NVSwitch stores) instead of returning to the host for NCCL:
+//   * halo of the search direction: a rank's SpMV reads p of a few rows it does not own (0.4 % of the rows at 2 ranks,
+//     2 % at 8 on the C3 system: the Laplacian couples a vertex only to its 1-ring).  It keeps its OWN copy of p for those
+//     rows and updates it itself: the owner stores z = M^-1 r of its halo rows into the readers' z arrays right after the
+//     residual update -- BEFORE the all-reduce that yields beta -- and every reader then forms p = z + beta p for its
+//     imported rows with the same two roundings as the owner.  The exchange therefore rides on the barrier of the
+//     all-reduce that CG needs anyway; there is no third cross-GPU barrier per iteration;
+//   * dot products: two all-reduces per iteration (p.t; |r|^2 and r.z).  Every block leaves its fp64 partial sums in a
+//     table and takes a ticket; the LAST block of the rank adds the table in block order, stores the rank's sums into slot
+//     [parity][rank] of every peer, fences at system scope and raises its epoch flag at every peer; all blocks of all
+//     ranks wait for all flags and add the P slots in rank order -> bit-identical scalars on every GPU.  This one step is
+//     reduction, cross-GPU barrier and grid-wide barrier at once (no cooperative-groups grid.sync in the loop);
+//   * one device-local barrier per iteration (ticket counter) between the update of p and the next SpMV.
+// Results are deterministic for a given rank count and grid; they differ from the single-GPU kernel only by the
+// summation order of the reductions (per block, per rank, then across ranks).
 //
-// Measured (round 2, C3 on 2 B200): a first version that all-gathered the whole slice of p every iteration and let every
-// thread issue a system fence per barrier took 146 us per iteration against 71 us on one GPU; see DESIGN.md section 5.
-#include <cooperative_groups.h>
+// Measured (round 2, C3 on 2 B200, 149 iterations): all-gather of the whole slice of p + one system fence per thread:
+// 146 us per iteration; halo-only pushes of p with three flag barriers bracketed by grid.sync(): 113 us; one GPU: 70 us.
 #include <math.h>
 
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace b2 {
 
 constexpr int MG_MAX_RANKS = 8;
 
 // Layout of the peer-visible block every rank allocates (and exports through one cudaIpc handle):
-//   float4 p[R] | float x[3][R] | double part[2][MG_MAX_RANKS][8] | uint32 flag[MG_MAX_RANKS] (padded to 64 B)
+//   float4 p[R] | float4 z[R] | float x[3][R] | double part[2][MG_MAX_RANKS][8] | uint32 flag[MG_MAX_RANKS] (padded to 64 B)
+// p is only written by the owner of the block; z (halo rows), x (final all-gather), part and flag are written by peers.
 struct MgBlock {
-    float4 *p;
+    float4 *p, *z;
     float *x;
     double *part;
     uint32_t *flag;
 };
-// every section starts on a 64-byte boundary (R may be odd: 28 R bytes would leave the doubles misaligned)
+// every section starts on a 64-byte boundary (R may be odd: 12 R bytes would leave the doubles misaligned)
 __host__ __device__ inline size_t mg_align64(size_t n) { return (n + 63) & ~(size_t)63; }
 __host__ __device__ inline size_t mg_block_bytes(uint32_t R)
 {
-    return mg_align64((size_t)R * 16) + mg_align64((size_t)R * 12) + mg_align64(2 * MG_MAX_RANKS * 8 * sizeof(double)) + 64;
+    return 2 * mg_align64((size_t)R * 16) + mg_align64((size_t)R * 12) + mg_align64(2 * MG_MAX_RANKS * 8 * sizeof(double)) + 64;
 }
 __host__ __device__ inline MgBlock mg_carve(void *base, uint32_t R)
 {
     MgBlock b;
     char *c = (char *)base;
     b.p = (float4 *)c; c += mg_align64((size_t)R * 16);
+    b.z = (float4 *)c; c += mg_align64((size_t)R * 16);
     b.x = (float *)c; c += mg_align64((size_t)R * 12);
     b.part = (double *)c; c += mg_align64(2 * MG_MAX_RANKS * 8 * sizeof(double));
     b.flag = (uint32_t *)c;
@@ -60,8 +63,11 @@ struct PcgMg {
     const float *diag_val, *inv_diag, *rhs;   // replicated assembly (k_matrix), indexed by global row
     float *r, *t;                // [3][R] local scratch (own rows used)
     const uint8_t *dest;         // [R] for own rows: bit k = rank k reads this row's entry of p (halo destination mask)
+    const uint32_t *imp;         // rows of other ranks whose entry of p this rank's SpMV reads (halo imports)
+    const uint32_t *n_imp;       // their number (device side: written by k_pcg_mg_imports)
     double *blockpart;           // [grid][8] per-block partials of this rank
-    uint32_t *status;            // [0..2] iterations, [3..5] residual bits, [6] loops, [7] barrier timeouts
+    uint32_t *status;            // [0..2] iterations, [3..5] residual bits, [6] loops, [7] barrier timeouts, [8] epoch,
+                                 // [10] tickets of the all-reduces, [11] tickets of the device-local barrier
     void *peer[MG_MAX_RANKS];    // base pointers of every rank's MgBlock (peer[rank] = own)
     uint32_t max_iters;
     float tol;
@@ -79,6 +85,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
 {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -99,113 +111,137 @@ __device__ __forceinline__ void mg_block_reduce6(double v[6], double *smem)
     }
 }
 
-// Cross-GPU barrier, called by ALL threads of the grid.  Everything every thread of this rank stored to peer memory
-// before the call is visible to every thread of every rank after it.  One system-scope fence per BLOCK (after the block's
-// own barrier; the fence of one thread is cumulative over what the block barrier ordered before it), not one per thread.
-__device__ __forceinline__ bool mg_barrier(cg::grid_group &grid, const PcgMg &q, uint32_t epoch)
+// All-reduce of six partial sums across all blocks of all ranks = grid-wide barrier + cross-GPU barrier, in one step.
+// `seq` counts the calls of this solve (1, 2, ...): the ticket that completes call `seq` is seq * gridDim.x.  `remote`:
+// this rank stored into peer memory since the previous call (halo of z, final x): those stores are fenced at system
+// scope by one thread per block, after the block's own barrier, before the ticket.  Everything any thread of any rank
+// stored before its call is visible to every thread of every rank after it.
+__device__ __forceinline__ bool mg_allreduce6(const PcgMg &q, double acc[6], double *smem, uint32_t *s_last, int parity,
+                                              uint32_t epoch, uint32_t seq, bool remote, bool alive, double tot[6])
 {
-    __syncthreads();
-    if (threadIdx.x == 0) __threadfence_system();
-    grid.sync();
-    if (blockIdx.x == 0 && threadIdx.x < q.nranks) {
-        const uint32_t k = threadIdx.x;
-        __threadfence_system();
-        st_release_sys(mg_carve(q.peer[k], q.R).flag + q.rank, epoch);          // tell peer k: rank `rank` reached `epoch`
-        const uint32_t *mine = mg_carve(q.peer[q.rank], q.R).flag + k;          // wait until peer k reached it too
-        unsigned long long spins = 0;
-        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-            __nanosleep(32);
-            if (++spins > q.spin_limit) { atomicAdd(q.status + 7, 1u); break; }
-        }
-    }
-    grid.sync();
-    // the verdict must be grid-uniform: every thread reads the timeout counter the pollers wrote before the
-    // grid-wide barrier, so all threads leave the PCG loop in the same iteration (no mismatched grid.sync)
-    return __ldcg(q.status + 7) == 0u;
-}
-
-// All-reduce of six partial sums across the ranks, fused with the barrier: per-block partials -> grid.sync -> block 0 sums
-// them (fixed order), stores the rank's sums into slot [parity][rank] of every peer, fences, raises its epoch flag at every
-// peer and waits for theirs -> grid.sync -> every thread adds the slots in rank order (identical on every GPU).
-__device__ __forceinline__ bool mg_allreduce6(cg::grid_group &grid, const PcgMg &q, double acc[6], double *smem, int parity,
-                                              uint32_t epoch, double tot[6])
-{
+    // after a timeout (a peer or a block is gone) nobody waits any more; `alive` is uniform within a block, and no
+    // construct below needs it to be uniform across blocks (tickets and polls all time out by themselves)
+    if (!alive) { for (int k = 0; k < 6; ++k) tot[k] = 0.0; return false; }
     mg_block_reduce6(acc, smem);
-    if (threadIdx.x == 0) for (int k = 0; k < 6; ++k) q.blockpart[(size_t)blockIdx.x * 8 + k] = acc[k];
-    grid.sync();
-    if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 6; ++k) q.blockpart[(size_t)blockIdx.x * 8 + k] = acc[k];
+        if (remote) __threadfence_system(); else __threadfence();
+        const uint32_t ticket = atomicAdd(q.status + 10, 1u);
+        *s_last = (ticket + 1u == seq * gridDim.x) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (*s_last) {   // the last block of this rank: every other block's partials and stores are behind its ticket
+        __threadfence();
         double v[6] = {0, 0, 0, 0, 0, 0};
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
-            for (int k = 0; k < 6; ++k) v[k] += q.blockpart[(size_t)b * 8 + k];
+        for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+            for (int k = 0; k < 6; ++k) v[k] += __ldcg(q.blockpart + (size_t)b * 8 + k);
         mg_block_reduce6(v, smem);
         if (threadIdx.x < q.nranks) {
             const uint32_t k = threadIdx.x;
             const MgBlock pk = mg_carve(q.peer[k], q.R);
             for (int j = 0; j < 6; ++j) pk.part[((size_t)parity * MG_MAX_RANKS + q.rank) * 8 + j] = v[j];
             __threadfence_system();
-            st_release_sys(pk.flag + q.rank, epoch);
-            const uint32_t *mine = mg_carve(q.peer[q.rank], q.R).flag + k;
-            unsigned long long spins = 0;
-            while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-                __nanosleep(32);
-                if (++spins > q.spin_limit) { atomicAdd(q.status + 7, 1u); break; }
-            }
+            st_release_sys(pk.flag + q.rank, epoch);                 // tell rank k: rank `rank` reached `epoch`
         }
     }
-    grid.sync();
+    if (threadIdx.x < q.nranks) {                                    // every block waits until every rank reached it
+        const uint32_t *mine = mg_carve(q.peer[q.rank], q.R).flag + threadIdx.x;
+        unsigned long long spins = 0;
+        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+            __nanosleep(20);
+            if (++spins > q.spin_limit) { atomicAdd(q.status + 7, 1u); break; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last[1] = __ldcg(q.status + 7);   // one verdict per block
     const double *part = mg_carve(q.peer[q.rank], q.R).part + (size_t)parity * MG_MAX_RANKS * 8;
     for (int k = 0; k < 6; ++k) {
         double sum = 0.0;
         for (uint32_t r = 0; r < q.nranks; ++r) sum += __ldcg(part + (size_t)r * 8 + k);   // rank order: identical on every GPU
         tot[k] = sum;
     }
-    return __ldcg(q.status + 7) == 0u;
+    __syncthreads();
+    return s_last[1] == 0u;
 }
 
-// the entry of p of one own row goes to the ranks that read it
-__device__ __forceinline__ void mg_push_p(const PcgMg &q, uint32_t i, const float4 &v)
+// device-local barrier of the persistent grid (ticket counter; a timeout instead of a hang if a block went away)
+__device__ __forceinline__ bool mg_local_sync(const PcgMg &q, uint32_t *s_last, uint32_t seq, bool alive)
+{
+    if (!alive) return false;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(q.status + 11, 1u);
+        const uint32_t target = seq * gridDim.x;
+        unsigned long long spins = 0;
+        while ((int32_t)(ld_acquire_gpu(q.status + 11) - target) < 0) {
+            __nanosleep(20);
+            if (++spins > q.spin_limit) { atomicAdd(q.status + 7, 1u); break; }
+        }
+        s_last[1] = __ldcg(q.status + 7);
+    }
+    __syncthreads();
+    return s_last[1] == 0u;
+}
+
+// z = M^-1 r of one own row goes to the ranks that read this row's entry of p
+__device__ __forceinline__ void mg_push_z(const PcgMg &q, uint32_t i, const float4 &v)
 {
     for (uint32_t mk = q.dest[i]; mk; mk &= mk - 1u) {
         const uint32_t k = (uint32_t)__ffs((int)mk) - 1u;
-        mg_carve(q.peer[k], q.R).p[i] = v;
+        mg_carve(q.peer[k], q.R).z[i] = v;
     }
+}
+
+// owner of a row: rank k owns [R k / P, R (k + 1) / P)
+__device__ __forceinline__ uint32_t mg_owner(uint32_t row, uint32_t R, uint32_t nranks)
+{
+    uint32_t k = (uint32_t)(((uint64_t)row * nranks) / R);
+    while (k + 1 < nranks && row >= (uint32_t)((uint64_t)R * (k + 1) / nranks)) ++k;
+    while (k > 0 && row < (uint32_t)((uint64_t)R * k / nranks)) --k;
+    return k;
 }
 
 }  // namespace
 
 // destination mask of every own row: the ranks whose row ranges hold a row with this row among its columns (the matrix is
-// symmetric: those are the ranks of this row's own columns)
+// symmetric: those are the owners of this row's own columns); the same pass marks the columns this rank imports
 __global__ void __launch_bounds__(256) k_pcg_mg_dest(uint32_t R, uint32_t r0, uint32_t r1, uint32_t rank, uint32_t nranks,
                                                      const uint32_t *__restrict__ csr_ptr, const uint32_t *__restrict__ csr_enc,
-                                                     uint8_t *dest)
+                                                     uint8_t *dest, uint8_t *imp_mark)
 {
     const uint32_t i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= r1) return;
     uint32_t mask = 0;
     for (uint32_t e = csr_ptr[i] + 1; e < csr_ptr[i + 1]; ++e) {
         const uint32_t col = csr_enc[e] & 0x7FFFFFFFu;
-        // rank k owns [R k / P, R (k + 1) / P): k = floor((col P + P - 1) / R) up to the rounding of the bounds
-        uint32_t k = (uint32_t)(((uint64_t)col * nranks) / R);
-        while (k + 1 < nranks && col >= (uint32_t)((uint64_t)R * (k + 1) / nranks)) ++k;
-        while (k > 0 && col < (uint32_t)((uint64_t)R * k / nranks)) --k;
-        if (k != rank) mask |= 1u << k;
+        const uint32_t k = mg_owner(col, R, nranks);
+        if (k != rank) { mask |= 1u << k; imp_mark[col] = 1; }
     }
     dest[i] = (uint8_t)mask;
+}
+// the marked rows, in any order
+__global__ void __launch_bounds__(256) k_pcg_mg_imports(uint32_t R, const uint8_t *__restrict__ imp_mark, uint32_t *imp, uint32_t *n_imp)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < R && imp_mark[i]) imp[atomicAdd(n_imp, 1u)] = i;
 }
 
 constexpr int MG_THREADS = 1024;
 __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
 {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double smem[(MG_THREADS / 32) * 6];
+    __shared__ double smem[(MG_THREADS / 32) * 6 + 1];
+    uint32_t *s_last = reinterpret_cast<uint32_t *>(smem + (MG_THREADS / 32) * 6);   // [0] "last block of the rank", [1] failure verdict
     const uint32_t R = q.R;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const MgBlock own = mg_carve(q.peer[q.rank], R);
+    const uint32_t n_imp = *q.n_imp;
     double acc[6], tot[6];
-    uint32_t epoch = q.epoch0;
+    uint32_t epoch = q.epoch0, seq = 0, lseq = 0;
+    int parity = 0;
     bool alive = true;
 
-    // r = rhs, p = M^-1 r on the own rows; the halo entries of p go to the ranks that read them
+    // r = rhs, p = M^-1 r on the own rows AND on the imported rows (the assembly is replicated: no exchange needed)
     for (int k = 0; k < 6; ++k) acc[k] = 0.0;
     for (uint32_t i = q.r0 + tid; i < q.r1; i += nth) {
         const float id = q.inv_diag[i];
@@ -218,13 +254,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
             acc[c] += (double)rv * rv;
             acc[3 + c] += (double)rv * pv[c];
         }
-        const float4 p4 = make_float4(pv[0], pv[1], pv[2], 0.0f);
-        own.p[i] = p4;
-        mg_push_p(q, i, p4);
+        own.p[i] = make_float4(pv[0], pv[1], pv[2], 0.0f);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) __threadfence_system();   // the pushes of this block before the flags of the all-reduce below
-    alive = mg_allreduce6(grid, q, acc, smem, 0, ++epoch, tot) && alive;
+    for (uint32_t j = tid; j < n_imp; j += nth) {
+        const uint32_t i = q.imp[j];
+        const float id = q.inv_diag[i];
+        own.p[i] = make_float4(id * q.rhs[i], id * q.rhs[(size_t)R + i], id * q.rhs[2 * (size_t)R + i], 0.0f);
+    }
+    alive = mg_allreduce6(q, acc, smem, s_last, parity, ++epoch, ++seq, false, alive, tot); parity ^= 1;
     float rhsNorm2[3], threshold[3], absNew[3], resNorm2[3];
     bool active[3];
     uint32_t iters[3] = {0, 0, 0};
@@ -238,7 +275,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
     uint32_t loops = 0;
     const float lam2 = 0.1f * 0.1f;
     while (alive && (active[0] || active[1] || active[2])) {
-        // phase 1: t = A p on the own rows (own entries and the halo the peers pushed are local), p.t; two rows in flight
+        // phase 1: t = A p on the own rows (own entries and the imported halo entries are local), p.t; two rows in flight
         for (int k = 0; k < 6; ++k) acc[k] = 0.0;
         for (uint32_t i0 = q.r0 + tid; i0 < q.r1; i0 += 2 * nth) {
             const uint32_t i1 = i0 + nth;
@@ -267,17 +304,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
                 acc[0] += (double)pb.x * b0; acc[1] += (double)pb.y * b1; acc[2] += (double)pb.z * b2;
             }
         }
-        alive = mg_allreduce6(grid, q, acc, smem, 1, ++epoch, tot) && alive;
+        alive = mg_allreduce6(q, acc, smem, s_last, parity, ++epoch, ++seq, false, alive, tot); parity ^= 1;
         float alpha[3];
         for (int c = 0; c < 3; ++c) alpha[c] = active[c] ? absNew[c] / (float)tot[c] : 0.0f;
 
-        // phase 2: x += a p, r -= a t, |r|^2, r.z
+        // phase 2: x += a p, r -= a t, |r|^2, r.z; z = M^-1 r of the halo rows goes to the ranks that read them
         for (int k = 0; k < 6; ++k) acc[k] = 0.0;
         for (uint32_t i = q.r0 + tid; i < q.r1; i += nth) {
             const float4 pi = own.p[i];
             const float pv[3] = {pi.x, pi.y, pi.z};
             const float id = q.inv_diag[i];
-            float xv[3], rv0[3], tv[3];
+            float xv[3], rv0[3], tv[3], zv[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
             for (int c = 0; c < 3; ++c) { const size_t o = (size_t)c * R + i; xv[c] = own.x[o]; rv0[c] = q.r[o]; tv[c] = q.t[o]; }
 #pragma unroll
@@ -287,11 +324,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
                 own.x[o] = xv[c] + alpha[c] * pv[c];
                 const float rv = rv0[c] - alpha[c] * tv[c];
                 q.r[o] = rv;
+                zv[c] = id * rv;
                 acc[c] += (double)rv * rv;
-                acc[3 + c] += (double)rv * (id * rv);
+                acc[3 + c] += (double)rv * zv[c];
             }
+            if (q.dest[i]) mg_push_z(q, i, make_float4(zv[0], zv[1], zv[2], 0.0f));
         }
-        alive = mg_allreduce6(grid, q, acc, smem, 0, ++epoch, tot) && alive;
+        alive = mg_allreduce6(q, acc, smem, s_last, parity, ++epoch, ++seq, true, alive, tot); parity ^= 1;
         float beta[3] = {0.0f, 0.0f, 0.0f};
         bool upd[3];
         for (int c = 0; c < 3; ++c) {
@@ -305,8 +344,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
             upd[c] = true;
             if (++iters[c] >= q.max_iters) active[c] = false;
         }
-        // phase 3: p = z + beta p on the own rows; halo entries also into the copies of the ranks that read them
-        if (upd[0] || upd[1] || upd[2])
+        // phase 3: p = z + beta p on the own rows and, from the z the owners pushed, on the imported rows
+        if (upd[0] || upd[1] || upd[2]) {
             for (uint32_t i = q.r0 + tid; i < q.r1; i += nth) {
                 float4 pi = own.p[i];
                 const float id = q.inv_diag[i];
@@ -315,16 +354,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
                 if (upd[1]) pi.y = id * r1v + beta[1] * pi.y;
                 if (upd[2]) pi.z = id * r2v + beta[2] * pi.z;
                 own.p[i] = pi;
-                mg_push_p(q, i, pi);
             }
+            for (uint32_t j = tid; j < n_imp; j += nth) {
+                const uint32_t i = q.imp[j];
+                float4 pi = own.p[i];
+                const float4 zi = __ldcg(own.z + i);
+                if (upd[0]) pi.x = zi.x + beta[0] * pi.x;
+                if (upd[1]) pi.y = zi.y + beta[1] * pi.y;
+                if (upd[2]) pi.z = zi.z + beta[2] * pi.z;
+                own.p[i] = pi;
+            }
+        }
         ++loops;
-        alive = mg_barrier(grid, q, ++epoch) && alive;
+        alive = mg_local_sync(q, s_last, ++lseq, alive);
     }
     // x -= mean(x) (:277), then every rank gets the complete solution
     for (int k = 0; k < 6; ++k) acc[k] = 0.0;
     for (uint32_t i = q.r0 + tid; i < q.r1; i += nth)
         for (int c = 0; c < 3; ++c) acc[c] += (double)own.x[(size_t)c * R + i];
-    alive = mg_allreduce6(grid, q, acc, smem, 1, ++epoch, tot) && alive;
+    alive = mg_allreduce6(q, acc, smem, s_last, parity, ++epoch, ++seq, false, alive, tot); parity ^= 1;
     float mean[3];
     for (int c = 0; c < 3; ++c) mean[c] = R ? (float)(tot[c] / (double)R) : 0.0f;
     for (uint32_t i = q.r0 + tid; i < q.r1; i += nth)
@@ -332,7 +380,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
             const float v = own.x[(size_t)c * R + i] - mean[c];
             for (uint32_t k = 0; k < q.nranks; ++k) mg_carve(q.peer[k], R).x[(size_t)c * R + i] = v;
         }
-    alive = mg_barrier(grid, q, ++epoch) && alive;
+    for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+    alive = mg_allreduce6(q, acc, smem, s_last, parity, ++epoch, ++seq, true, alive, tot);   // barrier: all x stored everywhere
     if (tid == 0) {
         for (int c = 0; c < 3; ++c) {
             q.status[c] = iters[c];
@@ -353,6 +402,8 @@ struct MgState {
     DevBuf<double> blockpart;
     DevBuf<uint32_t> status;
     DevBuf<uint8_t> dest;     // halo destination mask of every row
+    DevBuf<uint8_t> imp_mark; // rows of other ranks this rank reads
+    DevBuf<uint32_t> imp, n_imp;
     uint32_t *pinned = nullptr;
 };
 
@@ -385,10 +436,14 @@ int seam_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t nranks, void *handle64)
     B2_TRY(m->blockpart.alloc(4096 * 8));   // every allocation happens here: nothing inside the solve waits for the device
     B2_TRY(m->status.alloc(16));
     B2_TRY(m->dest.alloc(c->R));
+    B2_TRY(m->imp_mark.alloc(c->R));
+    B2_TRY(m->imp.alloc(c->R));
+    B2_TRY(m->n_imp.alloc(1));
     B2_CUDA(cudaHostAlloc((void **)&m->pinned, 16 * sizeof(uint32_t), cudaHostAllocDefault));
     cudaFuncAttributes fa;   // load the kernels now (the first launch of a lazily loaded kernel synchronises the context)
     B2_CUDA(cudaFuncGetAttributes(&fa, (const void *)k_pcg_mg));
     B2_CUDA(cudaFuncGetAttributes(&fa, (const void *)k_pcg_mg_dest));
+    B2_CUDA(cudaFuncGetAttributes(&fa, (const void *)k_pcg_mg_imports));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
     memset(&h, 0, sizeof(h));
@@ -440,9 +495,13 @@ int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info)
     q.R = R; q.r0 = r0; q.r1 = r1; q.rank = m->rank; q.nranks = m->nranks;
     q.csr_ptr = c->csr_ptr.p; q.csr_enc = c->csr_enc.p; q.diag_val = c->seam_dval.p; q.inv_diag = c->seam_diag.p; q.rhs = c->seam_rhs.p;
     q.r = c->seam_r.p; q.t = c->seam_t.p; q.blockpart = m->blockpart.p; q.status = m->status.p; q.dest = m->dest.p;
-    if (r1 > r0) B2_LAUNCH k_pcg_mg_dest<<<(r1 - r0 + 255) / 256, 256, 0, s>>>(R, r0, r1, m->rank, m->nranks, c->csr_ptr.p, c->csr_enc.p, m->dest.p);
+    B2_TRY(m->imp_mark.zero(s));
+    B2_TRY(m->n_imp.zero(s));
+    if (r1 > r0) B2_LAUNCH k_pcg_mg_dest<<<(r1 - r0 + 255) / 256, 256, 0, s>>>(R, r0, r1, m->rank, m->nranks, c->csr_ptr.p, c->csr_enc.p, m->dest.p, m->imp_mark.p);
+    B2_LAUNCH k_pcg_mg_imports<<<(R + 255) / 256, 256, 0, s>>>(R, m->imp_mark.p, m->imp.p, m->n_imp.p);
+    q.imp = m->imp.p; q.n_imp = m->n_imp.p;
     for (int k = 0; k < MG_MAX_RANKS; ++k) q.peer[k] = m->peer[k];
-    q.max_iters = 1000u; q.tol = 0.0001f; q.epoch0 = m->epoch; q.spin_limit = 50ull * 1000 * 1000;
+    q.max_iters = 1000u; q.tol = 0.0001f; q.epoch0 = m->epoch; q.spin_limit = 4ull * 1000 * 1000;   // x (20 ns sleep + a system-scope load): a few seconds
     void *args[] = {&q};
     cudaEvent_t e0, e1;
     B2_CUDA(cudaEventCreate(&e0)); B2_CUDA(cudaEventCreate(&e1));

@@ -270,6 +270,7 @@ template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T __ldcg(const T *p) { return *(const volatile T *)p; }
 static inline uint2 __ldcg(const uint2 *p) { return *p; }
 static inline uint4 __ldcg(const uint4 *p) { return *p; }
+static inline float4 __ldcg(const float4 *p) { return *p; }
 template <typename T> static inline void __stcg(T *p, T v) { *(volatile T *)p = v; }
 static inline void __threadfence() {}
 static inline void __threadfence_system() {}

@@ -16,6 +16,7 @@ namespace b2 {
 namespace {
 inline void st_release_sys(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
 inline uint32_t ld_acquire_sys(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+inline uint32_t ld_acquire_gpu(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 }  // namespace
 }  // namespace b2
 #include "seam_mg_kernels.inc"
@@ -84,6 +85,9 @@ int emul_seam_mg(const float *verts, uint32_t Vn, const uint32_t *faces, uint32_
     std::vector<std::vector<uint32_t> > st(ranks, std::vector<uint32_t>(16, 0u));
     std::vector<PcgMg> q(ranks);
     std::vector<std::vector<uint8_t> > dest(ranks, std::vector<uint8_t>(R, 0xFF));   // 0xFF outside the own rows: never read
+    std::vector<std::vector<uint8_t> > imark(ranks, std::vector<uint8_t>(R, 0));
+    std::vector<std::vector<uint32_t> > imp(ranks, std::vector<uint32_t>(R, 0u));
+    std::vector<uint32_t> nimp(ranks, 0u);
     uint32_t halo_rows = 0;
     for (uint32_t k = 0; k < ranks; ++k) {
         PcgMg &p = q[k];
@@ -95,8 +99,9 @@ int emul_seam_mg(const float *verts, uint32_t Vn, const uint32_t *faces, uint32_
         p.max_iters = 1000u; p.tol = 0.0001f; p.epoch0 = 0xFFFFFFF0u;   // start close to the wrap-around of the epoch counter
         p.spin_limit = 1000000000ull;
         if (p.r1 > p.r0)
-            emul::launch_serial((p.r1 - p.r0 + 255) / 256, 256, [&] { k_pcg_mg_dest(R, p.r0, p.r1, k, ranks, csr_ptr.data(), csr_enc.data(), dest[k].data()); });
-        p.dest = dest[k].data();
+            emul::launch_serial((p.r1 - p.r0 + 255) / 256, 256, [&] { k_pcg_mg_dest(R, p.r0, p.r1, k, ranks, csr_ptr.data(), csr_enc.data(), dest[k].data(), imark[k].data()); });
+        emul::launch_serial((R + 255) / 256, 256, [&] { k_pcg_mg_imports(R, imark[k].data(), imp[k].data(), &nimp[k]); });
+        p.dest = dest[k].data(); p.imp = imp[k].data(); p.n_imp = &nimp[k];
         for (uint32_t i = p.r0; i < p.r1; ++i) halo_rows += dest[k][i] != 0;
     }
     st[0][15] = halo_rows;   // reported through the status words of rank 0

@@ -61,8 +61,8 @@ def emul():
     with open(os.path.join(OUT, "seam_mg_kernels.inc"), "w") as f:
         f.write(_kernel_part("seam_mg.cu", "// ---- host side: peer block management and launch",
                              ("__device__ __forceinline__ void st_release_sys", "__device__ __forceinline__ void mg_block_reduce6"))
-                .replace("    __shared__ double smem[(MG_THREADS / 32) * 6];\n",
-                         "    double *smem = (double *)emul::block_shared(sizeof(double) * (MG_THREADS / 32) * 6);\n"))
+                .replace("    __shared__ double smem[(MG_THREADS / 32) * 6 + 1];\n",
+                         "    double *smem = (double *)emul::block_shared(sizeof(double) * ((MG_THREADS / 32) * 6 + 1));\n"))
     with open(os.path.join(OUT, "patches_kernels.inc"), "w") as f:
         f.write(_kernel_part("patches.cu", "void patches_free(b2tex_ctx"))
     with open(os.path.join(OUT, "localseam_kernels.inc"), "w") as f:
@@ -561,7 +561,7 @@ def test_device_view_selection_generic_paths(emul, orc, case):
 @pytest.mark.parametrize("ranks,grid", [(2, 2), (3, 1)])
 def test_device_multi_gpu_seam_solve(emul, orc, scene_mod, get_scene, ranks, grid):
     """k_pcg_mg on `ranks` emulated devices at once (emul::launch_ranks: one grid.sync scope per device, peer blocks =
-    each other's host buffers): the rows are split across the ranks, the search direction is all-gathered by peer stores,
+    each other's host buffers): the rows are split across the ranks, z = M^-1 r of the halo rows travels by peer stores (the readers update their own copy of p),
     dot products go through per-rank slots summed in rank order, barriers are epoch flags in peer memory (started 16 below
     the 32-bit wrap-around).  Every rank must end with the SAME complete solution, with the single-GPU iteration counts,
     within 1e-4 of the oracle, and no barrier may time out."""

@@ -11,7 +11,9 @@ os.makedirs(out_dir, exist_ok=True)
 lines = [f"# ncu summary {tag} (C3: 1 997 120 faces / 200 views 1080p, 1x B200)", ""]
 
 # ---- launch list: share of the step per kernel (cold-cache, serialised: compare SHARES, not absolutes) ----
-lp = os.path.join(ROOT, "gpurun_out", "launches_bench.csv")
+lp = os.path.join(ROOT, "gpurun_out", f"{tag}_launches_bench.csv")
+if not os.path.exists(lp):
+    lp = os.path.join(ROOT, "gpurun_out", "launches_bench.csv")
 if os.path.exists(lp):
     txt = open(lp, errors="replace").read()
     start = txt.find('"ID"')
@@ -29,14 +31,15 @@ if os.path.exists(lp):
         a[0] += 1
         a[1] += ms
     total = sum(a[1] for a in agg.values())
-    lines += ["## Launch list of `python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline` (2 passes of the hot path)",
+    lines += ["## Launch list of `python bench.py --steps 2 --warmup 1 --no-verify --no-e2e --no-cpu-baseline` (3 passes of the hot path)",
               "", f"total kernel time {total:.1f} ms over {sum(a[0] for a in agg.values())} launches", "",
               "| kernel | launches | total ms | share |", "|---|---:|---:|---:|"]
     for n, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
         lines.append(f"| `{n[:70]}` | {c} | {ms:.3f} | {100 * ms / total:.1f}% |")
     lines.append("")
     import shutil
-    shutil.copy(lp, os.path.join(out_dir, f"{tag}_launches_bench.csv"))
+    if os.path.abspath(lp) != os.path.abspath(os.path.join(out_dir, f"{tag}_launches_bench.csv")):
+        shutil.copy(lp, os.path.join(out_dir, f"{tag}_launches_bench.csv"))
 
 # ---- full captures ----
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -46,8 +49,9 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__grid_size", "launch__block_size", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 traffic = {}
 lines += ["## `ncu --set full --clock-control none` captures (one launch each, `tools/run_pipeline.py C3 1`)", ""]
-for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep"))):
-    k = os.path.basename(rep)[5:-8]
+reps = sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"{tag}_prof_*.ncu-rep"))) or sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep")))
+for rep in reps:
+    k = os.path.basename(rep)[:-8].split("prof_")[1]
     try:
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, timeout=120).stdout
     except Exception as e:
