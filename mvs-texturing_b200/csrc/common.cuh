@@ -203,7 +203,10 @@ struct b2tex_ctx {
     b2::DevBuf<unsigned long long> mrf_energy;   // [max_iterations + 2] fixed-point energies
     b2::DevBuf<unsigned long long> mrf_dbg;      // phase timers of k_forest (diagnostic)
     uint32_t mrf_mask_words = 0;
-    uint32_t mrf_tree_smem = 0;
+    uint32_t mrf_tree_smem = 0, mrf_tree_cap = 0;
+    b2::DevBuf<float> mrf_M;           // [3][nnz] messages child -> parent (k_tree)
+    b2::DevBuf<uint16_t> mrf_J;        // [3][nnz] copy positions (k_tree)
+    b2::DevBuf<uint4> mrf_rec;         // [3 F] 48-byte node records in forest order (k_tree_prep)
     b2::DevBuf<uint4> mrf_adj4;        // compact degree<=3 adjacency
     b2::DevBuf<uint32_t> mrf_queue;    // forest frontier lists + stamps
     uint32_t *mrf_host_flags = nullptr;   // pinned: stop flags the host polls behind the launches it queued

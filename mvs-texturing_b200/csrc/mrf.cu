@@ -8,25 +8,17 @@
 //   * messages are summed in adjacency order in fp32 (no FMA: additions and minima only)
 //   * the energy used for termination is 32.32 fixed point, summed with integer atomics.
 //
-// Execution (one iteration = 4 launches, NO host round trip: the stop rule is evaluated on the device
+// Execution (one iteration = 5 launches, NO host round trip: the stop rule is evaluated on the device
 // and the host only polls a pinned flag a few iterations behind the launches it has queued):
 //   k_forest   persistent cooperative kernel: root selection, `rounds` growth rounds on a frontier,
 //              separated by grid.sync().  Every node that joins records (tree, slot) -- the tree of its
 //              parent and its arrival number in that tree -- and adds its label count to the tree's
 //              totals, so that the kernel can lay the forest out TREE BY TREE (levels ascending inside
 //              a tree) without any sort: one block-aggregated allocation pass + one scatter pass.
-//   k_tree<G>  the trees of an induced forest do not touch each other (every edge that leaves a tree
-//              ends at a node whose label is fixed in this iteration), so the whole min-sum DP of a
-//              tree -- bottom-up messages AND top-down assignment -- runs inside ONE warp on data staged
-//              in shared memory: a CTA claims a chunk of trees, packs as many as fit into its shared
-//              memory pool, every warp stages its trees with 16-byte asynchronous copies (cp.async, one commit
-//              group per tree, so the copies of the next tree overlap the DP of the current one),
-//              builds per-node label bitmasks in shared memory (O(1) merge-join of the sorted label
-//              lists by popcount), sweeps the levels up and down with __syncwarp() between levels, and
-//              writes the new labels.  The messages H never exist in global memory: DRAM traffic per
-//              forest node is 6 B per label (cost + view, read once) + ~60 B of node metadata, against
-//              the 14 B per label of a sweep through global memory.  Trees that do not fit
-//              (or contain a node of degree > 3) take the same recursion through global memory.
+//   k_tree_prep + k_tree<G>  the trees of an induced forest do not touch each other (every edge that leaves a tree
+//              ends at a node whose label is fixed in this iteration), so the whole min-sum DP of a tree -- bottom-up
+//              messages AND top-down assignment -- runs inside ONE warp, streamed through L2 without staging and
+//              without block- or grid-wide barriers (see the comment above k_tree_prep).
 //   k_energy   fixed-point energy -> efix[t] on the device
 //   k_stop     StopWhenReturnsDiminish (view_selection.cpp:84) on the device; once it fires, the
 //              launches the host has already queued return immediately
@@ -66,6 +58,7 @@ __device__ __forceinline__ bool root_cand(uint32_t v, uint32_t seed_t, uint32_t 
     return mix32(prio(v, seed_t) ^ 0x68E31DA4u) % rdiv == 0;
 }
 
+struct NodeRec;
 struct Mrf {
     uint32_t F, nb, ne;          // nodes, owned node range
     const uint32_t *adj_ptr, *adj_idx;
@@ -89,6 +82,11 @@ struct Mrf {
     uint32_t K, mask_words;
     uint32_t part_size, rounds, rdiv, seed, iter;
     uint32_t tree_smem;          // dynamic shared memory of k_tree (bytes)
+    NodeRec *rec;                // per forest node, in `order` layout (k_tree_prep)
+    float *M;                    // [3][mstride] messages child -> parent, per adjacency slot, at the parent's row positions
+    uint16_t *J;                 // [3][mstride] position of that label in the child's list if the child should copy it, else 0xFFFF
+    size_t mstride;
+    uint32_t tree_cap;           // longest label list the shared-memory scratch of k_tree holds
 };
 // control block layout (uint32 words)
 constexpr int CTL_QN = 0;                        // [MAX_LEVELS+1] frontier sizes per round
@@ -135,6 +133,16 @@ __device__ __forceinline__ uint32_t nb_at(const Mrf &m, const Nb &n, uint32_t i)
     return m.adj_idx[n.base + i];
 }
 
+// longest label list of the owned faces
+__global__ void __launch_bounds__(256) k_max_labels(const uint64_t *__restrict__ ptr, uint32_t nb, uint32_t ne, uint32_t *out)
+{
+    uint32_t mx = 0;
+    for (uint32_t v = nb + blockIdx.x * blockDim.x + threadIdx.x; v < ne; v += gridDim.x * blockDim.x)
+        mx = max(mx, (uint32_t)(ptr[v + 1] - ptr[v]));
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
+}
+
 __global__ void __launch_bounds__(256) k_build_adj4(uint32_t F, const uint32_t *__restrict__ adj_ptr,
                                                     const uint32_t *__restrict__ adj_idx, uint4 *adj4)
 {
@@ -151,34 +159,11 @@ __global__ void __launch_bounds__(256) k_build_adj4(uint32_t F, const uint32_t *
 }
 
 // ---- shared-memory / async-copy primitives (the host emulation replaces this block) ----
-// 16-byte asynchronous global -> shared copies (LDGSTS, L2 only: every row is read exactly once), grouped per tree.
-// (A first version staged every row with one cp.async.bulk -- the TMA engine: ~90 descriptor-less bulk copies of
-// ~200 bytes per tree ran at about one copy per 260 cycles per SM and made the kernel 10x slower than these.)
-__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem) : "memory");
-}
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
-}
-__device__ __forceinline__ long long sm_clock() { return clock64(); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// wait until at most `pending` of this thread's committed groups are still in flight
-__device__ __forceinline__ void cp_async_wait_pending(uint32_t pending)
-{
-    switch (pending) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-    }
 }
 // ---- end of primitives ----
 
@@ -494,64 +479,83 @@ __global__ void __launch_bounds__(FOREST_THREADS, 1) k_forest(Mrf m, int build_t
     stamp(5);   // scatter (thread 0's share)
 }
 
-// ---- min-sum DP of whole trees in shared memory ------------------------------------------------------------------
+// ---- min-sum DP of whole trees: one warp per tree, streamed through L2 ------------------------------------------------
+// The trees of an induced forest do not touch each other (every edge that leaves a tree ends at a node whose label is
+// fixed in this iteration), so a tree is solved by ONE warp from its leaves to its root and back, without any block- or
+// grid-wide barrier; 48 resident warps per SM hide the latency of each other's loads.  Nothing of a tree is staged:
+//   k_tree_prep  one thread per forest node writes a 48-byte record in forest order: row extents, the role of each of the
+//                three neighbours (child / parent / fixed label / none) and where the node's message to its parent goes.
+//                This takes the three-deep chain of dependent loads (order -> adjacency -> labels / positions -> parent's
+//                adjacency) out of the serial path of the DP.
+//   k_tree<G>    bottom-up, level by level, G lanes per node (32 / G nodes of one level at a time): h(l) = cost(l) + the
+//                terms of the neighbours in adjacency order -- a child contributes its Potts message
+//                min(h_c(l), hmin_c + 1), which the CHILD wrote into the message row of that adjacency slot at the
+//                parent's row position (M[slot][ptr[parent] + k], one float per label of the parent), so the parent reads
+//                it with the same coalesced index as its own costs -- then min / arg-min by two warp reductions.  The
+//                node's own h row lives in a small shared-memory scratch only until its message is formed (binary search
+//                of every label of the parent in the node's sorted label list).  Next to every message entry the child
+//                leaves the position of that label in its own list if choosing it is optimal given the parent
+//                (J[slot][...], 0xFFFF = "take the arg-min"), so the top-down pass is one thread per node: two loads.
+// DRAM traffic per forest node: 6 B per label (cost + view, read once) + 6 B per label of its parent written (message +
+// position; the read-back hits L2) + ~100 B of record, against the 14 B per label of a sweep through global memory
+// tables.  Trees with a node of degree > 3 or a label list longer than the scratch take the same recursion
+// through the global tables H / hminp1 / amin (tree_solve_global).
 constexpr int TREE_THREADS = 512;
 constexpr int TREE_WARPS = TREE_THREADS / 32;
-constexpr int TREE_CHUNK = 32;       // trees claimed per global atomic (<= 8 staged per warp: cp_async_wait_pending)
 constexpr uint32_t NBR_SKIP = 0u, NBR_CHILD = 1u << 30, NBR_FIXED = 2u << 30, NBR_PARENT = 3u << 30;
 constexpr uint32_t NBR_KIND = 3u << 30, NBR_ARG = ~NBR_KIND;
 
-// upper bound of the shared memory one tree needs (cost / view rows are padded to the 16-byte granules of the async
-// copies: <= 6 extra floats and <= 14 extra u16 per node; index rows have one entry per label of the PARENT:
-// `msum` = sum over the non-root nodes of the parent's label count, accumulated by k_forest)
-__host__ __device__ __forceinline__ uint32_t tree_hcap(uint32_t cnt, uint32_t nnz) { return (nnz + 6u * cnt + 3u) & ~3u; }
-__host__ __device__ __forceinline__ uint32_t tree_vcap(uint32_t cnt, uint32_t nnz) { return (nnz + 14u * cnt + 7u) & ~7u; }
-__host__ __device__ __forceinline__ uint32_t tree_mcap(uint32_t msum) { return (msum + 7u) & ~7u; }   // keeps the view rows behind it 16-byte aligned
-constexpr uint32_t TREE_NODE_BYTES = 56u;   // per-node tables below
-__host__ __device__ __forceinline__ uint64_t tree_bytes(uint32_t cnt, uint32_t hcap, uint32_t vcap, uint32_t mcap)
-{
-    return 4ull * hcap + 2ull * vcap + 2ull * mcap + (uint64_t)cnt * TREE_NODE_BYTES;
-}
-
-struct TreeStatic {
-    uint32_t t_cnt[TREE_CHUNK], t_nnz[TREE_CHUNK], t_start[TREE_CHUNK], t_msum[TREE_CHUNK];
-    uint32_t t_node0[TREE_CHUNK], t_h0[TREE_CHUNK], t_v0[TREE_CHUNK], t_m0[TREE_CHUNK], t_slow[TREE_CHUNK];
-    uint32_t chunk_first, sb_n, sb_nodes, sb_hcap, sb_vcap, sb_mcap;
-    long long c_prep, c_up, c_down;   // diagnostic cycle counters (thread 0)
-    uint16_t lstart[MAX_LEVELS + 2];   // first slot of every level in lnode (sub-batch wide level buckets)
-    uint16_t lfill[MAX_LEVELS + 2];
+struct __align__(16) NodeRec {
+    uint32_t v;          // node
+    uint32_t n_lev;      // label count | level << 16
+    uint64_t p0;         // first entry of the node's cost / view rows
+    uint32_t nbr[3];     // per adjacency slot: kind | argument (FIXED: the label, PARENT: the parent node)
+    uint32_t pslot_pn;   // adjacency slot of this node at its parent | label count of the parent << 16
+    uint64_t pp0;        // first entry of the parent's rows
+    uint32_t amin;       // written bottom-up: position of the node's best label given its subtree
+    uint32_t pad;
 };
+static_assert(sizeof(NodeRec) == 48, "NodeRec layout");
 
-// pointers into the dynamic shared memory of one sub-batch
-struct TreePool {
-    float *H;          // [hcap]  cost rows, turned into the min-sum tables in place
-    uint16_t *V;       // [vcap]  view rows
-    uint16_t *J;       // [mcap]  per non-root node: position of every label of the PARENT in the node's own row, 0xFFFF = absent
-    uint32_t *gid, *hoff, *voff, *moff, *nbr, *am, *plo, *phi;   // plo / phi: first entry of the node's rows in the global arrays
-    float *hm;
-    uint16_t *nlab, *lev, *np;
-    uint16_t *lnode;   // the nodes of the sub-batch bucketed by level
-};
-__device__ __forceinline__ TreePool carve_pool(unsigned char *base, uint32_t nodes, uint32_t hcap, uint32_t vcap, uint32_t mcap)
+__global__ void __launch_bounds__(256) k_tree_prep(Mrf m)
 {
-    TreePool p;
-    p.H = reinterpret_cast<float *>(base); base += (size_t)hcap * 4;
-    p.V = reinterpret_cast<uint16_t *>(base); base += (size_t)vcap * 2;
-    p.J = reinterpret_cast<uint16_t *>(base); base += (size_t)mcap * 2;
-    p.gid = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
-    p.hoff = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
-    p.voff = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
-    p.moff = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
-    p.nbr = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 12;
-    p.am = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
-    p.plo = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
-    p.phi = reinterpret_cast<uint32_t *>(base); base += (size_t)nodes * 4;
-    p.hm = reinterpret_cast<float *>(base); base += (size_t)nodes * 4;
-    p.nlab = reinterpret_cast<uint16_t *>(base); base += (size_t)nodes * 2;
-    p.lev = reinterpret_cast<uint16_t *>(base); base += (size_t)nodes * 2;
-    p.np = reinterpret_cast<uint16_t *>(base); base += (size_t)nodes * 2;
-    p.lnode = reinterpret_cast<uint16_t *>(base);
-    return p;
+    if (__ldcg(m.state + ST_STOP)) return;
+    const uint32_t total = __ldcg(m.ctl + CTL_CURSOR);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint32_t v = m.order[i];
+    const uint64_t p0 = m.ptr[v];
+    const uint32_t n = (uint32_t)(m.ptr[v + 1] - p0);
+    const uint4 a4 = __ldg(m.adj4 + v);
+    NodeRec r;
+    r.v = v; r.n_lev = n | ((uint32_t)m.olev[i] << 16); r.p0 = p0;
+    r.nbr[0] = r.nbr[1] = r.nbr[2] = NBR_SKIP;
+    r.pslot_pn = 0; r.pp0 = 0; r.amin = 0; r.pad = 0;
+    if (n > m.tree_cap) atomicOr(&m.ttab[m.tjoin[v].x].x, 0x80000000u);   // longer than the scratch: through global memory
+    if (a4.w <= 3) {
+        // all six neighbour loads first (independent), classification afterwards
+        uint32_t xl[3] = {0u, 0u, 0u}, pl[3] = {NO_NODE, NO_NODE, NO_NODE}, wn[3] = {a4.x, a4.y, a4.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if ((uint32_t)a < a4.w && wn[a] != NO_NODE) { xl[a] = m.labels[wn[a]]; pl[a] = m.pos[wn[a]]; }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (xl[a] == 0u) continue;   // unseen faces carry no edges (view_selection.cpp:30,35)
+            if (pl[a] == NO_NODE) { r.nbr[a] = NBR_FIXED | xl[a]; continue; }
+            if (pl[a] > i) { r.nbr[a] = NBR_CHILD; continue; }   // a forest neighbour is in the same tree: deeper = child
+            const uint32_t w = wn[a];
+            const uint4 b4 = __ldg(m.adj4 + w);
+            const uint64_t q0 = m.ptr[w];
+            const uint32_t pn = (uint32_t)(m.ptr[w + 1] - q0);
+            const uint32_t ps = b4.x == v ? 0u : (b4.y == v ? 1u : 2u);
+            r.nbr[a] = NBR_PARENT | w;
+            r.pslot_pn = ps | (pn << 16);
+            r.pp0 = q0;
+        }
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(m.rec + i);
+    const uint4 *src = reinterpret_cast<const uint4 *>(&r);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
 }
 
 // first index of the run of equal levels that ends at `end` (exclusive), searched inside [a, end)
@@ -583,253 +587,6 @@ __device__ __forceinline__ uint32_t level_run_end(LevPtr lev, uint32_t s, uint32
         if (run < 32u) break;
     }
     return e;
-}
-
-// Staging, phase 1 -- one THREAD per node of the sub-batch: everything that needs global memory round trips (node id ->
-// row extents, adjacency -> labels and forest positions of the three neighbours), all nodes at once.
-__device__ void batch_load_nodes(const Mrf &m, const TreePool &p, const TreeStatic &ts, uint32_t done, uint32_t sb_n, uint32_t N)
-{
-    for (uint32_t li = threadIdx.x; li < N; li += TREE_THREADS) {
-        uint32_t t = done;
-        for (uint32_t i = done; i < done + sb_n; ++i)   // node0 ascends over the staged trees of the sub-batch
-            if (!ts.t_slow[i] && ts.t_node0[i] <= li) t = i;
-        const uint32_t node0 = ts.t_node0[t], start = ts.t_start[t], i = li - node0;
-        const uint32_t v = m.order[start + i];
-        const uint32_t lv = m.olev[start + i];
-        const uint64_t p0 = m.ptr[v];
-        const uint32_t n = (uint32_t)(m.ptr[v + 1] - p0);
-        const uint4 a4 = __ldg(m.adj4 + v);
-        // all six neighbour loads first (independent), classification afterwards
-        uint32_t xl[3] = {0u, 0u, 0u}, pl[3] = {NO_NODE, NO_NODE, NO_NODE};
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const uint32_t w = a == 0 ? a4.x : (a == 1 ? a4.y : a4.z);
-            if ((uint32_t)a < a4.w && w != NO_NODE) { xl[a] = m.labels[w]; pl[a] = m.pos[w]; }
-        }
-        p.gid[li] = v;
-        p.nlab[li] = (uint16_t)n;
-        p.lev[li] = (uint16_t)lv;
-        p.plo[li] = (uint32_t)p0;
-        p.phi[li] = (uint32_t)(p0 >> 32);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            uint32_t enc = NBR_SKIP;
-            if (xl[a] != 0u) {   // unseen faces carry no edges (view_selection.cpp:30,35)
-                if (pl[a] != NO_NODE) {   // a forest neighbour is in the same tree: deeper = child
-                    const uint32_t lj = pl[a] - start;
-                    enc = (lj > i ? NBR_CHILD : NBR_PARENT) | (node0 + lj);
-                } else enc = NBR_FIXED | xl[a];
-            }
-            p.nbr[3 * li + a] = enc;
-        }
-    }
-}
-
-// Staging, phase 2 -- one WARP per tree, shared memory only: row offsets by prefix sums, asynchronous 16-byte copies of the
-// cost and view rows (from the aligned-down start of every row), offsets of the index rows
-__device__ void tree_layout(const Mrf &m, const TreePool &p, uint32_t cnt, uint32_t node0, uint32_t h0, uint32_t v0, uint32_t m0,
-                            uint32_t lane)
-{
-    uint32_t hcarry = h0, vcarry = v0, mcarry = m0;
-    const uint32_t half = lane >> 4, sl = lane & 15u;   // two rows per step, 16 lanes (= 16 chunks of 16 bytes) each
-    for (uint32_t c = 0; c < cnt; c += 32) {
-        const uint32_t i = c + lane, li = node0 + i;
-        const bool valid = i < cnt;
-        uint32_t n = 0, hsz = 0, vsz = 0, npar = 0;
-        uint64_t p0 = 0;
-        if (valid) {
-            n = p.nlab[li];
-            p0 = ((uint64_t)p.phi[li] << 32) | p.plo[li];
-            hsz = ((uint32_t)(p0 & 3u) + n + 3u) & ~3u;
-            vsz = ((uint32_t)(p0 & 7u) + n + 7u) & ~7u;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const uint32_t en = p.nbr[3 * li + a];
-                if ((en & NBR_KIND) == NBR_PARENT) npar = p.nlab[en & NBR_ARG];
-            }
-        }
-        uint32_t hi = hsz, vi = vsz, mi = npar;
-        for (int s = 1; s < 32; s <<= 1) {
-            const uint32_t oh = __shfl_up_sync(0xffffffffu, hi, s), ov = __shfl_up_sync(0xffffffffu, vi, s),
-                           om = __shfl_up_sync(0xffffffffu, mi, s);
-            if ((int)lane >= s) { hi += oh; vi += ov; mi += om; }
-        }
-        const uint32_t ho = hcarry + hi - hsz, vo = vcarry + vi - vsz;
-        if (valid) {
-            p.hoff[li] = ho + (uint32_t)(p0 & 3u);
-            p.voff[li] = vo + (uint32_t)(p0 & 7u);
-            p.moff[li] = mcarry + mi - npar;
-            p.np[li] = (uint16_t)npar;
-        }
-        hcarry += __shfl_sync(0xffffffffu, hi, 31);
-        vcarry += __shfl_sync(0xffffffffu, vi, 31);
-        mcarry += __shfl_sync(0xffffffffu, mi, 31);
-        const uint32_t rows = min(32u, cnt - c);
-        const unsigned long long src_c = (unsigned long long)(m.cost + (p0 & ~(uint64_t)3));
-        const unsigned long long src_v = (unsigned long long)(m.view + (p0 & ~(uint64_t)7));
-        for (uint32_t j = 0; j < rows; j += 2) {
-            const uint32_t jj = min(j + half, 31u);
-            const unsigned long long sc = __shfl_sync(0xffffffffu, src_c, jj), sv = __shfl_sync(0xffffffffu, src_v, jj);
-            const uint32_t rho = __shfl_sync(0xffffffffu, ho, jj), rvo = __shfl_sync(0xffffffffu, vo, jj);
-            const uint32_t hch = __shfl_sync(0xffffffffu, hsz, jj) >> 2, vch = __shfl_sync(0xffffffffu, vsz, jj) >> 3;
-            if (j + half < rows) {
-                for (uint32_t q = sl; q < hch; q += 16) cp_async16(p.H + rho + 4u * q, (const float *)sc + 4u * q);
-                for (uint32_t q = sl; q < vch; q += 16) cp_async16(p.V + rvo + 8u * q, (const uint16_t *)sv + 8u * q);
-            }
-        }
-    }
-    cp_async_commit();
-}
-
-// The DP of ALL staged trees of a sub-batch at once, by the whole CTA: the trees are independent, so one level of all of
-// them is one parallel step (a single tree has only ~3 nodes per level).  Nodes are bucketed by level across the
-// sub-batch.  Bottom-up, a node gets G lanes: h(l) = cost(l) + the terms of its neighbours in adjacency order -- a child c
-// contributes the Potts message min(h_c(l), hmin_c + 1), found through the child's index row J_c (where each label of
-// THIS node sits in the child's row; built once per sub-batch by merging the two sorted label lists, so the inner loop
-// has no search), a fixed neighbour 0 or 1 -- then min / arg-min by shuffles.  Top-down one thread per node.
-template <int G>
-__device__ void batch_solve(const Mrf &m, const TreePool &p, TreeStatic &ts, uint32_t N)
-{
-    constexpr uint32_t NG = TREE_THREADS / G;   // nodes in flight per step
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, glane = tid & (G - 1), group = tid / G;
-    const uint32_t nlev = m.rounds + 1u;
-    const bool prof = m.dbg != nullptr && tid == 0;
-    long long tc = prof ? sm_clock() : 0;
-    // ---- level histogram (two 16-bit counters per word) ----
-    for (uint32_t i = tid; i <= nlev; i += TREE_THREADS) ts.lfill[i] = 0;
-    __syncthreads();
-    for (uint32_t li = tid; li < N; li += TREE_THREADS) {
-        const uint32_t l = p.lev[li];
-        atomicAdd(reinterpret_cast<uint32_t *>(ts.lfill) + (l >> 1), (l & 1u) ? 0x10000u : 1u);
-    }
-    // ---- index rows: merge of the parent's and the node's sorted label lists (one thread per non-root node) ----
-    for (uint32_t li = tid; li < N; li += TREE_THREADS) {
-        const uint32_t npar = p.np[li];
-        if (!npar) continue;
-        uint32_t par = 0;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const uint32_t en = p.nbr[3 * li + a];
-            if ((en & NBR_KIND) == NBR_PARENT) par = en & NBR_ARG;
-        }
-        const uint16_t *pv = p.V + p.voff[par], *cv = p.V + p.voff[li];
-        uint16_t *J = p.J + p.moff[li];
-        const uint32_t n = p.nlab[li];
-        uint32_t j = 0;
-        for (uint32_t k = 0; k < npar; ++k) {
-            const uint32_t want = pv[k];
-            while (j < n && cv[j] < want) ++j;
-            J[k] = (j < n && cv[j] == want) ? (uint16_t)j : (uint16_t)0xFFFFu;
-        }
-    }
-    __syncthreads();
-    if (tid < 32) {   // exclusive scan of the level counts -> lstart
-        uint32_t carry = 0;
-        for (uint32_t base = 0; base <= nlev; base += 32) {
-            const uint32_t i = base + lane;
-            const uint32_t c = i <= nlev ? ts.lfill[i] : 0u;
-            uint32_t incl = c;
-            for (int sft = 1; sft < 32; sft <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, sft);
-                if ((int)lane >= sft) incl += o;
-            }
-            if (i <= nlev) ts.lstart[i] = (uint16_t)(carry + incl - c);
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) ts.lstart[nlev + 1] = (uint16_t)carry;
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i <= nlev; i += TREE_THREADS) ts.lfill[i] = ts.lstart[i];
-    __syncthreads();
-    for (uint32_t li = tid; li < N; li += TREE_THREADS) {
-        const uint32_t l = p.lev[li];
-        const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(ts.lfill) + (l >> 1), (l & 1u) ? 0x10000u : 1u);
-        p.lnode[(l & 1u) ? (old >> 16) : (old & 0xFFFFu)] = (uint16_t)li;
-    }
-    __syncthreads();
-    if (prof) { const long long t = sm_clock(); ts.c_prep += t - tc; tc = t; }
-    // ---- bottom-up: deepest level first ----
-    for (uint32_t L = nlev; L-- > 0;) {
-        const uint32_t s = ts.lstart[L], e = ts.lstart[L + 1];
-        if (s == e) continue;
-        for (uint32_t base = s; base < e; base += NG) {
-            const uint32_t idx = base + group;
-            const bool act = idx < e;
-            float bh = INFINITY;
-            uint32_t bk = 0xFFFFFFFFu, li = 0, n = 0;
-            float *Hv = p.H;
-            if (act) {
-                li = p.lnode[idx];
-                n = p.nlab[li];
-                Hv = p.H + p.hoff[li];
-                const uint16_t *viewv = p.V + p.voff[li];
-                const uint32_t e0 = p.nbr[3 * li], e1 = p.nbr[3 * li + 1], e2 = p.nbr[3 * li + 2];
-                // per neighbour slot: a child (its index row, table and hmin + 1), a fixed label (0 = none: labels start
-                // at 1), or nothing
-                const bool c0 = (e0 & NBR_KIND) == NBR_CHILD, c1 = (e1 & NBR_KIND) == NBR_CHILD, c2 = (e2 & NBR_KIND) == NBR_CHILD;
-                const uint32_t a0 = e0 & NBR_ARG, a1 = e1 & NBR_ARG, a2 = e2 & NBR_ARG;
-                const uint16_t *j0 = c0 ? p.J + p.moff[a0] : nullptr, *j1 = c1 ? p.J + p.moff[a1] : nullptr,
-                               *j2 = c2 ? p.J + p.moff[a2] : nullptr;
-                const float *h0 = c0 ? p.H + p.hoff[a0] : nullptr, *h1 = c1 ? p.H + p.hoff[a1] : nullptr,
-                            *h2 = c2 ? p.H + p.hoff[a2] : nullptr;
-                const float g0 = c0 ? p.hm[a0] : 0.0f, g1 = c1 ? p.hm[a1] : 0.0f, g2 = c2 ? p.hm[a2] : 0.0f;
-                const uint32_t x0 = (e0 & NBR_KIND) == NBR_FIXED ? a0 : 0u;
-                const uint32_t x1 = (e1 & NBR_KIND) == NBR_FIXED ? a1 : 0u;
-                const uint32_t x2 = (e2 & NBR_KIND) == NBR_FIXED ? a2 : 0u;
-#pragma unroll 2
-                for (uint32_t k = glane; k < n; k += G) {
-                    const uint32_t lab = (uint32_t)viewv[k] + 1u;
-                    float h = Hv[k];
-                    if (c0) { float msg = g0; const uint32_t j = j0[k]; if (j != 0xFFFFu) { const float hw = h0[j]; if (hw < msg) msg = hw; } h = h + msg; }
-                    else if (x0) h = h + (lab != x0 ? 1.0f : 0.0f);
-                    if (c1) { float msg = g1; const uint32_t j = j1[k]; if (j != 0xFFFFu) { const float hw = h1[j]; if (hw < msg) msg = hw; } h = h + msg; }
-                    else if (x1) h = h + (lab != x1 ? 1.0f : 0.0f);
-                    if (c2) { float msg = g2; const uint32_t j = j2[k]; if (j != 0xFFFFu) { const float hw = h2[j]; if (hw < msg) msg = hw; } h = h + msg; }
-                    else if (x2) h = h + (lab != x2 ? 1.0f : 0.0f);
-                    Hv[k] = h;
-                    if (h < bh) { bh = h; bk = k; }
-                }
-            }
-            {   // min / arg-min over the G lanes of the node by two integer warp reductions: every h is >= 0 (costs in [0, 1],
-                // messages sums of such), so the unsigned order of the bit patterns is the float order; ties -> smallest index
-                const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(uint32_t)(G - 1)));
-                const uint32_t hb = __float_as_uint(bh);
-                const uint32_t hmin = __reduce_min_sync(gmask, hb);
-                bk = __reduce_min_sync(gmask, hb == hmin ? bk : 0xFFFFFFFFu);
-                bh = __uint_as_float(hmin);
-            }
-            if (act && glane == 0) { p.hm[li] = bh + 1.0f; p.am[li] = bk; }
-        }
-        __syncthreads();
-    }
-    if (prof) { const long long t = sm_clock(); ts.c_up += t - tc; tc = t; }
-    // ---- top-down: shallowest level first, one thread per node; am becomes the position of the chosen label ----
-    for (uint32_t L = 0; L < nlev; ++L) {
-        const uint32_t s = ts.lstart[L], e = ts.lstart[L + 1];
-        if (s == e) continue;
-        for (uint32_t idx = s + tid; idx < e; idx += TREE_THREADS) {
-            const uint32_t li = p.lnode[idx];
-            uint32_t bk = p.am[li];
-            if (p.np[li]) {
-                uint32_t par = 0;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const uint32_t en = p.nbr[3 * li + a];
-                    if ((en & NBR_KIND) == NBR_PARENT) par = en & NBR_ARG;
-                }
-                const uint32_t j = p.J[p.moff[li] + p.am[par]];   // the parent's label in this node's row
-                if (j != 0xFFFFu && p.H[p.hoff[li] + j] <= p.hm[li]) bk = j;
-            }
-            p.am[li] = bk;
-        }
-        __syncthreads();
-    }
-    if (prof) { const long long t = sm_clock(); ts.c_down += t - tc; tc = t; }
-    for (uint32_t li = tid; li < N; li += TREE_THREADS) {
-        const uint32_t v = p.gid[li], bk = p.am[li];
-        m.labels[v] = (uint32_t)p.V[p.voff[li] + bk] + 1u;
-        m.lidx[v] = bk;
-    }
 }
 
 // the same recursion through global memory: any degree, any size (one node at a time, 32 lanes over its labels)
@@ -900,85 +657,184 @@ __device__ void tree_solve_global(const Mrf &m, uint32_t start, uint32_t cnt, ui
     }
 }
 
-template <int G>
-__global__ void __launch_bounds__(TREE_THREADS) k_tree(Mrf m)
+
+// scratch of one lane group of k_tree: h row [cap] f32 | label list [cap] u16 (only used without bitmasks) |
+// label bitmask [mw] u32 | prefix popcounts [mw] u16 (padded to 4 bytes)
+__host__ __device__ __forceinline__ uint32_t tree_group_bytes(uint32_t cap, uint32_t mw) { return cap * 6u + mw * 4u + ((mw * 2u + 3u) & ~3u); }
+
+template <int G, int MINB>
+__global__ void __launch_bounds__(TREE_THREADS, MINB) k_tree(Mrf m)
 {
     if (__ldcg(m.state + ST_STOP)) return;
     extern __shared__ __align__(16) unsigned char tree_dyn[];
-    __shared__ TreeStatic ts;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    constexpr uint32_t NPW = 32 / G;   // nodes of one level a warp works on at a time
+    constexpr int PRE = 4;             // labels of the parent a lane holds in registers ahead of the message loop
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, glane = lane & (G - 1), sub = lane / G;
+    const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(uint32_t)(G - 1)));
+    const uint32_t cap = m.tree_cap, mw = m.mask_words;
+    // scratch of this lane group: the node's h row; its label set as a bitmask with prefix popcounts (position of a label in
+    // the sorted list in O(1)); without bitmasks (more than 2047 views) the sorted list itself, searched by bisection
+    unsigned char *scr = tree_dyn + ((size_t)warp * NPW + sub) * tree_group_bytes(cap, mw);
+    float *Hs = reinterpret_cast<float *>(scr);
+    uint16_t *Vs = reinterpret_cast<uint16_t *>(Hs + cap);
+    uint32_t *Ms = reinterpret_cast<uint32_t *>(Vs + cap);
+    uint16_t *Ps = reinterpret_cast<uint16_t *>(Ms + mw);
     const uint32_t nroots = m.ctl[CTL_NROOTS];
-    // diagnostic (B2TEX_FOREST_TIMING): cycles thread 0 of every CTA spends per phase, summed over CTAs and launches
-    const bool prof = m.dbg != nullptr && threadIdx.x == 0;
-    long long tc = prof ? sm_clock() : 0, c_claim = 0, c_stage = 0, c_solve = 0;
-    unsigned long long n_sb = 0, max_nodes = 0;
-    auto lap = [&](long long &acc) { if (prof) { const long long t = sm_clock(); acc += t - tc; tc = t; } };
-    if (threadIdx.x == 0) { ts.c_prep = 0; ts.c_up = 0; ts.c_down = 0; }
+    const size_t ms = m.mstride;
     for (;;) {
-        if (threadIdx.x == 0) ts.chunk_first = atomicAdd(&m.ctl[CTL_CLAIM], (uint32_t)TREE_CHUNK);
-        __syncthreads();
-        const uint32_t first = ts.chunk_first;
-        if (first >= nroots) break;
-        const uint32_t nchunk = min((uint32_t)TREE_CHUNK, nroots - first);
-        if (threadIdx.x < nchunk) {
-            const uint4 t = m.ttab[first + threadIdx.x];
-            ts.t_cnt[threadIdx.x] = t.x; ts.t_nnz[threadIdx.x] = t.y; ts.t_start[threadIdx.x] = t.z; ts.t_msum[threadIdx.x] = t.w;
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&m.ctl[CTL_CLAIM], 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= nroots) break;
+        const uint4 te = __ldcg(m.ttab + t);
+        const uint32_t cnt = te.x & 0x7FFFFFFFu, start = te.z;
+        if (te.x >> 31) {   // a node of degree > 3 or a label list longer than the scratch
+            if (lane == 0) atomicAdd(m.state + ST_SLOW, 1u);
+            tree_solve_global(m, start, cnt, lane);
+            continue;
         }
-        __syncthreads();
-        for (uint32_t done = 0; done < nchunk;) {
-            if (threadIdx.x == 0) {   // pack the next trees of the chunk into the pool, in order
-                uint32_t n = 0, nodes = 0, hcap = 0, vcap = 0, mcap = 0, slow = 0;
-                while (done + n < nchunk) {
-                    const uint32_t i = done + n, cnt = ts.t_cnt[i] & 0x7FFFFFFFu, nnz = ts.t_nnz[i];
-                    const uint32_t hc = tree_hcap(cnt, nnz), vc = tree_vcap(cnt, nnz), mc = tree_mcap(ts.t_msum[i]);
-                    if ((ts.t_cnt[i] >> 31) || tree_bytes(cnt, hc, vc, mc) > m.tree_smem || cnt > 16384u) {   // through global memory
-                        ts.t_slow[i] = 1u; ts.t_node0[i] = 0; ts.t_h0[i] = 0; ts.t_v0[i] = 0; ts.t_m0[i] = 0;
-                        ++n; ++slow;
-                        continue;
-                    }
-                    if (tree_bytes(nodes + cnt, hcap + hc, vcap + vc, mcap + mc) > m.tree_smem) break;
-                    ts.t_slow[i] = 0u; ts.t_node0[i] = nodes; ts.t_h0[i] = hcap; ts.t_v0[i] = vcap; ts.t_m0[i] = mcap;
-                    nodes += cnt; hcap += hc; vcap += vc; mcap += mc;
-                    ++n;
+        NodeRec *rec = m.rec + start;
+        // ---- bottom-up: the node array is sorted by level, so walking it from its end visits the deepest level first.
+        // ---- A step takes the next (up to) NPW nodes of ONE level; the records of the step after it are already on
+        // ---- their way (the node array is walked in order, only the cut at a level boundary is data dependent).
+        auto load_rec = [&](uint32_t hi, uint4 &r0, uint4 &r1, uint4 &r2) {   // node hi - sub, if there is one
+            r0 = make_uint4(0u, 0xFFFF0000u, 0u, 0u); r1 = make_uint4(0u, 0u, 0u, 0u); r2 = r1;   // level 0xFFFF: never active
+            if (hi != NO_NODE && hi >= sub) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(rec + (hi - sub));
+                r0 = __ldcg(rp); r1 = __ldcg(rp + 1); r2 = __ldcg(rp + 2);
+            }
+        };
+        uint32_t hi = cnt - 1u;   // cnt >= 1: a tree has a root
+        uint4 n0, n1, n2;
+        load_rec(hi, n0, n1, n2);
+        while (hi != NO_NODE) {
+            const uint4 r0 = n0, r1 = n1, r2 = n2;
+            const uint32_t i = hi - sub;   // meaningful where act
+            const uint32_t lev_top = __shfl_sync(0xffffffffu, r0.y >> 16, 0);
+            const bool act = hi >= sub && (r0.y >> 16) == lev_top;
+            const uint32_t nact = (uint32_t)__popc(__ballot_sync(0xffffffffu, act && glane == 0));   // levels are contiguous
+            hi = hi >= nact ? hi - nact : NO_NODE;
+            load_rec(hi, n0, n1, n2);   // prefetch: consumed in the next step
+            const uint32_t n = act ? (r0.y & 0xFFFFu) : 0u;
+            const uint64_t p0 = ((uint64_t)r0.w << 32) | r0.z;
+            const uint32_t e0 = r1.x, e1 = r1.y, e2 = r1.z;
+            const bool c0 = (e0 & NBR_KIND) == NBR_CHILD, c1 = (e1 & NBR_KIND) == NBR_CHILD, c2 = (e2 & NBR_KIND) == NBR_CHILD;
+            const uint32_t x0 = (e0 & NBR_KIND) == NBR_FIXED ? (e0 & NBR_ARG) : 0u;
+            const uint32_t x1 = (e1 & NBR_KIND) == NBR_FIXED ? (e1 & NBR_ARG) : 0u;
+            const uint32_t x2 = (e2 & NBR_KIND) == NBR_FIXED ? (e2 & NBR_ARG) : 0u;
+            const bool has_parent = act && ((e0 & NBR_KIND) == NBR_PARENT || (e1 & NBR_KIND) == NBR_PARENT || (e2 & NBR_KIND) == NBR_PARENT);
+            const uint32_t ps = r1.w & 3u, pn = has_parent ? (r1.w >> 16) : 0u;
+            const uint64_t pp0 = ((uint64_t)r2.y << 32) | r2.x;
+            const uint16_t *pview = m.view + pp0;
+            // the parent's labels this lane will look up: loaded together with the node's own rows, not after the reduction
+            uint32_t want[PRE];
+#pragma unroll
+            for (int q = 0; q < PRE; ++q) { const uint32_t k = glane + (uint32_t)q * G; want[q] = k < pn ? (uint32_t)pview[k] : 0u; }
+            for (uint32_t w = glane; w < mw; w += G) Ms[w] = 0u;
+            __syncwarp();
+            const float *costv = m.cost + p0;
+            const uint16_t *viewv = m.view + p0;
+            const float *m0 = m.M + p0, *m1 = m.M + ms + p0, *m2 = m.M + 2 * ms + p0;
+            float bh = INFINITY;
+            uint32_t bk = 0xFFFFFFFFu;
+#pragma unroll 2
+            for (uint32_t k = glane; k < n; k += G) {
+                const uint32_t vw = viewv[k];
+                const uint32_t lab = vw + 1u;
+                float h = costv[k];
+                if (c0) h = h + __ldcg(m0 + k); else if (x0) h = h + (lab != x0 ? 1.0f : 0.0f);
+                if (c1) h = h + __ldcg(m1 + k); else if (x1) h = h + (lab != x1 ? 1.0f : 0.0f);
+                if (c2) h = h + __ldcg(m2 + k); else if (x2) h = h + (lab != x2 ? 1.0f : 0.0f);
+                Hs[k] = h;
+                if (mw) atomicOr(Ms + (vw >> 5), 1u << (vw & 31u)); else Vs[k] = (uint16_t)vw;
+                if (h < bh) { bh = h; bk = k; }
+            }
+            {   // min / arg-min over the G lanes of the node by two integer warp reductions: every h is >= 0 (costs in [0, 1],
+                // messages sums of such), so the unsigned order of the bit patterns is the float order; ties -> smallest index
+                const uint32_t hb = __float_as_uint(bh);
+                const uint32_t hmin = __reduce_min_sync(gmask, hb);
+                bk = __reduce_min_sync(gmask, hb == hmin ? bk : 0xFFFFFFFFu);
+                bh = __uint_as_float(hmin);
+            }
+            const float hm = bh + 1.0f;
+            __syncwarp();
+            if (act && glane == 0) {   // for the top-down pass: the best label given the subtree, position and value
+                rec[i].amin = bk;
+                rec[i].pad = (uint32_t)viewv[bk] + 1u;
+            }
+            if (mw) {   // prefix popcounts of the label bitmask
+                for (uint32_t w = glane; w < mw; w += G) {
+                    uint32_t c = 0;
+                    for (uint32_t u = 0; u < w; ++u) c += (uint32_t)__popc(Ms[u]);
+                    Ps[w] = (uint16_t)c;
                 }
-                ts.sb_n = n; ts.sb_nodes = nodes; ts.sb_hcap = hcap; ts.sb_vcap = vcap; ts.sb_mcap = mcap;
-                if (slow) atomicAdd(m.state + ST_SLOW, slow);
+                __syncwarp();
             }
-            __syncthreads();
-            lap(c_claim);
-            const uint32_t sb_n = ts.sb_n;
-            const TreePool pool = carve_pool(tree_dyn, ts.sb_nodes, ts.sb_hcap, ts.sb_vcap, ts.sb_mcap);
-            // trees that do not fit (or hold a node of degree > 3) go through global memory, one warp each; the others
-            // are staged (global round trips by one thread per node, row copies by one warp per tree) and then solved
-            // together by the whole CTA
-            batch_load_nodes(m, pool, ts, done, sb_n, ts.sb_nodes);
-            __syncthreads();
-            for (uint32_t i = done + warp; i < done + sb_n; i += TREE_WARPS) {
-                const uint32_t cnt = ts.t_cnt[i] & 0x7FFFFFFFu;
-                if (ts.t_slow[i]) tree_solve_global(m, ts.t_start[i], cnt, lane);
-                else tree_layout(m, pool, cnt, ts.t_node0[i], ts.t_h0[i], ts.t_v0[i], ts.t_m0[i], lane);
+            if (has_parent) {   // the message to the parent, one entry per label of the parent
+                float *mo = m.M + (size_t)ps * ms + pp0;
+                uint16_t *jo = m.J + (size_t)ps * ms + pp0;
+                auto emit = [&](uint32_t k, uint32_t w) {   // w = view of the parent's label k
+                    float msg = hm;
+                    uint32_t jj = 0xFFFFu;
+                    bool found;
+                    uint32_t j;
+                    if (mw) {
+                        const uint32_t word = Ms[w >> 5], bit = w & 31u;
+                        found = (word >> bit) & 1u;
+                        j = (uint32_t)Ps[w >> 5] + (uint32_t)__popc(word & ((1u << bit) - 1u));
+                    } else {
+                        uint32_t lo = 0, hi2 = n;
+                        while (lo < hi2) {
+                            const uint32_t mid = (lo + hi2) >> 1;
+                            if (Vs[mid] < w) lo = mid + 1; else hi2 = mid;
+                        }
+                        j = lo;
+                        found = lo < n && Vs[lo] == w;
+                    }
+                    if (found) {
+                        const float hw = Hs[j];
+                        if (hw < msg) msg = hw;
+                        if (hw <= hm) jj = j;
+                    }
+                    __stcg(mo + k, msg);
+                    __stcg(jo + k, (uint16_t)jj);
+                };
+#pragma unroll
+                for (int q = 0; q < PRE; ++q) { const uint32_t k = glane + (uint32_t)q * G; if (k < pn) emit(k, want[q]); }
+                for (uint32_t k = glane + (uint32_t)PRE * G; k < pn; k += G) emit(k, (uint32_t)pview[k]);
             }
-            cp_async_wait_pending(0);
-            __syncthreads();
-            lap(c_stage);
-            if (ts.sb_nodes) batch_solve<G>(m, pool, ts, ts.sb_nodes);
-            __syncthreads();
-            lap(c_solve);
-            ++n_sb;
-            if (ts.sb_nodes > max_nodes) max_nodes = ts.sb_nodes;
-            done += sb_n;
+            __syncwarp();
         }
-    }
-    if (prof) {
-        atomicAdd(m.dbg + 8, (unsigned long long)c_claim);
-        atomicAdd(m.dbg + 9, (unsigned long long)c_stage);
-        atomicAdd(m.dbg + 10, (unsigned long long)c_solve);
-        atomicAdd(m.dbg + 11, n_sb);
-        atomicMax(m.dbg + 12, max_nodes);
-        atomicAdd(m.dbg + 13, 1ull);
-        atomicAdd(m.dbg + 14, (unsigned long long)ts.c_prep);
-        atomicAdd(m.dbg + 15, (unsigned long long)ts.c_up);
-        atomicAdd(m.dbg + 7, (unsigned long long)ts.c_down);
+        // ---- top-down: shallowest level first, one thread per node, up to 32 nodes of one level per step ----
+        for (uint32_t s = 0; s < cnt;) {
+            const uint32_t i = s + lane;
+            uint4 r0 = make_uint4(0u, 0xFFFF0000u, 0u, 0u), r1 = make_uint4(0u, 0u, 0u, 0u), r2 = r1;
+            if (i < cnt) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(rec + i);
+                r0 = __ldcg(rp); r1 = __ldcg(rp + 1); r2 = __ldcg(rp + 2);
+            }
+            const uint32_t lev0 = __shfl_sync(0xffffffffu, r0.y >> 16, 0);
+            const uint32_t same = __ballot_sync(0xffffffffu, i < cnt && (r0.y >> 16) == lev0);
+            const uint32_t run = same == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~same) - 1u;   // >= 1
+            if (lane < run) {
+                uint32_t bk = r2.z, lab = r2.w, pv = NO_NODE;
+                if ((r1.x & NBR_KIND) == NBR_PARENT) pv = r1.x & NBR_ARG;
+                if ((r1.y & NBR_KIND) == NBR_PARENT) pv = r1.y & NBR_ARG;
+                if ((r1.z & NBR_KIND) == NBR_PARENT) pv = r1.z & NBR_ARG;
+                if (pv != NO_NODE) {   // the parent was assigned one level earlier (by this warp)
+                    const uint32_t ps = r1.w & 3u;
+                    const uint64_t pp0 = ((uint64_t)r2.y << 32) | r2.x;
+                    const uint32_t kp = __ldcg(m.lidx + pv);
+                    const uint32_t plab = __ldcg(m.labels + pv);
+                    const uint32_t j = __ldcg(m.J + (size_t)ps * ms + pp0 + kp);
+                    if (j != 0xFFFFu) { bk = j; lab = plab; }
+                }
+                __stcg(m.labels + r0.x, lab);
+                __stcg(m.lidx + r0.x, bk);
+            }
+            __syncwarp();
+            s += run;
+        }
     }
 }
 
@@ -1188,6 +1044,9 @@ Mrf make_mrf(b2tex_ctx *c, uint32_t iter)
     m.seed = p.seed;
     m.iter = iter;
     m.tree_smem = c->mrf_tree_smem;
+    m.rec = reinterpret_cast<NodeRec *>(c->mrf_rec.p);
+    m.M = c->mrf_M.p; m.J = c->mrf_J.p; m.mstride = c->nnz;
+    m.tree_cap = c->mrf_tree_cap;
     return m;
 }
 
@@ -1219,21 +1078,31 @@ int launch_forest(b2tex_ctx *c, Mrf &m, int build_trees)
     return B2TEX_OK;
 }
 
-template <int G>
-int launch_tree(b2tex_ctx *c, Mrf &m)
+template <int G, int MINB>
+int launch_tree_variant(b2tex_ctx *c, Mrf &m)
 {
     static bool attr_set = false;   // opt in to > 48 KB of dynamic shared memory (per function, once)
     if (!attr_set) {
-        B2_CUDA(cudaFuncSetAttribute(k_tree<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(k_tree<G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
     int per_sm = 0;
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree<G>, TREE_THREADS, m.tree_smem));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree<G, MINB>, TREE_THREADS, m.tree_smem));
     if (per_sm < 1) { set_error("k_tree cannot be resident with %u bytes of shared memory", m.tree_smem); return B2TEX_ERR_CUDA; }
     const int grid = c->num_sms * per_sm;
-    B2_LAUNCH k_tree<G><<<grid, TREE_THREADS, m.tree_smem, c->stream>>>(m);
+    B2_LAUNCH k_tree<G, MINB><<<grid, TREE_THREADS, m.tree_smem, c->stream>>>(m);
     B2_KERNEL_CHECK();
     return B2TEX_OK;
+}
+
+template <int G>
+int launch_tree(b2tex_ctx *c, Mrf &m)
+{
+    const uint32_t n = m.ne - m.nb;
+    B2_LAUNCH k_tree_prep<<<(n + 255) / 256, 256, 0, c->stream>>>(m);   // at most n forest nodes; the kernel reads the count
+    // 3 CTAs of 512 threads per SM (40 registers, a few spills) or 2 (64 registers): the kernel lives on resident warps
+    static const int minb = getenv("B2TEX_TREE_BLOCKS") ? atoi(getenv("B2TEX_TREE_BLOCKS")) : 3;
+    return minb == 2 ? launch_tree_variant<G, 2>(c, m) : launch_tree_variant<G, 3>(c, m);
 }
 
 // peers of this context, or nranks == 1
@@ -1345,6 +1214,9 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
     // stream inside the driver; with several ranks driven from one process that blocks the peers' launches)
     if (!c->mrf_host_flags) B2_CUDA(cudaHostAlloc((void **)&c->mrf_host_flags, (64 + 2 * MRF_SLOTS + 64) * sizeof(uint32_t), cudaHostAllocDefault));
     B2_TRY(c->mrf_H.alloc(c->nnz));
+    B2_TRY(c->mrf_M.alloc(3 * (size_t)c->nnz));
+    B2_TRY(c->mrf_J.alloc(3 * (size_t)c->nnz));
+    B2_TRY(c->mrf_rec.alloc(3 * F));   // 48-byte records as uint4 triples
     B2_TRY(c->mrf_hminp1.alloc(F));
     B2_TRY(c->mrf_amin.alloc(F));
     B2_TRY(c->mrf_level.alloc(F));
@@ -1379,9 +1251,22 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
     uint32_t words = (c->K + 1 + 31) / 32;
     static const bool no_masks = getenv("B2TEX_NO_MASKS") != nullptr;
     c->mrf_mask_words = (c->K == 0 || words > (uint32_t)MAX_MASK_WORDS || no_masks) ? 0 : words;
-    // shared-memory pool of k_tree: room for a few average trees (~ rounds * 2.7 nodes) per CTA
-    uint32_t smem = 100 * 1024;
-    if (const char *e = getenv("B2TEX_TREE_SMEM_KB")) smem = (uint32_t)std::max(8, std::min(200, atoi(e))) * 1024u;
+    // shared-memory scratch of k_tree: one h row + label list (6 bytes per label) per lane group; the longest label
+    // list decides (longer ones -- only if a face sees more than 1024 views -- go through the global tables)
+    uint32_t maxn = 0;
+    if (nodes) {
+        B2_TRY(c->s_limits.alloc(1));
+        B2_TRY(c->s_limits.zero(c->stream));
+        B2_LAUNCH k_max_labels<<<std::max(1, c->num_sms * 4), 256, 0, c->stream>>>(c->dc_ptr.p, c->face_begin, c->face_end, c->s_limits.p);
+        B2_KERNEL_CHECK();
+        B2_CUDA(cudaMemcpyAsync(c->mrf_host_flags + 32, c->s_limits.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        maxn = c->mrf_host_flags[32];
+    }
+    uint32_t cap = std::min(1024u, std::max(16u, (maxn + 15u) & ~15u));
+    if (const char *e = getenv("B2TEX_TREE_CAP")) cap = (uint32_t)std::max(16, std::min(1024, atoi(e) & ~15));
+    c->mrf_tree_cap = cap;
+    uint32_t smem = (uint32_t)TREE_WARPS * (32u / (uint32_t)c->mrf_group) * tree_group_bytes(cap, c->mrf_mask_words);
     c->mrf_tree_smem = smem;
     return B2TEX_OK;
 }
@@ -1442,8 +1327,9 @@ int mrf_prepare(b2tex_ctx *c, const b2tex_mrf_params *p)
     cudaFuncAttributes fa;
     const void *fns[] = {(const void *)k_forest, (const void *)k_energy, (const void *)k_stop, (const void *)k_label_check,
                          (const void *)k_build_adj4, (const void *)k_halo_build, (const void *)k_halo_push, (const void *)k_range_push,
-                         (const void *)k_mg_sync, (const void *)k_tree<4>, (const void *)k_tree<8>, (const void *)k_tree<16>,
-                         (const void *)k_tree<32>, (const void *)k_init_labels<4>, (const void *)k_init_labels<8>,
+                         (const void *)k_mg_sync, (const void *)k_tree_prep, (const void *)k_max_labels, (const void *)k_tree<4, 3>, (const void *)k_tree<8, 3>, (const void *)k_tree<16, 3>,
+                         (const void *)k_tree<32, 3>, (const void *)k_tree<4, 2>, (const void *)k_tree<8, 2>, (const void *)k_tree<16, 2>,
+                         (const void *)k_tree<32, 2>, (const void *)k_init_labels<4>, (const void *)k_init_labels<8>,
                          (const void *)k_init_labels<16>, (const void *)k_init_labels<32>};
     for (const void *f : fns) B2_CUDA(cudaFuncGetAttributes(&fa, f));
     return B2TEX_OK;
@@ -1550,11 +1436,7 @@ int mrf_run(b2tex_ctx *c, const b2tex_mrf_params *p, b2tex_mrf_info *info, doubl
         B2_CUDA(cudaStreamSynchronize(s));
         fprintf(stderr, "k_forest phases over %u iterations [us]: round0 %.1f seed %.1f growth %.1f alloc %.1f scatter %.1f\n", t_end,
                 d[1] / 1e3, d[2] / 1e3, d[3] / 1e3, d[4] / 1e3, d[5] / 1e3);
-        const double ctas = d[13] ? (double)d[13] : 1.0;
-        fprintf(stderr, "k_tree solve split per CTA-launch [kcycles]: masks+buckets %.1f up %.1f down %.1f\n", d[14] / ctas / 1e3, d[15] / ctas / 1e3, d[7] / ctas / 1e3);
-        fprintf(stderr, "k_tree per CTA-launch [kcycles]: claim+pack %.1f stage %.1f solve %.1f; sub-batches/CTA-launch %.1f, largest sub-batch %llu nodes, "
-                        "trees through global memory %u, forest nodes %llu in %llu labels\n", d[8] / ctas / 1e3, d[9] / ctas / 1e3, d[10] / ctas / 1e3,
-                (double)d[11] / ctas, d[12], st[ST_SLOW], fn, fz);
+        fprintf(stderr, "k_tree: trees through global memory %u, forest nodes %llu in %llu labels\n", st[ST_SLOW], fn, fz);
     }
     if (st[ST_BAD]) { set_error("Incorrect labeling"); return B2TEX_ERR_LABELING; }
     return B2TEX_OK;

@@ -22,6 +22,8 @@
 // Measured (round 2, C3 on 2 B200, 149 iterations): all-gather of the whole slice of p + one system fence per thread:
 // 146 us per iteration; halo-only pushes of p with three flag barriers bracketed by grid.sync(): 113 us; one GPU: 70 us.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -67,7 +69,9 @@ struct PcgMg {
     const uint32_t *n_imp;       // their number (device side: written by k_pcg_mg_imports)
     double *blockpart;           // [grid][8] per-block partials of this rank
     uint32_t *status;            // [0..2] iterations, [3..5] residual bits, [6] loops, [7] barrier timeouts, [8] epoch,
-                                 // [10] tickets of the all-reduces, [11] tickets of the device-local barrier
+                                 // [10] tickets of the all-reduces, [11] tickets of the device-local barrier,
+                                 // [16..21] ns block 0 spent in SpMV / all-reduce A / update / all-reduce B / p / local barrier
+    uint32_t timing;             // diagnostic (B2TEX_SEAM_TIMING): fill status[16..21]
     void *peer[MG_MAX_RANKS];    // base pointers of every rank's MgBlock (peer[rank] = own)
     uint32_t max_iters;
     float tol;
@@ -86,6 +90,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned long long mg_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
 {
@@ -240,6 +250,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
     uint32_t epoch = q.epoch0, seq = 0, lseq = 0;
     int parity = 0;
     bool alive = true;
+    const bool prof = q.timing && tid == 0;
+    unsigned long long tprev = prof ? mg_timer_ns() : 0ull;
+    auto lap = [&](int slot) {
+        if (prof) { const unsigned long long t = mg_timer_ns(); q.status[16 + slot] += (uint32_t)(t - tprev); tprev = t; }
+    };
 
     // r = rhs, p = M^-1 r on the own rows AND on the imported rows (the assembly is replicated: no exchange needed)
     for (int k = 0; k < 6; ++k) acc[k] = 0.0;
@@ -304,7 +319,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
                 acc[0] += (double)pb.x * b0; acc[1] += (double)pb.y * b1; acc[2] += (double)pb.z * b2;
             }
         }
+        lap(0);
         alive = mg_allreduce6(q, acc, smem, s_last, parity, ++epoch, ++seq, false, alive, tot); parity ^= 1;
+        lap(1);
         float alpha[3];
         for (int c = 0; c < 3; ++c) alpha[c] = active[c] ? absNew[c] / (float)tot[c] : 0.0f;
 
@@ -330,7 +347,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
             }
             if (q.dest[i]) mg_push_z(q, i, make_float4(zv[0], zv[1], zv[2], 0.0f));
         }
+        lap(2);
         alive = mg_allreduce6(q, acc, smem, s_last, parity, ++epoch, ++seq, true, alive, tot); parity ^= 1;
+        lap(3);
         float beta[3] = {0.0f, 0.0f, 0.0f};
         bool upd[3];
         for (int c = 0; c < 3; ++c) {
@@ -366,7 +385,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
             }
         }
         ++loops;
+        lap(4);
         alive = mg_local_sync(q, s_last, ++lseq, alive);
+        lap(5);
     }
     // x -= mean(x) (:277), then every rank gets the complete solution
     for (int k = 0; k < 6; ++k) acc[k] = 0.0;
@@ -390,6 +411,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
         }
         q.status[6] = loops;
         q.status[8] = epoch;
+        q.status[22] = n_imp;
     }
 }
 
@@ -434,12 +456,12 @@ int seam_mg_export(b2tex_ctx *c, uint32_t rank, uint32_t nranks, void *handle64)
     B2_CUDA(cudaStreamSynchronize(c->stream));
     m->peer[rank] = m->block;
     B2_TRY(m->blockpart.alloc(4096 * 8));   // every allocation happens here: nothing inside the solve waits for the device
-    B2_TRY(m->status.alloc(16));
+    B2_TRY(m->status.alloc(32));
     B2_TRY(m->dest.alloc(c->R));
     B2_TRY(m->imp_mark.alloc(c->R));
     B2_TRY(m->imp.alloc(c->R));
     B2_TRY(m->n_imp.alloc(1));
-    B2_CUDA(cudaHostAlloc((void **)&m->pinned, 16 * sizeof(uint32_t), cudaHostAllocDefault));
+    B2_CUDA(cudaHostAlloc((void **)&m->pinned, 32 * sizeof(uint32_t), cudaHostAllocDefault));
     cudaFuncAttributes fa;   // load the kernels now (the first launch of a lazily loaded kernel synchronises the context)
     B2_CUDA(cudaFuncGetAttributes(&fa, (const void *)k_pcg_mg));
     B2_CUDA(cudaFuncGetAttributes(&fa, (const void *)k_pcg_mg_dest));
@@ -501,6 +523,8 @@ int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info)
     B2_LAUNCH k_pcg_mg_imports<<<(R + 255) / 256, 256, 0, s>>>(R, m->imp_mark.p, m->imp.p, m->n_imp.p);
     q.imp = m->imp.p; q.n_imp = m->n_imp.p;
     for (int k = 0; k < MG_MAX_RANKS; ++k) q.peer[k] = m->peer[k];
+    static const bool seam_timing = getenv("B2TEX_SEAM_TIMING") != nullptr;
+    q.timing = seam_timing ? 1u : 0u;
     q.max_iters = 1000u; q.tol = 0.0001f; q.epoch0 = m->epoch; q.spin_limit = 4ull * 1000 * 1000;   // x (20 ns sleep + a system-scope load): a few seconds
     void *args[] = {&q};
     cudaEvent_t e0, e1;
@@ -509,10 +533,10 @@ int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info)
     count_launch();
     B2_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg_mg, dim3(grid), dim3(MG_THREADS), args, 0, s));
     B2_CUDA(cudaEventRecord(e1, s));
-    uint32_t st[16];
+    uint32_t st[32];
     // read back through pinned memory: a copy to pageable memory waits for the stream inside the driver, which (ranks driven
     // from one process) would keep the peers from launching the kernel this one is waiting for
-    if (!m->pinned) B2_CUDA(cudaHostAlloc((void **)&m->pinned, 16 * sizeof(uint32_t), cudaHostAllocDefault));
+    if (!m->pinned) B2_CUDA(cudaHostAlloc((void **)&m->pinned, 32 * sizeof(uint32_t), cudaHostAllocDefault));
     B2_CUDA(cudaMemcpyAsync(m->pinned, m->status.p, sizeof(st), cudaMemcpyDeviceToHost, s));
     // the complete solution sits in the own peer block: copy it where the single-GPU path leaves it
     B2_CUDA(cudaMemcpyAsync(c->seam_x.p, mg_carve(m->block, R).x, 3 * (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -522,6 +546,9 @@ int seam_mg_solve(b2tex_ctx *c, b2tex_seam_info *info)
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     m->epoch = st[8];
+    if (seam_timing)
+        fprintf(stderr, "k_pcg_mg rank %u: %u iterations, block 0 [us]: spmv %.0f allreduce_a %.0f update %.0f allreduce_b %.0f p %.0f local_barrier %.0f; imports %u\n",
+                m->rank, st[6], st[16] / 1e3, st[17] / 1e3, st[18] / 1e3, st[19] / 1e3, st[20] / 1e3, st[21] / 1e3, st[22]);
     if (st[7]) { set_error("k_pcg_mg: %u cross-GPU barrier timeouts (a peer did not arrive)", st[7]); return B2TEX_ERR_CUDA; }
     for (int ch = 0; ch < 3; ++ch) { info->iterations[ch] = st[ch]; memcpy(&info->residual[ch], &st[3 + ch], 4); }
     info->cg_launch_iterations = st[6];

@@ -245,6 +245,16 @@ static inline unsigned __reduce_min_sync(unsigned mask, unsigned v)
     emul::wait(w->bar);
     return r;
 }
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v)
+{
+    emul::Warp *w = emul::g_cur->warp;
+    w->slot[threadIdx.x & 31u] = v;
+    emul::wait(w->bar);
+    unsigned r = 0u;
+    for (unsigned l = 0; l < 32; ++l) if ((mask >> l) & 1u) r = std::max(r, (unsigned)w->slot[l]);
+    emul::wait(w->bar);
+    return r;
+}
 static inline unsigned __ballot_sync(unsigned, bool p)
 {
     emul::Warp *w = emul::g_cur->warp;

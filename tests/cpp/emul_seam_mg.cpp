@@ -17,6 +17,7 @@ namespace {
 inline void st_release_sys(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
 inline uint32_t ld_acquire_sys(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 inline uint32_t ld_acquire_gpu(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+inline unsigned long long mg_timer_ns() { return 0; }
 }  // namespace
 }  // namespace b2
 #include "seam_mg_kernels.inc"
@@ -82,7 +83,7 @@ int emul_seam_mg(const float *verts, uint32_t Vn, const uint32_t *faces, uint32_
     std::vector<std::vector<char> > blocks(ranks, std::vector<char>(mg_block_bytes(R), 0));
     std::vector<std::vector<float> > rr(ranks, std::vector<float>(3 * (size_t)R)), tt(ranks, std::vector<float>(3 * (size_t)R));
     std::vector<std::vector<double> > bp(ranks, std::vector<double>((size_t)grid * 8, 0.0));
-    std::vector<std::vector<uint32_t> > st(ranks, std::vector<uint32_t>(16, 0u));
+    std::vector<std::vector<uint32_t> > st(ranks, std::vector<uint32_t>(32, 0u));
     std::vector<PcgMg> q(ranks);
     std::vector<std::vector<uint8_t> > dest(ranks, std::vector<uint8_t>(R, 0xFF));   // 0xFF outside the own rows: never read
     std::vector<std::vector<uint8_t> > imark(ranks, std::vector<uint8_t>(R, 0));
@@ -96,7 +97,7 @@ int emul_seam_mg(const float *verts, uint32_t Vn, const uint32_t *faces, uint32_
         p.csr_ptr = csr_ptr.data(); p.csr_enc = csr_enc.data(); p.diag_val = dval.data(); p.inv_diag = inv_diag.data(); p.rhs = rhs3.data();
         p.r = rr[k].data(); p.t = tt[k].data(); p.blockpart = bp[k].data(); p.status = st[k].data();
         for (uint32_t j = 0; j < (uint32_t)MG_MAX_RANKS; ++j) p.peer[j] = j < ranks ? (void *)blocks[j].data() : nullptr;
-        p.max_iters = 1000u; p.tol = 0.0001f; p.epoch0 = 0xFFFFFFF0u;   // start close to the wrap-around of the epoch counter
+        p.timing = 0u; p.max_iters = 1000u; p.tol = 0.0001f; p.epoch0 = 0xFFFFFFF0u;   // start close to the wrap-around of the epoch counter
         p.spin_limit = 1000000000ull;
         if (p.r1 > p.r0)
             emul::launch_serial((p.r1 - p.r0 + 255) / 256, 256, [&] { k_pcg_mg_dest(R, p.r0, p.r1, k, ranks, csr_ptr.data(), csr_enc.data(), dest[k].data(), imark[k].data()); });

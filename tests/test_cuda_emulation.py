@@ -144,8 +144,8 @@ def test_device_data_cost_kernels(emul, orc, get_scene, name, data_term, vis):
 
 
 @pytest.mark.parametrize("name,kw", [("tiny", {}), ("occ", {}), ("occ", dict(root_div=0, rounds=200)), ("occ", dict(num_parts=2)),
-                                     ("occ", dict(group=32)), ("messy", {}), ("occ", dict(smem=6144)), ("occ", dict(smem=2048, group=8)),
-                                     ("occ", dict(rounds=32, root_div=256, smem=16384))])
+                                     ("occ", dict(group=32)), ("messy", {}), ("occ", dict(cap=16)), ("occ", dict(cap=16, group=8)),
+                                     ("occ", dict(rounds=32, root_div=256, cap=32))])
 def test_device_view_selection_kernels(emul, orc, scene_mod, get_scene, name, kw):
     """csrc/mrf.cu on fibers vs orc_view_selection: identical forest levels in iteration 1, identical iteration count,
     identical labels (=> identical energy).  `occ`: unseen faces (label 0, excluded from the graph), ten components,
@@ -154,12 +154,12 @@ def test_device_view_selection_kernels(emul, orc, scene_mod, get_scene, name, kw
     adj = scene_mod.face_adjacency(s.faces)
     dc = orc.data_costs(s)
     P = dict(orc.DEFAULT_MRF)
-    okw = {k: v for k, v in kw.items() if k not in ("group", "smem")}
+    okw = {k: v for k, v in kw.items() if k not in ("group", "cap")}
     P.update(okw)
     o = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1, **okw)
     F = s.num_faces
     params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], P["num_parts"], kw.get("group", 0),
-                       kw.get("smem", 0), 0], np.uint32)
+                       kw.get("cap", 0), 0], np.uint32)
     stats = np.zeros(4, np.uint64)
     labels = np.zeros(F, np.uint32)
     trace = np.full(P["max_iterations"] + 1, np.nan)
@@ -174,13 +174,14 @@ def test_device_view_selection_kernels(emul, orc, scene_mod, get_scene, name, kw
     assert abs(trace[it] - o["energy"]) <= 1e-6 * max(1.0, o["energy"])
     if name == "occ":
         assert (o["labels"] == 0).sum() > 10
-    if kw.get("root_div", 1) == 0 or kw.get("smem", 1 << 20) <= 6144:
-        assert stats[0] > 0          # trees that do not fit the pool took the global-memory recursion
-    elif name != "messy" and "smem" not in kw:
-        assert stats[0] == 0, stats  # default pool: every tree of these scenes is solved in shared memory
+    maxn = int(np.diff(dc["face_ptr"]).max())
+    if "cap" in kw and maxn > kw["cap"]:
+        assert stats[0] > 0          # trees with a label list longer than the scratch took the global-memory recursion
+    elif name != "messy":
+        assert stats[0] == 0, stats  # every tree of these scenes (manifold, lists within the scratch) is solved by k_tree proper
 
 
-@pytest.mark.parametrize("name,ranks,kw", [("occ", 2, {}), ("occ", 3, dict(smem=4096)), ("C2s", 4, {}), ("tiny", 8, {}), ("messy", 2, {})])
+@pytest.mark.parametrize("name,ranks,kw", [("occ", 2, {}), ("occ", 3, dict(cap=16)), ("C2s", 4, {}), ("tiny", 8, {}), ("messy", 2, {})])
 def test_device_multi_gpu_view_selection(emul, orc, scene_mod, get_scene, name, ranks, kw):
     """The multi-GPU view selection on `ranks` emulated devices: every rank owns a contiguous face range, runs k_forest /
     k_tree on it, stores the labels of its boundary faces into the label arrays of the ranks that own a neighbour
@@ -194,7 +195,7 @@ def test_device_multi_gpu_view_selection(emul, orc, scene_mod, get_scene, name, 
     P = dict(orc.DEFAULT_MRF)
     o = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1, num_parts=ranks)
     F = s.num_faces
-    params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], ranks, 0, kw.get("smem", 0), ranks], np.uint32)
+    params = np.array([P["max_iterations"], P["rounds"], P["root_div"], P["seed"], P["window"], ranks, 0, kw.get("cap", 0), ranks], np.uint32)
     stats = np.zeros(4, np.uint64)
     labels = np.zeros(F, np.uint32)
     trace = np.full(P["max_iterations"] + 1, np.nan)
