@@ -11,16 +11,22 @@
 //     imported rows with the same two roundings as the owner.  The exchange therefore rides on the barrier of the
 //     all-reduce that CG needs anyway; there is no third cross-GPU barrier per iteration;
 //   * dot products: two all-reduces per iteration (p.t; |r|^2 and r.z).  Every block leaves its fp64 partial sums in a
-//     table and takes a ticket; the LAST block of the rank adds the table in block order, stores the rank's sums into slot
-//     [parity][rank] of every peer, fences at system scope and raises its epoch flag at every peer; all blocks of all
-//     ranks wait for all flags and add the P slots in rank order -> bit-identical scalars on every GPU.  This one step is
-//     reduction, cross-GPU barrier and grid-wide barrier at once (no cooperative-groups grid.sync in the loop);
+//     table and takes a ticket; the LAST block of the rank adds the table in block order and stores the rank's sums into
+//     slot [parity][rank] of every peer as twelve 8-byte words {32 bits of payload, epoch}: payload and flag travel in one
+//     store, so neither side needs a system-scope fence (the "LL" protocol of collective libraries); all blocks of all
+//     ranks poll the P x 12 words of the epoch and add the P slots in rank order -> bit-identical scalars on every GPU.
+//     This one step is reduction, cross-GPU barrier and grid-wide barrier at once (no cooperative-groups grid.sync in the
+//     loop).  The halo entries of z are self-validating in the same way: the unused fourth component of the float4
+//     carries the epoch, the reader polls the entry itself;
 //   * one device-local barrier per iteration (ticket counter) between the update of p and the next SpMV.
 // Results are deterministic for a given rank count and grid; they differ from the single-GPU kernel only by the
 // summation order of the reductions (per block, per rank, then across ranks).
 //
 // Measured (round 2, C3 on 2 B200, 149 iterations): all-gather of the whole slice of p + one system fence per thread:
-// 146 us per iteration; halo-only pushes of p with three flag barriers bracketed by grid.sync(): 113 us; one GPU: 70 us.
+// 146 us per iteration; halo-only pushes of p with three flag barriers bracketed by grid.sync(): 113 us; two fused
+// all-reduce barriers with fence.sys + st.release.sys flags: 78 us, of which 22 us compute and 23 + 30 us inside the two
+// all-reduces (the system-scope fences); the same with self-validating words instead of fences: 52 us (13 + 14 us in the
+// all-reduces); with the block reduction finished by one warp: 39 us (7 + 7 us); one GPU (k_pcg): 70 us.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -32,19 +38,21 @@ namespace b2 {
 constexpr int MG_MAX_RANKS = 8;
 
 // Layout of the peer-visible block every rank allocates (and exports through one cudaIpc handle):
-//   float4 p[R] | float4 z[R] | float x[3][R] | double part[2][MG_MAX_RANKS][8] | uint32 flag[MG_MAX_RANKS] (padded to 64 B)
-// p is only written by the owner of the block; z (halo rows), x (final all-gather), part and flag are written by peers.
+//   float4 p[R] | float4 z[R] | float x[3][R] | uint2 ll[2][MG_MAX_RANKS][12] | uint32 flag[MG_MAX_RANKS] (padded to 64 B)
+// p is only written by the owner of the block; z (halo rows, w = epoch tag), x (final all-gather) and ll (all-reduce slots:
+// {half of a double, epoch} per word) are written by peers.
+constexpr int MG_LL_WORDS = 12;   // six doubles as twelve self-validating 8-byte words
 struct MgBlock {
     float4 *p, *z;
     float *x;
-    double *part;
+    uint2 *ll;
     uint32_t *flag;
 };
 // every section starts on a 64-byte boundary (R may be odd: 12 R bytes would leave the doubles misaligned)
 __host__ __device__ inline size_t mg_align64(size_t n) { return (n + 63) & ~(size_t)63; }
 __host__ __device__ inline size_t mg_block_bytes(uint32_t R)
 {
-    return 2 * mg_align64((size_t)R * 16) + mg_align64((size_t)R * 12) + mg_align64(2 * MG_MAX_RANKS * 8 * sizeof(double)) + 64;
+    return 2 * mg_align64((size_t)R * 16) + mg_align64((size_t)R * 12) + mg_align64(2 * MG_MAX_RANKS * MG_LL_WORDS * sizeof(uint2)) + 64;
 }
 __host__ __device__ inline MgBlock mg_carve(void *base, uint32_t R)
 {
@@ -53,7 +61,7 @@ __host__ __device__ inline MgBlock mg_carve(void *base, uint32_t R)
     b.p = (float4 *)c; c += mg_align64((size_t)R * 16);
     b.z = (float4 *)c; c += mg_align64((size_t)R * 16);
     b.x = (float *)c; c += mg_align64((size_t)R * 12);
-    b.part = (double *)c; c += mg_align64(2 * MG_MAX_RANKS * 8 * sizeof(double));
+    b.ll = (uint2 *)c; c += mg_align64(2 * MG_MAX_RANKS * MG_LL_WORDS * sizeof(uint2));
     b.flag = (uint32_t *)c;
     return b;
 }
@@ -91,6 +99,28 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// 8- and 16-byte accesses that are performed as ONE transaction and never cached in L1 (payload and tag arrive together)
+__device__ __forceinline__ void st_volatile_v2(uint2 *p, uint32_t a, uint32_t b)
+{
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 ld_volatile_v2(const uint2 *p)
+{
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_v4(float4 *p, float a, float b, float c, uint32_t tag)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)),
+                 "r"(__float_as_uint(c)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const float4 *p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long mg_timer_ns()
 {
     unsigned long long t;
@@ -104,6 +134,8 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
     return v;
 }
 
+// Sum of six doubles over the block, in a fixed order: shuffles inside every warp, one row per warp in shared memory,
+// then the first warp adds the rows (lane = warp) by shuffles again.  Only thread 0 ends up with the sums.
 __device__ __forceinline__ void mg_block_reduce6(double v[6], double *smem)
 {
     for (int k = 0; k < 6; ++k)
@@ -113,19 +145,22 @@ __device__ __forceinline__ void mg_block_reduce6(double v[6], double *smem)
     if (lane == 0)
         for (int k = 0; k < 6; ++k) smem[warp * 6 + k] = v[k];
     __syncthreads();
-    const int nw = blockDim.x >> 5;
-    for (int k = 0; k < 6; ++k) {
-        double s = 0.0;
-        for (int w = 0; w < nw; ++w) s += smem[w * 6 + k];
-        v[k] = s;
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int k = 0; k < 6; ++k) {
+            double s = lane < nw ? smem[lane * 6 + k] : 0.0;
+            for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            v[k] = s;
+        }
     }
 }
 
 // All-reduce of six partial sums across all blocks of all ranks = grid-wide barrier + cross-GPU barrier, in one step.
 // `seq` counts the calls of this solve (1, 2, ...): the ticket that completes call `seq` is seq * gridDim.x.  `remote`:
-// this rank stored into peer memory since the previous call (halo of z, final x): those stores are fenced at system
-// scope by one thread per block, after the block's own barrier, before the ticket.  Everything any thread of any rank
-// stored before its call is visible to every thread of every rank after it.
+// this rank stored ordinary data into peer memory since the previous call (the final all-gather of x): those stores are
+// fenced at system scope by one thread per block, after the block's own barrier, before the ticket, and once more before
+// the words go out; then everything any thread of any rank stored before its call is visible to every thread of every
+// rank after it.  Inside the iteration nothing needs that: the halo of z validates itself.
 __device__ __forceinline__ bool mg_allreduce6(const PcgMg &q, double acc[6], double *smem, uint32_t *s_last, int parity,
                                               uint32_t epoch, uint32_t seq, bool remote, bool alive, double tot[6])
 {
@@ -146,28 +181,41 @@ __device__ __forceinline__ bool mg_allreduce6(const PcgMg &q, double acc[6], dou
         for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x)
             for (int k = 0; k < 6; ++k) v[k] += __ldcg(q.blockpart + (size_t)b * 8 + k);
         mg_block_reduce6(v, smem);
-        if (threadIdx.x < q.nranks) {
-            const uint32_t k = threadIdx.x;
-            const MgBlock pk = mg_carve(q.peer[k], q.R);
-            for (int j = 0; j < 6; ++j) pk.part[((size_t)parity * MG_MAX_RANKS + q.rank) * 8 + j] = v[j];
-            __threadfence_system();
-            st_release_sys(pk.flag + q.rank, epoch);                 // tell rank k: rank `rank` reached `epoch`
+        __syncthreads();
+        if (threadIdx.x == 0) for (int k = 0; k < 6; ++k) smem[k] = v[k];
+        __syncthreads();
+        if (threadIdx.x < q.nranks * MG_LL_WORDS) {   // one 8-byte word {half of a sum, epoch} per thread
+            const uint32_t k = threadIdx.x / MG_LL_WORDS, hw = threadIdx.x % MG_LL_WORDS;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(smem[hw >> 1]);
+            if (remote) __threadfence_system();   // the final all-gather of x: ordinary stores before the words that announce them
+            st_volatile_v2(mg_carve(q.peer[k], q.R).ll + ((size_t)parity * MG_MAX_RANKS + q.rank) * MG_LL_WORDS + hw,
+                           (uint32_t)(bits >> (32 * (hw & 1u))), epoch);
         }
     }
-    if (threadIdx.x < q.nranks) {                                    // every block waits until every rank reached it
-        const uint32_t *mine = mg_carve(q.peer[q.rank], q.R).flag + threadIdx.x;
+    // every block collects the words of every rank (its own included): P x 12 pollers, payload and tag in one load
+    uint32_t *halves = reinterpret_cast<uint32_t *>(smem);   // [P][12]; smem is free again after the block reduction
+    __syncthreads();
+    if (threadIdx.x < q.nranks * MG_LL_WORDS) {
+        const uint2 *w = mg_carve(q.peer[q.rank], q.R).ll + (size_t)parity * MG_MAX_RANKS * MG_LL_WORDS +
+                         (size_t)(threadIdx.x / MG_LL_WORDS) * MG_LL_WORDS + threadIdx.x % MG_LL_WORDS;
         unsigned long long spins = 0;
-        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-            __nanosleep(20);
-            if (++spins > q.spin_limit) { atomicAdd(q.status + 7, 1u); break; }
+        uint2 got = ld_volatile_v2(w);
+        while (got.y != epoch) {
+            if (++spins > 64) __nanosleep(20);   // the words normally arrive within a few microseconds: poll hard first
+            if (spins > q.spin_limit) { atomicAdd(q.status + 7, 1u); break; }
+            got = ld_volatile_v2(w);
         }
+        halves[threadIdx.x] = got.x;
     }
     __syncthreads();
     if (threadIdx.x == 0) s_last[1] = __ldcg(q.status + 7);   // one verdict per block
-    const double *part = mg_carve(q.peer[q.rank], q.R).part + (size_t)parity * MG_MAX_RANKS * 8;
     for (int k = 0; k < 6; ++k) {
         double sum = 0.0;
-        for (uint32_t r = 0; r < q.nranks; ++r) sum += __ldcg(part + (size_t)r * 8 + k);   // rank order: identical on every GPU
+        for (uint32_t r = 0; r < q.nranks; ++r) {   // rank order: identical on every GPU
+            const unsigned long long bits = (unsigned long long)halves[r * MG_LL_WORDS + 2 * k] |
+                                            ((unsigned long long)halves[r * MG_LL_WORDS + 2 * k + 1] << 32);
+            sum += __longlong_as_double((long long)bits);
+        }
         tot[k] = sum;
     }
     __syncthreads();
@@ -195,11 +243,11 @@ __device__ __forceinline__ bool mg_local_sync(const PcgMg &q, uint32_t *s_last, 
 }
 
 // z = M^-1 r of one own row goes to the ranks that read this row's entry of p
-__device__ __forceinline__ void mg_push_z(const PcgMg &q, uint32_t i, const float4 &v)
+__device__ __forceinline__ void mg_push_z(const PcgMg &q, uint32_t i, float a, float b, float c, uint32_t tag)
 {
     for (uint32_t mk = q.dest[i]; mk; mk &= mk - 1u) {
         const uint32_t k = (uint32_t)__ffs((int)mk) - 1u;
-        mg_carve(q.peer[k], q.R).z[i] = v;
+        st_volatile_v4(mg_carve(q.peer[k], q.R).z + i, a, b, c, tag);   // one 16-byte store: values and tag arrive together
     }
 }
 
@@ -345,10 +393,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
                 acc[c] += (double)rv * rv;
                 acc[3 + c] += (double)rv * zv[c];
             }
-            if (q.dest[i]) mg_push_z(q, i, make_float4(zv[0], zv[1], zv[2], 0.0f));
+            if (q.dest[i]) mg_push_z(q, i, zv[0], zv[1], zv[2], epoch + 1u);   // tag = the epoch of the all-reduce that follows
         }
         lap(2);
-        alive = mg_allreduce6(q, acc, smem, s_last, parity, ++epoch, ++seq, true, alive, tot); parity ^= 1;
+        alive = mg_allreduce6(q, acc, smem, s_last, parity, ++epoch, ++seq, false, alive, tot); parity ^= 1;
         lap(3);
         float beta[3] = {0.0f, 0.0f, 0.0f};
         bool upd[3];
@@ -377,10 +425,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_pcg_mg(PcgMg q)
             for (uint32_t j = tid; j < n_imp; j += nth) {
                 const uint32_t i = q.imp[j];
                 float4 pi = own.p[i];
-                const float4 zi = __ldcg(own.z + i);
-                if (upd[0]) pi.x = zi.x + beta[0] * pi.x;
-                if (upd[1]) pi.y = zi.y + beta[1] * pi.y;
-                if (upd[2]) pi.z = zi.z + beta[2] * pi.z;
+                uint4 zi = ld_volatile_v4(own.z + i);   // the owner stored it before it entered the all-reduce: normally there
+                unsigned long long spins = 0;
+                while (zi.w != epoch && alive) {
+                    __nanosleep(20);
+                    if (++spins > q.spin_limit) { atomicAdd(q.status + 7, 1u); break; }
+                    zi = ld_volatile_v4(own.z + i);
+                }
+                if (upd[0]) pi.x = __uint_as_float(zi.x) + beta[0] * pi.x;
+                if (upd[1]) pi.y = __uint_as_float(zi.y) + beta[1] * pi.y;
+                if (upd[2]) pi.z = __uint_as_float(zi.z) + beta[2] * pi.z;
                 own.p[i] = pi;
             }
         }

@@ -119,7 +119,14 @@ class ShardedPipeline:
         t1 = time.perf_counter()
         mrf, trace = c.view_selection_run()
         t2 = time.perf_counter()
-        seam = c.seam_run()
+        if os.environ.get("B2TEX_SEAM_MG1", "0") == "1":   # experiment: the multi-GPU kernel on one rank
+            seam = c.seam_assemble()
+            if getattr(self, "_mg_rows", None) != int(seam.num_rows):
+                c.seam_mg_export(0, 1)
+                self._mg_rows = int(seam.num_rows)
+            c.seam_mg_solve(seam)
+        else:
+            seam = c.seam_run()
         t3 = time.perf_counter()
         return dict(dc=dc, mrf=mrf, seam=seam, trace=trace,
                     stage_s=dict(data_costs=t1 - t0, view_selection=t2 - t1, seam_leveling=t3 - t2))

@@ -267,6 +267,8 @@ static inline unsigned __ballot_sync(unsigned, bool p)
     return r;
 }
 
+static inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }

@@ -18,6 +18,13 @@ inline void st_release_sys(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = 
 inline uint32_t ld_acquire_sys(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 inline uint32_t ld_acquire_gpu(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 inline unsigned long long mg_timer_ns() { return 0; }
+inline void st_volatile_v2(uint2 *p, uint32_t a, uint32_t b) { uint2 v; v.x = a; v.y = b; *p = v; }
+inline uint2 ld_volatile_v2(const uint2 *p) { return *p; }
+inline void st_volatile_v4(float4 *p, float a, float b, float c, uint32_t tag)
+{
+    float4 v; v.x = a; v.y = b; v.z = c; memcpy(&v.w, &tag, 4); *p = v;
+}
+inline uint4 ld_volatile_v4(const float4 *p) { uint4 v; memcpy(&v, p, 16); return v; }
 }  // namespace
 }  // namespace b2
 #include "seam_mg_kernels.inc"
