@@ -59,6 +59,8 @@ int b2tex_create(int device, b2tex_ctx **out)
     B2_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    B2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    B2_CUDA(cudaEventCreateWithFlags(&c->images_uploaded, cudaEventDisableTiming));
     *out = c;
     return B2TEX_OK;
 }
@@ -72,6 +74,8 @@ void b2tex_destroy(b2tex_ctx *c)
     seam_mg_free(c);
     mrf_mg_free(c);
     if (c->mrf_host_flags) cudaFreeHost(c->mrf_host_flags);
+    if (c->images_uploaded) cudaEventDestroy(c->images_uploaded);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -150,12 +154,22 @@ int b2tex_set_views(b2tex_ctx *c, const b2tex_view *views, uint32_t K)
         c->img_off[v + 1] = c->img_off[v] + (size_t)views[v].width * views[v].height;
     }
     B2_TRY(c->rgb.alloc(3 * c->img_off[K]));
+    // deferred (one-shot entry points only: the caller's buffers stay valid until the call returns): the copies go to the
+    // copy stream and the stage that first touches pixels waits for them (wait_for_images); otherwise: done on return
+    cudaStream_t cs = c->defer_image_sync ? c->copy_stream : c->stream;
+    if (c->defer_image_sync) B2_CUDA(cudaStreamSynchronize(c->stream));   // the previous use of the image buffer is over
     for (uint32_t v = 0; v < K; ++v) {
         size_t px = (size_t)views[v].width * views[v].height;
-        B2_CUDA(cudaMemcpyAsync(c->rgb.p + 3 * c->img_off[v], views[v].rgb, 3 * px, cudaMemcpyHostToDevice, c->stream));
+        B2_CUDA(cudaMemcpyAsync(c->rgb.p + 3 * c->img_off[v], views[v].rgb, 3 * px, cudaMemcpyHostToDevice, cs));
         c->views_host[v].rgb = nullptr;
     }
-    B2_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->defer_image_sync) {
+        B2_CUDA(cudaEventRecord(c->images_uploaded, cs));
+        c->images_in_flight = true;
+    } else {
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        c->images_in_flight = false;
+    }
     c->images_prepared = false; c->prepared_data_term = -1; c->have_costs = false; c->have_seam = false;
     return B2TEX_OK;
 }
@@ -651,11 +665,16 @@ int b2tex_texture_hot_path(const float *verts, uint32_t nv, const uint32_t *face
     if (!dci) dci = &dc_local;
     if (!mi) mi = &mrf_local;
     if (!si) si = &seam_local;
+    // mesh first (small), then the images on the copy stream: BVH build, culling and the visibility rays of the data-cost
+    // stage need no pixels and run while the 1.2 GB (C3) of images are still crossing PCIe
     int rc = b2tex_set_mesh(c, verts, nv, faces, normals, nf);
+    c->defer_image_sync = true;
     if (rc == B2TEX_OK) rc = b2tex_set_views(c, views, K);
+    c->defer_image_sync = false;
     if (rc == B2TEX_OK) rc = b2tex_set_adjacency(c, adj_ptr, adj_idx);
     if (rc == B2TEX_OK) rc = b2tex_set_vertex_rings(c, vf_ptr, vf_idx, vv_ptr, vv_idx);
     if (rc == B2TEX_OK) rc = b2tex_data_costs_run(c, st, dci);
+    if (c->images_in_flight) { cudaStreamSynchronize(c->copy_stream); c->images_in_flight = false; }   // also on the error paths
     if (rc == B2TEX_OK) rc = b2tex_view_selection_run(c, mp, mi, nullptr);
     if (rc == B2TEX_OK && labels_out) rc = b2tex_labels_download(c, labels_out);
     if (rc == B2TEX_OK) rc = b2tex_seam_run(c, si);

@@ -143,6 +143,11 @@ struct b2tex_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    // one-shot entry points: the image upload runs on its own stream while the stages that need no pixels (BVH, cull,
+    // visibility rays) already run; `images_uploaded` is what the first pixel consumer waits for
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t images_uploaded = nullptr;
+    bool defer_image_sync = false, images_in_flight = false;
 
     // mesh
     uint32_t Vn = 0, F = 0;
@@ -260,6 +265,8 @@ struct ScopedTimer {
 };
 // stage entry points implemented in the individual .cu files
 int prepare_images(b2tex_ctx *c, int data_term, bool force = false);
+int prepare_views(b2tex_ctx *c, int data_term);    // camera block only (no pixel data needed)
+int wait_for_images(b2tex_ctx *c);                 // the compute stream waits for a deferred image upload
 int build_bvh(b2tex_ctx *c, bool force = false);
 int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *info);
 int data_costs_histogram(b2tex_ctx *c, float gmax);

@@ -644,7 +644,10 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     cudaStream_t s = c->stream;
     // image preparation and the BVH are part of the stage in the reference
     // (calculate_data_costs.cpp:144,157-163), so they are redone on every call
-    B2_TRY(prepare_images(c, st->data_term, true));
+    // The camera block first: BVH, culling and the visibility rays need no pixel, so with a deferred image upload
+    // (one-shot entry points) they run while the images are still on their way; the pixel work (Sobel, validity masks)
+    // follows right before k_quality, its first consumer.
+    B2_TRY(prepare_views(c, st->data_term));
     const bool vis = st->geometric_visibility_test != 0;
     if (vis) B2_TRY(build_bvh(c, true));
 
@@ -701,6 +704,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
                                                  ray_count);
         B2_KERNEL_CHECK();
     }
+    B2_TRY(prepare_images(c, st->data_term, true));   // waits for the upload if it is still in flight
     if (num_cand) {
         size_t qblocks = (num_cand + 255) / 256;
         ScopedTimer tm(c, "k_quality", 10.0 * (double)num_cand + mesh_bytes);

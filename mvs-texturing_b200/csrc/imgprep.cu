@@ -5,6 +5,7 @@
 //                        border quirk: image-border pixels are not invalidated)
 //   valid4             = AND of the 4 bilinear taps          (texture_view.cpp:264-277)
 // Integer/u8 outputs are bit-exact restatements; compiled with -fmad=false.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -130,6 +131,132 @@ __global__ void __launch_bounds__(256) k_lum_sobel_vec(const uint8_t *__restrict
     }
 }
 
+
+// ---- TMA variant: the rgb tile (+ 1 pixel halo) of a view is staged by ONE bulk tensor copy ------------------------------
+// The view set is described to the TMA unit as a 3-D tensor of 32-bit words [K][H][3 W / 4] (needs W % 16 == 0: global
+// strides are multiples of 16 bytes); a CTA asks for the box {100 words, TH3 + 2 rows, 1 view} that holds the
+// (TW3 + 2) x (TH3 + 2) pixels it needs -- rows and words outside the image arrive as zeros, which is exactly the
+// luminance the scalar kernel assigns there -- and waits on an mbarrier for the 13.6 KB to land; no thread issues a
+// global load.  Luminance is then computed four pixels per thread from 16-byte windows of the raw tile (byte
+// permutes), the Sobel sums four outputs per thread from six 32-bit words of the luminance tile with shared column
+// and row sums, and the gradient leaves as one 32-bit word per thread.  Same integer / fp32 arithmetic, bit-exact.
+constexpr int TW3 = 128, TH3 = 32;
+constexpr int BOXW3 = 100;                 // words per tile row: bytes [384 bx - 4, 384 bx + 396)
+constexpr int LUMW3 = 136;                 // luminance tile row pitch (132 pixels used)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) k_lum_sobel_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ grad_all,
+                                                       int w, int h, size_t view_stride_px)
+{
+    __shared__ __align__(128) uint32_t raw[(TH3 + 2) * BOXW3];
+    __shared__ __align__(16) uint8_t lum[(TH3 + 2) * LUMW3];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int x0 = blockIdx.x * TW3, y0 = blockIdx.y * TH3;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (TH3 + 2) * BOXW3 * 4;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&mbar)), "r"(bytes) : "memory");
+        const int c0 = (3 * x0) / 4 - 1, c1 = y0 - 1, c2 = (int)blockIdx.z;
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_addr(raw)), "l"(&tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(&mbar)) : "memory");
+    }
+    {   // every thread waits for the tile (phase 0 of the barrier)
+        uint32_t done = 0;
+        for (uint32_t spins = 0; !done; ++spins) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_addr(&mbar)) : "memory");
+            if (spins > (1u << 24)) __trap();   // a copy that never lands must not hang the device
+        }
+    }
+    // luminance, four pixels per thread: pixel q of group j sits at bytes 1 + 3 (4 j + q) .. of the row
+    for (int i = threadIdx.x; i < (TH3 + 2) * 33; i += blockDim.x) {
+        const int ly = i / 33, j = i - ly * 33;
+        const uint32_t *rw = raw + ly * BOXW3 + 3 * j;
+        const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2], w3 = rw[3];
+        uint32_t out = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int b = 1 + 3 * q;   // byte offset in the 16-byte window
+            auto byte_at = [&](int o) -> uint32_t {
+                const uint32_t word = o < 4 ? w0 : (o < 8 ? w1 : (o < 12 ? w2 : w3));
+                return (word >> (8 * (o & 3))) & 0xFFu;
+            };
+            const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn((float)byte_at(b), 0.21f), __fmul_rn((float)byte_at(b + 1), 0.72f)),
+                                                __fmul_rn((float)byte_at(b + 2), 0.07f)), 0.5f);
+            out |= ((uint32_t)(uint8_t)v) << (8 * q);
+        }
+        *reinterpret_cast<uint32_t *>(lum + ly * LUMW3 + 4 * j) = out;
+    }
+    __syncthreads();
+    // Sobel, four outputs per thread.  lum column c = image column x0 - 1 + c.
+    uint8_t *grad = grad_all + view_stride_px * blockIdx.z;
+    for (int i = threadIdx.x; i < TH3 * (TW3 / 4); i += blockDim.x) {
+        const int ly = i / (TW3 / 4), lx0 = (i - ly * (TW3 / 4)) * 4;
+        const int gy = y0 + ly, gx0 = x0 + lx0;
+        if (gy >= h || gx0 >= w) continue;
+        uint32_t t[3][2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const uint32_t *lp = reinterpret_cast<const uint32_t *>(lum + (ly + r) * LUMW3 + lx0);
+            t[r][0] = lp[0]; t[r][1] = lp[1];
+        }
+        auto px = [&](int r, int cidx) -> int { return (int)((t[r][cidx >> 2] >> (8 * (cidx & 3))) & 0xFFu); };
+        int col[6], rowt[4], rowb[4];   // column sums a + 2 d + g, row sums of the top / bottom row
+#pragma unroll
+        for (int cidx = 0; cidx < 6; ++cidx) col[cidx] = px(0, cidx) + 2 * px(1, cidx) + px(2, cidx);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            rowt[q] = px(0, q) + 2 * px(0, q + 1) + px(0, q + 2);
+            rowb[q] = px(2, q) + 2 * px(2, q + 1) + px(2, q + 2);
+        }
+        uint32_t o = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int gx = gx0 + q;
+            uint32_t out = 0;
+            if (gx < w && !(gy == 0 || gy == h - 1 || gx == 0 || gx == w - 1)) {
+                const int sx = col[q + 2] - col[q];   // (c - a) + 2 (f - d) + (k - g)
+                const int sy = rowb[q] - rowt[q];     // (g - a) + 2 (hh - b) + (k - c)
+                const int ss = sx * sx + sy * sy;     // < 2^24: exact in fp32
+                out = ss >= 255 * 255 ? 255u : (uint32_t)(int)__fsqrt_rn((float)ss);
+            }
+            o |= out << (8 * q);
+        }
+        uint8_t *dst = grad + (size_t)gy * w + gx0;
+        if (gx0 + 3 < w) *reinterpret_cast<uint32_t *>(dst) = o;   // w % 16 == 0 and gx0 % 4 == 0: aligned
+        else for (int q = 0; q < 4 && gx0 + q < w; ++q) dst[q] = (uint8_t)(o >> (8 * q));
+    }
+}
+
+// the tensor map of the rgb images of a uniform view set, or false if the layout does not qualify
+bool make_rgb_tensor_map(const uint8_t *rgb, int w, int h, uint32_t K, CUtensorMap *out)
+{
+    if (w % 16 != 0 || (((uintptr_t)rgb) & 15u) != 0 || w < 16 || h < 1) return false;
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked_up = false;
+    if (!looked_up) {
+        looked_up = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            encode = (EncodeFn)fn;
+    }
+    if (!encode) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)(3 * (size_t)w / 4), (cuuint64_t)h, (cuuint64_t)K};
+    const cuuint64_t strides[2] = {(cuuint64_t)(3 * (size_t)w), (cuuint64_t)(3 * (size_t)w * h)};   // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)BOXW3, (cuuint32_t)(TH3 + 2), 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)rgb, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 __global__ void k_corner_check(const ViewDev *views, int K, uint32_t *flags)
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -223,10 +350,51 @@ __global__ void k_valid4(const uint8_t *__restrict__ inv, uint8_t *__restrict__ 
 
 }  // namespace
 
+// the compute stream waits for a deferred image upload (b2tex_set_views on the copy stream)
+int wait_for_images(b2tex_ctx *c)
+{
+    if (c->images_in_flight) {
+        B2_CUDA(cudaStreamWaitEvent(c->stream, c->images_uploaded, 0));
+        c->images_in_flight = false;
+    }
+    return B2TEX_OK;
+}
+
+static void fill_view_block(b2tex_ctx *c, int data_term, std::vector<ViewDev> &vd)
+{
+    const uint32_t K = c->K;
+    vd.resize(K);
+    for (uint32_t v = 0; v < K; ++v) {
+        const b2tex_view &hv = c->views_host[v];
+        ViewDev &d = vd[v];
+        for (int i = 0; i < 3; ++i) { d.pos[i] = hv.pos[i]; d.dir[i] = hv.viewdir[i]; }
+        for (int i = 0; i < 9; ++i) d.proj[i] = hv.proj[i];
+        for (int i = 0; i < 12; ++i) d.w2c[i] = hv.w2c[i];
+        d.w = hv.width; d.h = hv.height;
+        d.rgb = c->rgb.p + 3 * c->img_off[v];
+        d.grad = data_term == 1 ? c->grad.p + c->img_off[v] : nullptr;
+        d.valid4 = nullptr;
+    }
+}
+
+// camera block of every view on the device (positions, matrices, image pointers): everything culling and the visibility
+// rays need; touches no pixel
+int prepare_views(b2tex_ctx *c, int data_term)
+{
+    if (!c->K) { set_error("prepare_images: no views set"); return B2TEX_ERR_ARG; }
+    if (data_term == 1) B2_TRY(c->grad.alloc(c->img_off[c->K]));
+    std::vector<ViewDev> vd;
+    fill_view_block(c, data_term, vd);
+    B2_TRY(c->views_dev.upload(vd.data(), c->K, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));   // vd is a local
+    return B2TEX_OK;
+}
+
 int prepare_images(b2tex_ctx *c, int data_term, bool force)
 {
     if (!force && c->images_prepared && c->prepared_data_term == data_term) return B2TEX_OK;
     if (!c->K) { set_error("prepare_images: no views set"); return B2TEX_ERR_ARG; }
+    B2_TRY(wait_for_images(c));
     cudaStream_t s = c->stream;
     const uint32_t K = c->K;
     size_t total_px = c->img_off[K];
@@ -239,7 +407,15 @@ int prepare_images(b2tex_ctx *c, int data_term, bool force)
             uniform = uniform && c->views_host[v].width == c->views_host[0].width
                 && c->views_host[v].height == c->views_host[0].height;
         static const bool scalar_sobel = getenv("B2TEX_SCALAR_SOBEL") != nullptr;
-        if (uniform && K <= 65535u && !scalar_sobel) {  // one launch for all views (blockIdx.z = view)
+        static const bool no_tma = getenv("B2TEX_NO_TMA") != nullptr;
+        CUtensorMap tmap;
+        if (uniform && K <= 65535u && !scalar_sobel && !no_tma &&
+            make_rgb_tensor_map(c->rgb.p, c->views_host[0].width, c->views_host[0].height, K, &tmap)) {
+            // image tiles staged by the TMA unit (one bulk tensor copy per CTA), all views in one launch
+            int w = c->views_host[0].width, h = c->views_host[0].height;
+            dim3 grid((w + TW3 - 1) / TW3, (h + TH3 - 1) / TH3, K);
+            B2_LAUNCH k_lum_sobel_tma<<<grid, 256, 0, s>>>(tmap, c->grad.p, w, h, (size_t)w * h);
+        } else if (uniform && K <= 65535u && !scalar_sobel) {  // one launch for all views (blockIdx.z = view)
             int w = c->views_host[0].width, h = c->views_host[0].height;
             dim3 grid((w + TW2 - 1) / TW2, (h + TH2 - 1) / TH2, K);
             B2_LAUNCH k_lum_sobel_vec<<<grid, 256, 0, s>>>(c->rgb.p, c->grad.p, w, h, (size_t)w * h, c->rgb.p,
@@ -255,18 +431,8 @@ int prepare_images(b2tex_ctx *c, int data_term, bool force)
     }
 
     // validity: only views with a zero-sum corner can have invalid pixels at all
-    std::vector<ViewDev> vd(K);
-    for (uint32_t v = 0; v < K; ++v) {
-        const b2tex_view &hv = c->views_host[v];
-        ViewDev &d = vd[v];
-        for (int i = 0; i < 3; ++i) { d.pos[i] = hv.pos[i]; d.dir[i] = hv.viewdir[i]; }
-        for (int i = 0; i < 9; ++i) d.proj[i] = hv.proj[i];
-        for (int i = 0; i < 12; ++i) d.w2c[i] = hv.w2c[i];
-        d.w = hv.width; d.h = hv.height;
-        d.rgb = c->rgb.p + 3 * c->img_off[v];
-        d.grad = data_term == 1 ? c->grad.p + c->img_off[v] : nullptr;
-        d.valid4 = nullptr;
-    }
+    std::vector<ViewDev> vd;
+    fill_view_block(c, data_term, vd);
     B2_TRY(c->views_dev.upload(vd.data(), K, s));
     B2_TRY(c->scalars.alloc(std::max<size_t>(K + 64, 256)));
     B2_LAUNCH k_corner_check<<<(K + 127) / 128, 128, 0, s>>>(c->views_dev.p, (int)K, c->scalars.p + 64);

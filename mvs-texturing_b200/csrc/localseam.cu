@@ -21,6 +21,8 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
+#include <memory>
+
 #include "patches.cuh"
 
 namespace cg = cooperative_groups;
@@ -468,6 +470,7 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
     if (P >= 0xFFFFFFFFull) { set_error("local seam leveling: more than 2^32 patch pixels"); return B2TEX_ERR_LIMITS; }
 
     // ---- host bookkeeping: vertex projections, seam edges and their projections ----
+    std::unique_ptr<ScopedTimer> t_host(new ScopedTimer(c, "ls.download+host_bookkeeping"));
     std::vector<float> tex(6 * (size_t)(T ? T : 1));
     std::vector<uint32_t> labels(F), adj_ptr((size_t)F + 1), mesh_faces(3 * (size_t)F);
     B2_TRY(ps.tex.download(tex.data(), 6 * (size_t)T, s));
@@ -492,7 +495,9 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
     for (uint32_t v = 0; v < NV; ++v)
         for (uint32_t k = sl.vert_info[2 * (size_t)v]; k < sl.vert_info[2 * (size_t)v] + sl.vert_info[2 * (size_t)v + 1]; ++k) vproj_vert[k] = v;
 
+    t_host.reset();
     // ---- colours, stamping ----
+    std::unique_ptr<ScopedTimer> t_col(new ScopedTimer(c, "ls.upload+colors+stamp"));
     DevBuf<uint32_t> &d_sample_edge = ps.sample_edge, &d_edge_info = ps.edge_info, &d_vert_info = ps.vert_info;
     DevBuf<uint32_t> &d_proj = ps.line_info, &d_vproj = ps.pixw_info;   // [proj_patch | proj_edge], [vproj_patch | vproj_vert]
     std::vector<uint32_t> pack(2 * (size_t)(NL ? NL : 1)), vpack(2 * (size_t)(NVP ? NVP : 1));
@@ -522,14 +527,18 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
                                                                          ps.pix_off.p, ps.key.p);
         B2_LAUNCH k_stamp_apply<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.key.p, d_vproj.p + NVP, ps.vert_color.p, d_proj.p + NL, ps.edge_proj.p,
                                          d_edge_info.p, ps.edge_color.p, ps.img.p, ps.blend.p);
+        t_col.reset();
         // ---- blending mask ----
+        ScopedTimer t_mask(c, "ls.blending_mask");
         B2_LAUNCH k_layer_init<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.valid.p, ps.layer.p);
         for (int it = 1; it <= STRIP_SIZE; ++it) B2_LAUNCH k_layer_step<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.valid.p, ps.layer.p, it);
         B2_LAUNCH k_sanitize<<<pb, 256, 0, s>>>(P, NP, ps.pix_off.p, ps.desc.p, ps.blend.p);
         B2_LAUNCH k_mask_final<<<pb, 256, 0, s>>>(P, ps.valid.p, ps.layer.p, ps.blend.p);
         B2_KERNEL_CHECK();
     }
+    t_col.reset();
     // ---- Poisson blending ----
+    ScopedTimer t_poi(c, "ls.poisson");
     uint32_t n = 0;
     uint32_t st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (P) {

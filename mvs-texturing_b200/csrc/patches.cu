@@ -19,6 +19,8 @@
 // result is independent of the execution order and identical to the sequential loop.
 #include <math.h>
 
+#include <memory>
+
 #include "patches.cuh"
 
 namespace b2 {
@@ -271,6 +273,7 @@ int patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info)
     ScopedTimer tm(c, "texture_patches");
 
     // ---- components on the host (graph traversal, order defining) ----
+    std::unique_ptr<ScopedTimer> t_host(new ScopedTimer(c, "tp.download+components"));
     const uint32_t F = c->F;
     std::vector<uint32_t> labels(F), adj_ptr((size_t)F + 1);
     B2_TRY(c->labels.download(labels.data(), F, s));
@@ -292,7 +295,9 @@ int patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info)
         comp_wh[2 * (size_t)k + 1] = (uint32_t)c->views_host[comps[k].label - 1].height;
     }
 
+    t_host.reset();
     // ---- projection + integer bounds per component ----
+    std::unique_ptr<ScopedTimer> t_proj(new ScopedTimer(c, "tp.upload+project+bbox"));
     B2_TRY(ps.comp_faces.upload(comp_faces.data(), T, s));
     B2_TRY(ps.slot_comp0.upload(slot_comp0.data(), T, s));
     B2_TRY(ps.comp_wh.upload(comp_wh.data(), 2 * (size_t)C, s));
@@ -306,7 +311,9 @@ int patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info)
     B2_TRY(ps.comp_bbox.download(bbox.data(), 4 * (size_t)C, s));
     B2_CUDA(cudaStreamSynchronize(s));
 
+    t_proj.reset();
     // ---- candidate merge on the host, then the per-slot / per-pixel work on the device ----
+    std::unique_ptr<ScopedTimer> t_plan(new ScopedTimer(c, "tp.merge_plan+upload"));
     plan_patches(comps, bbox.data(), ps.plan);
     const PatchPlan &pl = ps.plan;
     const uint32_t NP = pl.num_patches();
@@ -329,6 +336,8 @@ int patches_run(b2tex_ctx *c, int apply_adjust, b2tex_patch_info *info)
     B2_TRY(ps.key.alloc(P));
     B2_TRY(ps.valid.alloc(P));
     B2_TRY(ps.blend.alloc(P));
+    t_plan.reset();
+    ScopedTimer t_px(c, "tp.texcoords+crop+raster+apply");
     if (T) {
         B2_LAUNCH k_texcoords<<<(T + 255) / 256, 256, 0, s>>>(T, ps.slot_src.p, ps.slot_comp.p, ps.comp_min.p, ps.comp_chain.p, ps.chain.p,
                                                     ps.px.p, ps.tex.p);

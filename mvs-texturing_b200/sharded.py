@@ -329,13 +329,26 @@ def e2e_host_path(b2, torch, s, adj, rings, steps=1, warmup=1):
         if i >= warmup:
             ftimes.append(time.perf_counter() - t0)
     tf = sum(ftimes) / len(ftimes)
+    # the same call on PAGEABLE host buffers (what an unmodified texrecon holds: mve images live in ordinary heap memory)
+    ptimes = []
+    for i in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        b2.texture_hot_path(s, adj, rings)
+        torch.cuda.synchronize()
+        if i >= 1:
+            ptimes.append(time.perf_counter() - t0)
+    tp = sum(ptimes) / len(ptimes)
     mesh_b = sp.verts.nbytes + sp.faces.nbytes + sp.face_normals.nbytes
     return {"value": s.num_faces / tf, "unit": "faces/s",
             "h2d_bytes_per_step": int(mesh_b + sp.images.nbytes + ap.nbytes + ai.nbytes + sum(a.nbytes for a in pr)),
             "d2h_bytes_per_step": int(r["labels"].nbytes + r["row_ptr"].nbytes + r["row_label"].nbytes + r["x"].nbytes),
             "ms_per_step": 1e3 * tf,
+            "pageable_host": {"value": s.num_faces / tp, "unit": "faces/s", "ms_per_step": 1e3 * tp,
+                              "note": "same call, host buffers in ordinary (pageable) memory"},
             "path": "b2tex_texture_hot_path: pinned host mesh/images/graph in, labels + adjust values out "
-                    "(what texrecon does with --no_intermediate_results)",
+                    "(what texrecon does with --no_intermediate_results); the image upload runs on a copy stream under "
+                    "the BVH build, culling and visibility rays",
             "three_call_path": three}
     return {"value": s.num_faces / t, "unit": "faces/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t, "stage_ms_per_step": stages,

@@ -35,6 +35,12 @@ extern "C" {
 
 void emul_set_schedule(unsigned long long seed) { emul::set_schedule(seed); }   // 0 = round robin
 
+// fault injection: rank `r` never enters the kernel (a peer that died); the others must come back with barrier timeouts
+// instead of hanging.  spin = polls before a waiter gives up (small here: the emulator is slow).
+static int g_dead_rank = -1;
+static unsigned long long g_spin_limit = 1000000000ull;
+void emul_set_dead_rank(int r, unsigned long long spin) { g_dead_rank = r; g_spin_limit = spin ? spin : 1000000000ull; }
+
 void emul_seam_mg_free(void *p) { free(p); }
 
 // x_out: [ranks][R][3] -- the complete solution as every rank ends up with it; status_out: [ranks][16]
@@ -105,7 +111,7 @@ int emul_seam_mg(const float *verts, uint32_t Vn, const uint32_t *faces, uint32_
         p.r = rr[k].data(); p.t = tt[k].data(); p.blockpart = bp[k].data(); p.status = st[k].data();
         for (uint32_t j = 0; j < (uint32_t)MG_MAX_RANKS; ++j) p.peer[j] = j < ranks ? (void *)blocks[j].data() : nullptr;
         p.timing = 0u; p.max_iters = 1000u; p.tol = 0.0001f; p.epoch0 = 0xFFFFFFF0u;   // start close to the wrap-around of the epoch counter
-        p.spin_limit = 1000000000ull;
+        p.spin_limit = g_spin_limit;
         if (p.r1 > p.r0)
             emul::launch_serial((p.r1 - p.r0 + 255) / 256, 256, [&] { k_pcg_mg_dest(R, p.r0, p.r1, k, ranks, csr_ptr.data(), csr_enc.data(), dest[k].data(), imark[k].data()); });
         emul::launch_serial((R + 255) / 256, 256, [&] { k_pcg_mg_imports(R, imark[k].data(), imp[k].data(), &nimp[k]); });
@@ -115,7 +121,7 @@ int emul_seam_mg(const float *verts, uint32_t Vn, const uint32_t *faces, uint32_
     st[0][15] = halo_rows;   // reported through the status words of rank 0
     for (uint32_t k = 0; k < ranks; ++k)      // flags start at epoch0 ("everybody reached the epochs used so far")
         for (uint32_t j = 0; j < (uint32_t)MG_MAX_RANKS; ++j) mg_carve(blocks[k].data(), R).flag[j] = 0xFFFFFFF0u;
-    if (!emul::launch_ranks(ranks, grid, MG_THREADS, [&](unsigned rank) { k_pcg_mg(q[rank]); })) return -1;
+    if (!emul::launch_ranks(ranks, grid, MG_THREADS, [&](unsigned rank) { if ((int)rank != g_dead_rank) k_pcg_mg(q[rank]); })) return -1;
     for (uint32_t k = 0; k < ranks; ++k) {
         const float *xs = mg_carve(blocks[k].data(), R).x;
         for (uint32_t r = 0; r < R; ++r)

@@ -592,6 +592,33 @@ def test_device_multi_gpu_seam_solve(emul, orc, scene_mod, get_scene, ranks, gri
     assert np.linalg.norm(x[0] - o["x"]) / np.linalg.norm(o["x"]) < 1e-4
 
 
+def test_device_multi_gpu_seam_solve_survives_a_dead_peer(emul, orc, scene_mod, get_scene):
+    """A peer that never arrives (process died, GPU fell off the bus) must not hang the healthy ranks: every wait in k_pcg_mg
+    has a poll limit, the verdict is taken once per block, and after the first timeout nobody waits any more.  Rank 1 of 2 never
+    enters the kernel; rank 0 (two blocks) must leave it with barrier timeouts recorded in status[7]."""
+    s = get_scene("tiny")
+    adj = scene_mod.face_adjacency(s.faces)
+    rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
+    dc = orc.data_costs(s)
+    labels = orc.view_selection(adj[0], adj[1], dc["face_ptr"], dc["view"], dc["cost"], threads=1)["labels"]
+    views, keep = orc.make_views(s)
+    L = emul["emul_seam_mg"]
+    ranks, grid = 2, 2
+    R, xp = C.c_uint32(), C.c_void_p()
+    status = np.zeros(16 * ranks, np.uint32)
+    L.emul_set_dead_rank(C.c_int(1), C.c_uint64(300))
+    try:
+        rc = L.emul_seam_mg(orc._p(s.verts), C.c_uint32(s.verts.shape[0]), orc._p(s.faces), C.c_uint32(s.num_faces), orc._p(rings[0]),
+                            orc._p(rings[1]), orc._p(rings[2]), orc._p(rings[3]), orc._p(np.ascontiguousarray(labels, np.uint32)), views,
+                            C.c_uint32(s.num_views), C.c_uint32(ranks), C.c_uint32(grid), C.byref(R), C.byref(xp), orc._p(status))
+    finally:
+        L.emul_set_dead_rank(C.c_int(-1), C.c_uint64(0))
+    assert rc == 0, "the healthy rank never left the kernel"
+    L.emul_seam_mg_free(xp)
+    st = status.reshape(ranks, 16)
+    assert st[0, 7] > 0          # barrier timeouts reported (seam_mg_solve turns them into B2TEX_ERR_CUDA)
+
+
 def test_device_local_seam_leveling_without_global_leveling(emul, orc, local_inputs):
     """texrecon --skip_global_seam_leveling: zero-offset adjust_colors pass (texrecon.cpp:174-183), then local seam leveling on
     the raw patch colours (larger seam differences to blend away).  Against the reference TUs when available, else the oracle."""

@@ -33,6 +33,27 @@ def test_data_costs_bit_exact(b2, get_scene, oracle_pipeline, name):
     c.close()
 
 
+@pytest.mark.parametrize("name", ["tiny", "C2s", "occ2"])
+def test_gradient_images_bit_exact(b2, get_scene, orc, name):
+    """Every pixel of every gradient-magnitude image (texture_view.cpp:102-107) against the oracle.  The scene widths are
+    multiples of 16, so the tiles are staged by the TMA unit (k_lum_sobel_tma, one bulk tensor copy per CTA): 160x120 and
+    480x270 have partial tiles on both axes, 640x480 is 5 x 15 full tiles."""
+    import torch
+    from importlib import import_module
+    s = get_scene(name)
+    c = _ctx(b2, s)
+    c.data_costs_run()
+    ptr, n = c.device_ptr("grad")
+    K, H, W = s.num_views, s.height, s.width
+    assert n >= K * H * W
+    par = import_module("mvs-texturing_b200.sharded")
+    g = torch.as_tensor(par._DevArray(ptr, K * H * W, "|u1"), device="cuda").cpu().numpy().reshape(K, H, W)
+    c.close()
+    for v in range(K):
+        ref = orc.gradient_magnitude(s.images[v])
+        assert np.array_equal(g[v], ref), (name, v, int((g[v] != ref).sum()))
+
+
 def test_data_costs_area_term_and_no_visibility(b2, get_scene, orc):
     s = get_scene("small")
     for data_term, vis in [(0, True), (1, False), (0, False)]:

@@ -1,0 +1,87 @@
+"""Solver quality study (CPU, oracle): energy of the forest block-coordinate-descent solver at its stop rule and after 200
+iterations, against two lower bounds of the optimum of the SAME model (view_selection.cpp:26-90: unaries = data costs, unit
+Potts edges between seen adjacent faces, unseen faces cost 1):
+  LB_unary : sum of the cheapest label of every face (all pairwise terms >= 0)
+  LB_tree  : exact optimum (min-sum DP) of the model with only the edges of a BFS spanning forest kept -- dropping
+             non-negative terms can only lower the minimum, so it bounds the optimum of the full model from below.
+mapMAP itself is absent, so this is the yardstick for "how far from optimal can the labeling be".
+
+    python tools/mrf_quality.py C1 C1d C2s C3s          # writes profiles/r02_mrf_quality.md
+"""
+import importlib, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import oracle as O
+scene = importlib.import_module("mvs-texturing_b200.scene")
+
+
+def tree_lower_bound(ap, ai, fp, view, cost):
+    F = len(fp) - 1
+    n = np.diff(fp).astype(np.int64)
+    seen = n > 0
+    parent = np.full(F, -1, np.int64)
+    order = []
+    visited = ~seen            # unseen faces carry no edges: constant cost 1 each
+    for root in range(F):
+        if visited[root]:
+            continue
+        visited[root] = True
+        q = [root]
+        while q:
+            nq = []
+            for v in q:
+                order.append(v)
+                for w in ai[ap[v]:ap[v + 1]]:
+                    if not visited[w]:
+                        visited[w] = True; parent[w] = v; nq.append(w)
+            q = nq
+    h = [None] * F
+    total = float((~seen).sum())
+    for v in order:
+        h[v] = cost[fp[v]:fp[v + 1]].astype(np.float64).copy()
+    for v in reversed(order):   # children before parents (BFS order reversed)
+        p = parent[v]
+        hv = h[v]
+        hmin = hv.min()
+        if p < 0:
+            total += hmin
+            continue
+        lv, lp = view[fp[v]:fp[v + 1]], view[fp[p]:fp[p + 1]]
+        msg = np.full(len(lp), hmin + 1.0)
+        idx = np.searchsorted(lv, lp)
+        ok = (idx < len(lv))
+        ok[ok] &= lv[idx[ok]] == lp[ok]
+        msg[ok] = np.minimum(hv[idx[ok]], hmin + 1.0)
+        h[p] = h[p] + msg
+        h[v] = None
+    return total
+
+
+def main(names):
+    rows = []
+    for name in names:
+        s = scene.config(name)
+        ap, ai = scene.face_adjacency(s.faces)
+        o = O.data_costs(s)
+        fp, view, cost = o["face_ptr"], o["view"], o["cost"]
+        t0 = time.time()
+        m = O.view_selection(ap, ai, fp, view, cost)
+        t1 = time.time()
+        m200 = O.view_selection(ap, ai, fp, view, cost, max_iterations=200, window=10 ** 6)
+        n = np.diff(fp)
+        lb_unary = float(sum(cost[fp[v]:fp[v + 1]].min() if n[v] else 1.0 for v in range(len(n))))
+        lb_tree = tree_lower_bound(ap, ai, fp, view, cost)
+        rows.append((name, s.num_faces, m["energy_initial"], m["iterations"], m["energy"], m200["energy"], lb_unary, lb_tree))
+        print(rows[-1], f"({t1 - t0:.1f}s)", flush=True)
+    out = ["# MRF solver quality (oracle = CUDA path bit for bit; `python tools/mrf_quality.py`)", "",
+           "| scene | faces | E arg-min unaries | stop rule: iterations | E at the stop rule | E after 200 iterations | LB unaries | LB spanning forest | (E_stop - LB_tree) / LB_tree | (E_stop - E_200) / E_200 |",
+           "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
+    for r in rows:
+        out.append(f"| {r[0]} | {r[1]} | {r[2]:.1f} | {r[3]} | {r[4]:.1f} | {r[5]:.1f} | {r[6]:.1f} | {r[7]:.1f} | {100 * (r[4] - r[7]) / r[7]:.2f} % | {100 * (r[4] - r[5]) / r[5]:.2f} % |")
+    out += ["", "LB spanning forest keeps F - 1 of the ~1.5 F edges, so the true optimum lies between it and E after 200 iterations."]
+    open(os.path.join(ROOT, "profiles", "r02_mrf_quality.md"), "w").write("\n".join(out) + "\n")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or ["C1", "C1d", "C2s", "C3s"])
