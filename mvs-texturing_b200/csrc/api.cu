@@ -153,6 +153,16 @@ int b2tex_set_views(b2tex_ctx *c, const b2tex_view *views, uint32_t K)
         if (views[v].width < 2 || views[v].height < 2 || !views[v].rgb) { set_error("view %u: bad image", v); return B2TEX_ERR_ARG; }
         c->img_off[v + 1] = c->img_off[v] + (size_t)views[v].width * views[v].height;
     }
+    // a view with a zero-sum corner pixel gets a validity mask (texture_view.cpp:42-94), which the cull already reads
+    // (TextureView::inside -> valid_pixel): such scenes need their pixels first.  Four pixels per view, read on the host.
+    c->any_corner_flag = false;
+    for (uint32_t v = 0; v < K; ++v) {
+        const uint8_t *img = (const uint8_t *)views[v].rgb;
+        const size_t w = (size_t)views[v].width, h = (size_t)views[v].height;
+        const size_t corner[4] = {0, w - 1, (h - 1) * w, (h - 1) * w + w - 1};
+        for (size_t o : corner)
+            if ((int)img[3 * o] + img[3 * o + 1] + img[3 * o + 2] == 0) c->any_corner_flag = true;
+    }
     B2_TRY(c->rgb.alloc(3 * c->img_off[K]));
     // deferred (one-shot entry points only: the caller's buffers stay valid until the call returns): the copies go to the
     // copy stream and the stage that first touches pixels waits for them (wait_for_images); otherwise: done on return

@@ -145,9 +145,11 @@ struct b2tex_ctx {
     cudaStream_t stream = nullptr;
     // one-shot entry points: the image upload runs on its own stream while the stages that need no pixels (BVH, cull,
     // visibility rays) already run; `images_uploaded` is what the first pixel consumer waits for
+    b2::DevBuf<uint8_t> tmap_dev;   // the TMA descriptor of the rgb images (128 B) + a timeout counter
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t images_uploaded = nullptr;
     bool defer_image_sync = false, images_in_flight = false;
+    bool any_corner_flag = false;   // some view has a zero-sum corner pixel: validity masks exist and the cull reads them
 
     // mesh
     uint32_t Vn = 0, F = 0;

@@ -647,7 +647,10 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
     // The camera block first: BVH, culling and the visibility rays need no pixel, so with a deferred image upload
     // (one-shot entry points) they run while the images are still on their way; the pixel work (Sobel, validity masks)
     // follows right before k_quality, its first consumer.
-    B2_TRY(prepare_views(c, st->data_term));
+    // (Views with a validity mask -- a zero-sum corner pixel -- are the exception: the cull reads the mask, so there the pixel
+    // work comes first, as in the reference.)
+    if (c->any_corner_flag) B2_TRY(prepare_images(c, st->data_term, true));
+    else B2_TRY(prepare_views(c, st->data_term));
     const bool vis = st->geometric_visibility_test != 0;
     if (vis) B2_TRY(build_bvh(c, true));
 
@@ -704,7 +707,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
                                                  ray_count);
         B2_KERNEL_CHECK();
     }
-    B2_TRY(prepare_images(c, st->data_term, true));   // waits for the upload if it is still in flight
+    if (!c->any_corner_flag) B2_TRY(prepare_images(c, st->data_term, true));   // waits for the upload if it is still in flight
     if (num_cand) {
         size_t qblocks = (num_cand + 255) / 256;
         ScopedTimer tm(c, "k_quality", 10.0 * (double)num_cand + mesh_bytes);

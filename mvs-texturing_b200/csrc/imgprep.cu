@@ -135,59 +135,77 @@ __global__ void __launch_bounds__(256) k_lum_sobel_vec(const uint8_t *__restrict
 // ---- TMA variant: the rgb tile (+ 1 pixel halo) of a view is staged by ONE bulk tensor copy ------------------------------
 // The view set is described to the TMA unit as a 3-D tensor of 32-bit words [K][H][3 W / 4] (needs W % 16 == 0: global
 // strides are multiples of 16 bytes); a CTA asks for the box {100 words, TH3 + 2 rows, 1 view} that holds the
-// (TW3 + 2) x (TH3 + 2) pixels it needs -- rows and words outside the image arrive as zeros, which is exactly the
-// luminance the scalar kernel assigns there -- and waits on an mbarrier for the 13.6 KB to land; no thread issues a
-// global load.  Luminance is then computed four pixels per thread from 16-byte windows of the raw tile (byte
-// permutes), the Sobel sums four outputs per thread from six 32-bit words of the luminance tile with shared column
+// (TW3 + 2) x (TH3 + 2) pixels it needs and waits on an mbarrier for the 13.6 KB to land; no thread issues a global
+// load.  Boxes that reach outside the tensor are NOT used: with 32-bit elements the B200 raises "illegal instruction"
+// for them (measured, profiles/r02_tma_matrix.txt; 8-bit elements would zero-fill but are limited to 256-byte rows), so
+// the box of an edge tile is shifted back inside the image and the out-of-image pixels get luminance 0 explicitly, which
+// is what the scalar kernel assigns there.  Luminance is then computed four pixels per thread from 16-byte windows of
+// the raw tile, the Sobel sums four outputs per thread from six 32-bit words of the luminance tile with shared column
 // and row sums, and the gradient leaves as one 32-bit word per thread.  Same integer / fp32 arithmetic, bit-exact.
 constexpr int TW3 = 128, TH3 = 32;
-constexpr int BOXW3 = 100;                 // words per tile row: bytes [384 bx - 4, 384 bx + 396)
+constexpr int BOXW3 = 100;                 // words per tile row: bytes [384 bx - 4, 384 bx + 396) before the shift
 constexpr int LUMW3 = 136;                 // luminance tile row pitch (132 pixels used)
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(256) k_lum_sobel_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ grad_all,
-                                                       int w, int h, size_t view_stride_px)
+__device__ __forceinline__ void lum_sobel_tma_body(const CUtensorMap *tmap, uint8_t *__restrict__ grad_all,
+                                                   int w, int h, size_t view_stride_px, uint32_t *timeouts)
 {
     __shared__ __align__(128) uint32_t raw[(TH3 + 2) * BOXW3];
     __shared__ __align__(16) uint8_t lum[(TH3 + 2) * LUMW3];
     __shared__ __align__(8) unsigned long long mbar;
     const int x0 = blockIdx.x * TW3, y0 = blockIdx.y * TH3;
+    // wanted box start (words, rows) and the start actually used: shifted so that the box lies inside the tensor
+    const int c0 = (3 * x0) / 4 - 1, c1 = y0 - 1;
+    const int s0 = min(max(c0, 0), 3 * w / 4 - BOXW3), s1 = min(max(c1, 0), h - (TH3 + 2));
+    const int dx = c0 - s0, dy = c1 - s1;   // word / row of the wanted box inside the staged one
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the initialised barrier as the async proxy (TMA) sees it
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t bytes = (TH3 + 2) * BOXW3 * 4;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&mbar)), "r"(bytes) : "memory");
-        const int c0 = (3 * x0) / 4 - 1, c1 = y0 - 1, c2 = (int)blockIdx.z;
+        const int c2 = (int)blockIdx.z;
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                     ::"r"(smem_addr(raw)), "l"(&tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(&mbar)) : "memory");
+                     ::"r"(smem_addr(raw)), "l"(tmap), "r"(s0), "r"(s1), "r"(c2), "r"(smem_addr(&mbar)) : "memory");
     }
     {   // every thread waits for the tile (phase 0 of the barrier)
         uint32_t done = 0;
         for (uint32_t spins = 0; !done; ++spins) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                          : "=r"(done) : "r"(smem_addr(&mbar)) : "memory");
-            if (spins > (1u << 24)) __trap();   // a copy that never lands must not hang the device
+            if (spins > (1u << 22)) break;   // a copy that never lands must not hang the device
+        }
+        if (!done) {   // reported by the host as an error; nothing is written
+            if (threadIdx.x == 0) atomicAdd(timeouts, 1u);
+            return;
         }
     }
-    // luminance, four pixels per thread: pixel q of group j sits at bytes 1 + 3 (4 j + q) .. of the row
+    // luminance, four pixels per thread: pixel q of group j sits at bytes 1 + 3 (4 j + q) .. of the wanted row
     for (int i = threadIdx.x; i < (TH3 + 2) * 33; i += blockDim.x) {
         const int ly = i / 33, j = i - ly * 33;
-        const uint32_t *rw = raw + ly * BOXW3 + 3 * j;
-        const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2], w3 = rw[3];
+        const int gy = y0 - 1 + ly, r = ly + dy;   // image row, row in the staged box
         uint32_t out = 0;
+        if (gy >= 0 && gy < h) {
+            const uint32_t *rw = raw + r * BOXW3;
+            const int wi = 3 * j + dx;             // words wi .. wi + 3 of the staged row; clamped where no image pixel lives
+            const uint32_t w0 = rw[min(max(wi, 0), BOXW3 - 1)], w1 = rw[min(max(wi + 1, 0), BOXW3 - 1)],
+                           w2 = rw[min(max(wi + 2, 0), BOXW3 - 1)], w3 = rw[min(max(wi + 3, 0), BOXW3 - 1)];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int b = 1 + 3 * q;   // byte offset in the 16-byte window
-            auto byte_at = [&](int o) -> uint32_t {
-                const uint32_t word = o < 4 ? w0 : (o < 8 ? w1 : (o < 12 ? w2 : w3));
-                return (word >> (8 * (o & 3))) & 0xFFu;
-            };
-            const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn((float)byte_at(b), 0.21f), __fmul_rn((float)byte_at(b + 1), 0.72f)),
-                                                __fmul_rn((float)byte_at(b + 2), 0.07f)), 0.5f);
-            out |= ((uint32_t)(uint8_t)v) << (8 * q);
+            for (int q = 0; q < 4; ++q) {
+                const int gx = x0 - 1 + 4 * j + q;
+                if (gx < 0 || gx >= w) continue;   // luminance 0 outside the image
+                const int b = 1 + 3 * q;           // byte offset in the 16-byte window
+                auto byte_at = [&](int o) -> uint32_t {
+                    const uint32_t word = o < 4 ? w0 : (o < 8 ? w1 : (o < 12 ? w2 : w3));
+                    return (word >> (8 * (o & 3))) & 0xFFu;
+                };
+                const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn((float)byte_at(b), 0.21f), __fmul_rn((float)byte_at(b + 1), 0.72f)),
+                                                    __fmul_rn((float)byte_at(b + 2), 0.07f)), 0.5f);
+                out |= ((uint32_t)(uint8_t)v) << (8 * q);
+            }
         }
         *reinterpret_cast<uint32_t *>(lum + ly * LUMW3 + 4 * j) = out;
     }
@@ -232,10 +250,23 @@ __global__ void __launch_bounds__(256) k_lum_sobel_tma(const __grid_constant__ C
     }
 }
 
+// the descriptor either in global memory or (B2TEX_TMA_MODE=2) as a __grid_constant__ kernel parameter
+__global__ void __launch_bounds__(256) k_lum_sobel_tma(const CUtensorMap *__restrict__ tmap, uint8_t *__restrict__ grad_all,
+                                                       int w, int h, size_t view_stride_px, uint32_t *timeouts)
+{
+    lum_sobel_tma_body(tmap, grad_all, w, h, view_stride_px, timeouts);
+}
+__global__ void __launch_bounds__(256) k_lum_sobel_tma_param(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ grad_all,
+                                                             int w, int h, size_t view_stride_px, uint32_t *timeouts)
+{
+    lum_sobel_tma_body(&tmap, grad_all, w, h, view_stride_px, timeouts);
+}
+
 // the tensor map of the rgb images of a uniform view set, or false if the layout does not qualify
 bool make_rgb_tensor_map(const uint8_t *rgb, int w, int h, uint32_t K, CUtensorMap *out)
 {
-    if (w % 16 != 0 || (((uintptr_t)rgb) & 15u) != 0 || w < 16 || h < 1) return false;
+    // the box of an edge tile is shifted back inside the image: the image must be at least one box wide and high
+    if (w % 16 != 0 || (((uintptr_t)rgb) & 15u) != 0 || 3 * w / 4 < BOXW3 || h < TH3 + 2) return false;
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -407,14 +438,33 @@ int prepare_images(b2tex_ctx *c, int data_term, bool force)
             uniform = uniform && c->views_host[v].width == c->views_host[0].width
                 && c->views_host[v].height == c->views_host[0].height;
         static const bool scalar_sobel = getenv("B2TEX_SCALAR_SOBEL") != nullptr;
-        static const bool no_tma = getenv("B2TEX_NO_TMA") != nullptr;
-        CUtensorMap tmap;
-        if (uniform && K <= 65535u && !scalar_sobel && !no_tma &&
+        // B2TEX_TMA=0 switches the TMA-staged kernel off (diagnostic)
+        static const bool use_tma = !(getenv("B2TEX_TMA") && atoi(getenv("B2TEX_TMA")) == 0) && getenv("B2TEX_NO_TMA") == nullptr;
+        alignas(64) CUtensorMap tmap;
+        if (uniform && K <= 65535u && !scalar_sobel && use_tma &&
             make_rgb_tensor_map(c->rgb.p, c->views_host[0].width, c->views_host[0].height, K, &tmap)) {
-            // image tiles staged by the TMA unit (one bulk tensor copy per CTA), all views in one launch
+            // image tiles staged by the TMA unit (one bulk tensor copy per CTA), all views in one launch.  The 128-byte
+            // descriptor lives in global memory (64-byte aligned), next to a counter of copies that never arrived.
             int w = c->views_host[0].width, h = c->views_host[0].height;
+            B2_TRY(c->tmap_dev.alloc(256));
+            B2_CUDA(cudaMemcpyAsync(c->tmap_dev.p, &tmap, sizeof(tmap), cudaMemcpyHostToDevice, s));
+            B2_CUDA(cudaMemsetAsync(c->tmap_dev.p + 128, 0, 4, s));
+            B2_CUDA(cudaStreamSynchronize(s));   // tmap is a local
             dim3 grid((w + TW3 - 1) / TW3, (h + TH3 - 1) / TH3, K);
-            B2_LAUNCH k_lum_sobel_tma<<<grid, 256, 0, s>>>(tmap, c->grad.p, w, h, (size_t)w * h);
+            static const int tma_mode = getenv("B2TEX_TMA_MODE") ? atoi(getenv("B2TEX_TMA_MODE")) : 1;
+            if (tma_mode == 2)
+                B2_LAUNCH k_lum_sobel_tma_param<<<grid, 256, 0, s>>>(tmap, c->grad.p, w, h, (size_t)w * h, reinterpret_cast<uint32_t *>(c->tmap_dev.p + 128));
+            else
+                B2_LAUNCH k_lum_sobel_tma<<<grid, 256, 0, s>>>(reinterpret_cast<const CUtensorMap *>(c->tmap_dev.p), c->grad.p, w, h, (size_t)w * h,
+                                                     reinterpret_cast<uint32_t *>(c->tmap_dev.p + 128));
+            {
+                cudaError_t le = cudaGetLastError();
+                if (le != cudaSuccess) { set_error("k_lum_sobel_tma launch: %s", cudaGetErrorString(le)); return B2TEX_ERR_CUDA; }
+            }
+            uint32_t timeouts = 0;
+            B2_CUDA(cudaMemcpyAsync(&timeouts, c->tmap_dev.p + 128, 4, cudaMemcpyDeviceToHost, s));
+            B2_CUDA(cudaStreamSynchronize(s));
+            if (timeouts) { set_error("k_lum_sobel_tma: %u tile copies never arrived", timeouts); return B2TEX_ERR_CUDA; }
         } else if (uniform && K <= 65535u && !scalar_sobel) {  // one launch for all views (blockIdx.z = view)
             int w = c->views_host[0].width, h = c->views_host[0].height;
             dim3 grid((w + TW2 - 1) / TW2, (h + TH2 - 1) / TH2, K);

@@ -87,7 +87,6 @@ struct Mrf {
     uint16_t *J;                 // [3][mstride] position of that label in the child's list if the child should copy it, else 0xFFFF
     size_t mstride;
     uint32_t tree_cap;           // longest label list the shared-memory scratch of k_tree holds
-    uint32_t tree_prefetch;      // k_tree: L2 prefetch of the next step's rows (diagnostic switch B2TEX_TREE_PREFETCH=0)
 };
 // control block layout (uint32 words)
 constexpr int CTL_QN = 0;                        // [MAX_LEVELS+1] frontier sizes per round
@@ -166,7 +165,6 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // ---- end of primitives ----
 
 template <int G>
@@ -764,16 +762,6 @@ __global__ void __launch_bounds__(TREE_THREADS, MINB) k_tree(Mrf m)
                 rec[i].amin = bk;
                 rec[i].pad = (uint32_t)viewv[bk] + 1u;
             }
-            if (m.tree_prefetch && (n0.y >> 16) != 0xFFFFu) {   // the rows of the NEXT step's node on their way to L2 while this step's messages are formed
-                const uint32_t nn = n0.y & 0xFFFFu, npn = n1.w >> 16;
-                const float *nc = m.cost + (((uint64_t)n0.w << 32) | n0.z);
-                const uint16_t *nv = m.view + (((uint64_t)n0.w << 32) | n0.z), *npv = m.view + (((uint64_t)n2.y << 32) | n2.x);
-                for (uint32_t o = glane * 32u; o < nn; o += G * 32u) prefetch_l2(nc + o);
-                for (uint32_t o = glane * 64u; o < nn; o += G * 64u) prefetch_l2(nv + o);
-                for (uint32_t o = glane * 64u; o < npn; o += G * 64u) prefetch_l2(npv + o);
-                if (glane == 0 && nn) { prefetch_l2(nc + nn - 1u); prefetch_l2(nv + nn - 1u); }
-                if (glane == 1 && npn) prefetch_l2(npv + npn - 1u);
-            }
             if (mw) {   // prefix popcounts of the label bitmask
                 for (uint32_t w = glane; w < mw; w += G) {
                     uint32_t c = 0;
@@ -1059,8 +1047,6 @@ Mrf make_mrf(b2tex_ctx *c, uint32_t iter)
     m.rec = reinterpret_cast<NodeRec *>(c->mrf_rec.p);
     m.M = c->mrf_M.p; m.J = c->mrf_J.p; m.mstride = c->nnz;
     m.tree_cap = c->mrf_tree_cap;
-    static const bool no_prefetch = getenv("B2TEX_TREE_PREFETCH") && atoi(getenv("B2TEX_TREE_PREFETCH")) == 0;
-    m.tree_prefetch = no_prefetch ? 0u : 1u;
     return m;
 }
 

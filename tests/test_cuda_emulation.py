@@ -487,20 +487,24 @@ def test_device_seam_colours_stamping_and_blending_mask(emul, orc, local_inputs,
     assert sum(int((a["blending"] == 128).sum()) for a in ep) > 100 and sum(int((a["blending"] == 255).sum()) for a in ep) > 100
 
 
-def test_device_local_seam_leveling(emul, orc, local_inputs):
+@pytest.mark.parametrize("name", ["tiny", "occ", "messy"])
+def test_device_local_seam_leveling(emul, orc, local_inputs, name):
     """Full tex::local_seam_leveling on the device kernels (one batched CG over all patches, on fibers) vs the oracle
     (scipy splu per patch) and, when libtexref.so is there, vs the reference's own translation units (SparseLU shim):
     same validity masks, images within 5e-5 (CG tolerance 1e-5 relative residual; 8-bit quantisation is 4e-3)."""
     import patches as P
-    s, adj, rings, labels, seam, pp, pvpi = local_inputs("tiny")
+    s, adj, rings, labels, seam, pp, pvpi = local_inputs(name)
     pa = P.apply_adjust_values(s, pp, seam["row_ptr"], seam["row_label"], seam["x"])
     before = [q.image.copy() for q in pa]
     P.local_seam_leveling(s, adj, labels, pa, pvpi)
     ep, sizes = _emul_pipeline(emul, orc, s, adj, labels, seam, 2)
-    assert sizes[6] > 1000 and 10 < sizes[7] < 1000               # unknowns, CG iterations
+    assert sizes[6] > 500 and 10 < sizes[7] < 1000                # unknowns, CG iterations
+    worst = 0.0
     for a, b, b0 in zip(ep, pa, before):
         assert np.array_equal(a["validity"], b.validity)
-        assert np.abs(a["image"] - b.image).max() < 5e-5
+        worst = max(worst, float(np.abs(a["image"] - b.image).max()))
+    print(f"local seam leveling {name}: max |device - oracle| = {worst:.2e}, unknowns {sizes[6]}, CG iterations {sizes[7]}")
+    assert worst < 2e-5                                           # the bar of the oracle <-> reference pin
     assert max(float(np.abs(b.image - b0).max()) for b, b0 in zip(pa, before)) > 0.01
     try:
         import refpin

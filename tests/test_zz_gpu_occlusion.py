@@ -155,12 +155,14 @@ def test_golden_snapshots_of_the_texture_patches(b2, scene_mod, get_scene, name)
     c.close()
 
 
-def test_local_seam_leveling(b2, get_scene, scene_mod, orc):
+@pytest.mark.parametrize("name", ["tiny", "occ", "messy"])
+def test_local_seam_leveling(b2, get_scene, scene_mod, orc, name):
     """b2tex_local_seam_leveling_run (csrc/localseam.cu) after the global leveling, against oracle/patches.local_seam_leveling
-    (pinned to the reference's own translation units to 2e-5): same validity masks, images within 1e-4 -- the device
-    solves all patches with one batched CG (tolerance 1e-5) where the reference factorises each patch with SparseLU."""
+    (pinned to the reference's own translation units to 2e-5): same validity masks, images within 2e-5 (the bar of the
+    pin) -- the device solves all patches with one batched CG (tolerance 1e-5) where the reference factorises each patch with
+    SparseLU.  `occ`: occluded candidates, unseen faces, ten mesh components; `messy`: non-manifold fins, zero-area faces."""
     import patches as P
-    s = get_scene("tiny")
+    s = get_scene(name)
     ap, ai = scene_mod.face_adjacency(s.faces)
     rings = scene_mod.vertex_rings(s.faces, s.verts.shape[0])
     dc = orc.data_costs(s)
@@ -179,12 +181,12 @@ def test_local_seam_leveling(b2, get_scene, scene_mod, orc):
     pp, pvpi = P.generate_texture_patches(orc, s, (ap, ai), labels)
     pa = P.apply_adjust_values(s, pp, d["row_ptr"], d["row_label"], d["x"])
     P.local_seam_leveling(s, (ap, ai), labels, pa, pvpi)
-    assert linfo.num_seam_edges == len(P.find_seam_edges(s, (ap, ai), labels)) and linfo.num_unknowns > 1000
+    assert linfo.num_seam_edges == len(P.find_seam_edges(s, (ap, ai), labels)) and linfo.num_unknowns > 500
     assert all(r < 2e-5 for r in linfo.residual) and max(linfo.iterations) < 2000
     assert len(got) == len(pa)
     for a, b in zip(got, pa):
         assert np.array_equal(a["validity"], b.validity)
-        assert np.abs(a["image"] - b.image).max() < 1e-4
+        assert np.abs(a["image"] - b.image).max() < 2e-5
 
 
 def test_multi_gpu_seam_kernel_on_one_rank(b2, get_scene, oracle_pipeline):
