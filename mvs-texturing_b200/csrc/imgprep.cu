@@ -134,16 +134,17 @@ __global__ void __launch_bounds__(256) k_lum_sobel_vec(const uint8_t *__restrict
 
 // ---- TMA variant: the rgb tile (+ 1 pixel halo) of a view is staged by ONE bulk tensor copy ------------------------------
 // The view set is described to the TMA unit as a 3-D tensor of 32-bit words [K][H][3 W / 4] (needs W % 16 == 0: global
-// strides are multiples of 16 bytes); a CTA asks for the box {100 words, TH3 + 2 rows, 1 view} that holds the
-// (TW3 + 2) x (TH3 + 2) pixels it needs and waits on an mbarrier for the 13.6 KB to land; no thread issues a global
-// load.  Boxes that reach outside the tensor are NOT used: with 32-bit elements the B200 raises "illegal instruction"
-// for them (measured, profiles/r02_tma_matrix.txt; 8-bit elements would zero-fill but are limited to 256-byte rows), so
-// the box of an edge tile is shifted back inside the image and the out-of-image pixels get luminance 0 explicitly, which
-// is what the scalar kernel assigns there.  Luminance is then computed four pixels per thread from 16-byte windows of
+// strides are multiples of 16 bytes); a CTA asks for the box {104 words, TH3 + 2 rows, 1 view} that holds the
+// (TW3 + 2) x (TH3 + 2) pixels it needs and waits on an mbarrier for the 14.1 KB to land; no thread issues a global
+// load.  Two rules found by measurement on the B200 (tools/tma_matrix.cu, profiles/r02_tma_matrix.txt): the first
+// coordinate of the box must start on a 16-byte boundary of the row (anything else raises "illegal instruction"), so
+// the box starts three words early (104 words instead of 100); and the box of an edge tile is shifted back inside the
+// image instead of relying on out-of-bounds fill, the out-of-image pixels get luminance 0 explicitly, which is what the
+// scalar kernel assigns there.  Luminance is then computed four pixels per thread from 16-byte windows of
 // the raw tile, the Sobel sums four outputs per thread from six 32-bit words of the luminance tile with shared column
 // and row sums, and the gradient leaves as one 32-bit word per thread.  Same integer / fp32 arithmetic, bit-exact.
 constexpr int TW3 = 128, TH3 = 32;
-constexpr int BOXW3 = 100;                 // words per tile row: bytes [384 bx - 4, 384 bx + 396) before the shift
+constexpr int BOXW3 = 104;                 // words per tile row: bytes [384 bx - 16, 384 bx + 400) before the shift (16-byte aligned start)
 constexpr int LUMW3 = 136;                 // luminance tile row pitch (132 pixels used)
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -155,9 +156,10 @@ __device__ __forceinline__ void lum_sobel_tma_body(const CUtensorMap *tmap, uint
     __shared__ __align__(8) unsigned long long mbar;
     const int x0 = blockIdx.x * TW3, y0 = blockIdx.y * TH3;
     // wanted box start (words, rows) and the start actually used: shifted so that the box lies inside the tensor
-    const int c0 = (3 * x0) / 4 - 1, c1 = y0 - 1;
+    // (s0 stays a multiple of 4 words: 3 W / 4 and BOXW3 are)
+    const int c0 = (3 * x0) / 4 - 4, c1 = y0 - 1;
     const int s0 = min(max(c0, 0), 3 * w / 4 - BOXW3), s1 = min(max(c1, 0), h - (TH3 + 2));
-    const int dx = c0 - s0, dy = c1 - s1;   // word / row of the wanted box inside the staged one
+    const int dx = c0 - s0 + 3, dy = c1 - s1;   // word (of the byte-offset-1 layout used below) / row of the wanted box inside the staged one
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -1243,6 +1243,9 @@ int alloc_mrf(b2tex_ctx *c, const b2tex_mrf_params *p)
     double rho = nodes ? (double)c->nnz / nodes : 0.0;
     // lanes per node: a level of one tree holds only a few nodes, so wide groups idle on short label lists
     c->mrf_group = rho >= 64 ? 32 : rho >= 12 ? 16 : rho >= 6 ? 8 : 4;   // C3 (44 labels per node): 16 lanes 28.9 ms, 32 lanes 31.2 ms, 8 lanes 36.9 ms
+    // fewer trees than resident warps (small meshes, or one rank of many): a launch lasts as long as its largest tree, and
+    // half as many lanes per node mean twice as many nodes of a level per step (C3s: 16 lanes 4.8 ms, 8 lanes 4.1 ms)
+    if (c->mrf_group == 16 && (uint64_t)nodes / std::max(1u, p->root_div ? p->root_div : 1u) < (uint64_t)c->num_sms * 48u) c->mrf_group = 8;
     if (const char *g = getenv("B2TEX_MRF_GROUP")) {
         int v = atoi(g);
         if (v == 4 || v == 8 || v == 16 || v == 32) c->mrf_group = v;
