@@ -55,7 +55,7 @@ __device__ __forceinline__ bool box_hit(const float *lo, const float *hi, float 
 __device__ __forceinline__ bool bvh_occluded(const BvhNode *__restrict__ nodes,
                                              const float *__restrict__ tri, uint32_t num_tris,
                                              float ox, float oy, float oz, float dx, float dy, float dz,
-                                             float tmin, float tmax)
+                                             float tmin, float tmax, uint32_t *overflow)
 {
     if (num_tris == 0) return false;
     if (num_tris == 1) return tri_occludes(tri, ox, oy, oz, dx, dy, dz, tmin, tmax);
@@ -88,6 +88,7 @@ __device__ __forceinline__ bool bvh_occluded(const BvhNode *__restrict__ nodes,
                 if (tri_occludes(tri + 9 * (size_t)(~right), ox, oy, oz, dx, dy, dz, tmin, tmax)) return true;
             } else if (next < 0) next = right;
             else if (sp < 100) stack[sp++] = right;
+            else if (overflow) atomicOr(overflow, 1u);   // a subtree would be dropped: reported (B2TEX_ERR_LIMITS), never silent
         }
         if (next >= 0) { node = next; continue; }
         if (sp == 0) return false;

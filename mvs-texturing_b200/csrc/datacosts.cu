@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) k_rays(const float *__restrict__ verts, u
                                               uint32_t vwords, const uint32_t *__restrict__ vorder,
                                               const BvhNode *__restrict__ nodes,
                                               const float *__restrict__ tri, uint32_t num_tris,
-                                              unsigned long long *ray_count)
+                                              unsigned long long *ray_count, uint32_t *stack_overflow)
 {
     size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     size_t total = (size_t)K * vwords;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) k_rays(const float *__restrict__ verts, u
         float tmax = sqrtf(((0.0f + dx * dx) + dy * dy) + dz * dz);        // :204
         float tmin = tmax * 0.0001f;                                       // :205
         dx = dx / tmax; dy = dy / tmax; dz = dz / tmax;                    // :206
-        occ = bvh_occluded(nodes, tri, num_tris, ox, oy, oz, dx, dy, dz, tmin, tmax);
+        occ = bvh_occluded(nodes, tri, num_tris, ox, oy, oz, dx, dy, dz, tmin, tmax, stack_overflow);
     }
     uint32_t res = __ballot_sync(0xffffffffu, occ);
     if (lane == 0) {
@@ -613,7 +613,13 @@ static int finish_candidates(b2tex_ctx *c, const b2tex_settings *st, uint64_t nu
     B2_CUDA(cudaMemcpyAsync(&nnz, c->dc_ptr.p + F, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaMemcpyAsync(&maxbits, c->scalars.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaMemcpyAsync(&rays, ray_count, sizeof(rays), cudaMemcpyDeviceToHost, s));
+    uint32_t stack_overflow = 0;
+    B2_CUDA(cudaMemcpyAsync(&stack_overflow, c->scalars.p + 8, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
+    if (stack_overflow) {   // the reference's BVH has no such limit: refuse rather than risk a face counted as visible
+        set_error("visibility rays: the traversal stack (100 entries) overflowed");
+        return B2TEX_ERR_LIMITS;
+    }
     c->nnz = nnz;
     B2_TRY(c->dc_view.alloc(nnz));
     B2_TRY(c->dc_quality.alloc(nnz));
@@ -704,7 +710,7 @@ int data_costs_qualities(b2tex_ctx *c, const b2tex_settings *st, b2tex_dc_info *
         ScopedTimer tm(c, "k_rays", 8.0 * (double)warps + 12.0 * c->Vn);
         B2_LAUNCH k_rays<<<(unsigned)rblocks, 256, 0, s>>>(c->verts.p, c->Vn, c->views_dev.p, K, c->need_bits.p, c->occ_bits.p,
                                                  vwords, c->vorder.p, c->bvh.nodes.p, c->bvh.tri.p, c->bvh.num_tris,
-                                                 ray_count);
+                                                 ray_count, c->scalars.p + 8);
         B2_KERNEL_CHECK();
     }
     if (!c->any_corner_flag) B2_TRY(prepare_images(c, st->data_term, true));   // waits for the upload if it is still in flight
