@@ -4,8 +4,10 @@
 // prepare_blending_mask (texture_patch.cpp:197-297), TexturePatch::blend (:180-192) and poisson_blend
 // (poisson_blending.cpp:49-138).  Runs after patches_run() on the patches it left on the device.
 //
-//   host            : seam edges, their projections into the patches, sampling density, multi-patch vertices
-//                     (patches_host.h; graph bookkeeping on O(#seam edges) data)
+//   k_seam_edges, k_plan_edges, k_plan_samples, k_plan_vertices : seam edges, their projections into the patches, sampling
+//                     density, multi-patch vertices -- from the vertex -> face rings by count / scan / fill, the arrays
+//                     the host bookkeeping of patches_host.h produces, element for element (that code remains as the
+//                     path for > 16 patches around one vertex and as the cross-check of the emulation tests)
 //   k_edge_colors   : mean colour over the adjacent patches at every sample of every seam edge     (:20-37,:131-141)
 //   k_vertex_colors : mean colour of every vertex that lies in more than one patch                 (:155-168)
 //   k_stamp_keys / k_stamp_apply : vertex pixels, then Bresenham lines (:39-92), written with "last writer wins"
@@ -55,6 +57,165 @@ __device__ __forceinline__ void patch_linear_at(const float *__restrict__ img, i
     const float *a = img + 3 * ((size_t)fx + (size_t)fy * w), *b = img + 3 * ((size_t)fx1 + (size_t)fy * w);
     const float *c = img + 3 * ((size_t)fx + (size_t)fy1 * w), *d = img + 3 * ((size_t)fx1 + (size_t)fy1 * w);
     for (int k = 0; k < 3; ++k) out[k] = ((a[k] * (w0 * w2) + b[k] * (w1 * w2)) + c[k] * (w0 * w3)) + d[k] * (w1 * w3);
+}
+
+
+// ---- seam planning on the device -----------------------------------------------------------------------------------
+// What patches_host.h does in three passes over host copies (find_seam_edges, vertex_projections, plan_seam_lines;
+// 172 of the 217 ms of this stage on the C3 workload) follows from the vertex -> face rings without any sort:
+//   * a seam edge (v1 < v2) is projected into exactly the patches that own a face containing the edge (the "common face"
+//     test of seam_leveling.cpp:61-91), ascending patch id;
+//   * the projection of a vertex into a patch is the texture coordinate of the vertex in the FIRST slot (slots are patch
+//     major, in the reference's face order) of that patch that touches it (generate_texture_patches.cpp:520-535: "first
+//     projection wins");
+//   * a vertex is stamped if faces of more than one patch meet in it (local_seam_leveling.cpp:157).
+// Every list is produced by count -> exclusive scan -> fill, so the arrays are the host version's, element for element.
+constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
+constexpr int PLAN_MAXP = 16;   // distinct patches around one edge / vertex handled here (more: limit flag -> host path)
+
+struct SeamPlanIn {
+    const uint32_t *faces;        // [F][3]
+    const uint32_t *vf_ptr, *vf_idx;
+    const uint32_t *face_slot;    // [F] final slot of a face, NO_SLOT if it is in no patch
+    const uint32_t *slot_patch, *slot_face;
+    const float *tex;             // [slots][3][2]
+};
+
+__global__ void __launch_bounds__(256) k_face_slot(uint32_t T, const uint32_t *__restrict__ slot_face, uint32_t *face_slot)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) face_slot[slot_face[t]] = t;
+}
+
+// find_seam_edges (seam_leveling.cpp:16-59): one edge (v1 < v2) per pair of adjacent faces with different labels, face major
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_seam_edges(uint32_t F, const uint32_t *__restrict__ adj_ptr, const uint32_t *__restrict__ adj_idx,
+                                                    const uint32_t *__restrict__ labels, const uint32_t *__restrict__ faces,
+                                                    uint32_t *cnt, const uint32_t *__restrict__ off, uint32_t *edges)
+{
+    const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= F) return;
+    uint32_t n = 0;
+    for (uint32_t a = adj_ptr[node]; a < adj_ptr[node + 1]; ++a) {
+        const uint32_t adj = adj_idx[a];
+        if (node > adj || labels[node] == labels[adj]) continue;
+        uint32_t shared[4]; int ns = 0;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                if (faces[3 * (size_t)node + i] == faces[3 * (size_t)adj + j] && ns < 4) shared[ns++] = faces[3 * (size_t)node + i];
+        if (ns != 2 || shared[0] == shared[1]) continue;   // the reference asserts this
+        if (FILL) {
+            const uint32_t v1 = min(shared[0], shared[1]), v2 = max(shared[0], shared[1]);
+            edges[2 * (size_t)(off[node] + n)] = v1; edges[2 * (size_t)(off[node] + n) + 1] = v2;
+        }
+        ++n;
+    }
+    if (!FILL) cnt[node] = n;
+}
+
+__device__ __forceinline__ bool plan_face_has(const uint32_t *__restrict__ faces, uint32_t f, uint32_t v)
+{
+    return faces[3 * (size_t)f] == v || faces[3 * (size_t)f + 1] == v || faces[3 * (size_t)f + 2] == v;
+}
+// ascending list of distinct patches; false when it overflows
+__device__ __forceinline__ bool plan_insert(uint32_t *list, uint32_t &n, uint32_t q)
+{
+    uint32_t k = 0;
+    while (k < n && list[k] < q) ++k;
+    if (k < n && list[k] == q) return true;
+    if (n >= (uint32_t)PLAN_MAXP) return false;
+    for (uint32_t i = n; i > k; --i) list[i] = list[i - 1];
+    list[k] = q; ++n;
+    return true;
+}
+// texture coordinate of vertex v in the first slot of patch q that touches it
+__device__ __forceinline__ void plan_first_proj(const SeamPlanIn &in, uint32_t v, uint32_t q, float *xy)
+{
+    uint32_t best = NO_SLOT;
+    for (uint32_t a = in.vf_ptr[v]; a < in.vf_ptr[v + 1]; ++a) {
+        const uint32_t t = in.face_slot[in.vf_idx[a]];
+        if (t != NO_SLOT && in.slot_patch[t] == q && t < best) best = t;
+    }
+    xy[0] = xy[1] = 0.0f;
+    if (best == NO_SLOT) return;
+    const uint32_t f = in.slot_face[best];
+    const int j = in.faces[3 * (size_t)f] == v ? 0 : (in.faces[3 * (size_t)f + 1] == v ? 1 : 2);
+    xy[0] = in.tex[6 * (size_t)best + 2 * j]; xy[1] = in.tex[6 * (size_t)best + 2 * j + 1];
+}
+
+// find_mesh_edge_projections (seam_leveling.cpp:61-91) + the sampling density of local_seam_leveling.cpp:131-140, per seam edge.
+// count pass: cnt_proj[e], cnt_samp[e]; fill pass: edge_info, proj_patch | proj_edge, edge_proj
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_plan_edges(uint32_t NE, SeamPlanIn in, const uint32_t *__restrict__ edges, uint32_t *cnt_proj,
+                                                    uint32_t *cnt_samp, const uint32_t *__restrict__ off_proj, const uint32_t *__restrict__ off_samp,
+                                                    uint32_t NL, uint32_t *edge_info, uint32_t *proj_pack, float *edge_proj, uint32_t *limit_flags)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= NE) return;
+    const uint32_t v1 = edges[2 * (size_t)e], v2 = edges[2 * (size_t)e + 1];
+    uint32_t list[PLAN_MAXP], n = 0;
+    for (uint32_t a = in.vf_ptr[v1]; a < in.vf_ptr[v1 + 1]; ++a) {
+        const uint32_t f = in.vf_idx[a];
+        if (!plan_face_has(in.faces, f, v2)) continue;
+        const uint32_t t = in.face_slot[f];
+        if (t == NO_SLOT) continue;
+        if (!plan_insert(list, n, in.slot_patch[t])) atomicOr(limit_flags, 1u);
+    }
+    float max_length = 1.0f;
+    for (uint32_t k = 0; k < n; ++k) {
+        float p1[2], p2[2];
+        plan_first_proj(in, v1, list[k], p1);
+        plan_first_proj(in, v2, list[k], p2);
+        const float dx = p1[0] - p2[0], dy = p1[1] - p2[1];
+        const float length = sqrtf((0.0f + dx * dx) + dy * dy);
+        max_length = fmaxf(max_length, length);
+        if (FILL) {
+            const size_t o = (size_t)off_proj[e] + k;
+            proj_pack[o] = list[k]; proj_pack[(size_t)NL + o] = e;
+            edge_proj[4 * o] = p1[0]; edge_proj[4 * o + 1] = p1[1]; edge_proj[4 * o + 2] = p2[0]; edge_proj[4 * o + 3] = p2[1];
+        }
+    }
+    const uint32_t ns = (uint32_t)ceilf(max_length * 2.0f);   // :139
+    if (FILL) {
+        edge_info[4 * (size_t)e] = off_proj[e]; edge_info[4 * (size_t)e + 1] = n;
+        edge_info[4 * (size_t)e + 2] = off_samp[e]; edge_info[4 * (size_t)e + 3] = ns;
+    } else { cnt_proj[e] = n; cnt_samp[e] = ns; }
+}
+
+// every colour sample knows its edge
+__global__ void __launch_bounds__(256) k_plan_samples(uint32_t NE, const uint32_t *__restrict__ edge_info, uint32_t *sample_edge)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= NE) return;
+    const uint32_t b = edge_info[4 * (size_t)e + 2], n = edge_info[4 * (size_t)e + 3];
+    for (uint32_t j = 0; j < n; ++j) sample_edge[(size_t)b + j] = e;
+}
+
+// vertices in which faces of more than one patch meet (local_seam_leveling.cpp:155-176), ascending vertex id.
+// count pass: cnt_vert[v] (0 / 1), cnt_vproj[v]; fill pass: vert_info, vproj_patch | vproj_vert, vert_proj
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_plan_vertices(uint32_t Vn, SeamPlanIn in, uint32_t *cnt_vert, uint32_t *cnt_vproj,
+                                                       const uint32_t *__restrict__ off_vert, const uint32_t *__restrict__ off_vproj, uint32_t NVP,
+                                                       uint32_t *vert_info, uint32_t *vproj_pack, float *vert_proj, uint32_t *limit_flags)
+{
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= Vn) return;
+    uint32_t list[PLAN_MAXP], n = 0;
+    for (uint32_t a = in.vf_ptr[v]; a < in.vf_ptr[v + 1]; ++a) {
+        const uint32_t t = in.face_slot[in.vf_idx[a]];
+        if (t == NO_SLOT) continue;
+        if (!plan_insert(list, n, in.slot_patch[t])) atomicOr(limit_flags, 1u);
+    }
+    if (!FILL) { cnt_vert[v] = n > 1 ? 1u : 0u; cnt_vproj[v] = n > 1 ? n : 0u; return; }
+    if (n <= 1) return;
+    const uint32_t iv = off_vert[v], b = off_vproj[v];
+    vert_info[2 * (size_t)iv] = b; vert_info[2 * (size_t)iv + 1] = n;
+    for (uint32_t k = 0; k < n; ++k) {
+        float xy[2];
+        plan_first_proj(in, v, list[k], xy);
+        vproj_pack[(size_t)b + k] = list[k]; vproj_pack[(size_t)NVP + b + k] = iv;
+        vert_proj[2 * ((size_t)b + k)] = xy[0]; vert_proj[2 * ((size_t)b + k) + 1] = xy[1];
+    }
 }
 
 // mean_color_of_edge_point for sample j of its edge (:20-37), one thread per sample
@@ -469,6 +630,76 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
     const uint64_t P = ps.total_pixels;
     if (P >= 0xFFFFFFFFull) { set_error("local seam leveling: more than 2^32 patch pixels"); return B2TEX_ERR_LIMITS; }
 
+    // ---- seam planning: seam edges, their projections into the patches, sampling density, multi-patch vertices ----
+    DevBuf<uint32_t> &d_sample_edge = ps.sample_edge, &d_edge_info = ps.edge_info, &d_vert_info = ps.vert_info;
+    DevBuf<uint32_t> &d_proj = ps.line_info, &d_vproj = ps.pixw_info;   // [proj_patch | proj_edge], [vproj_patch | vproj_vert]
+    uint32_t NE = 0, S = 0, NV = 0, NL = 0, NVP = 0;
+    static const bool plan_on_host = getenv("B2TEX_LSEAM_HOST") != nullptr;   // diagnostic: the host bookkeeping of patches_host.h
+    bool planned = false;
+    if (c->have_rings && !plan_on_host && T && F < 0x7FFFFFFFu) {
+        ScopedTimer t_plan(c, "ls.plan_on_device");
+        const uint32_t Vn = c->Vn;
+        DevBuf<uint32_t> &face_slot = ps.plan_face_slot, &cnt_a = ps.plan_cnt_a, &cnt_b = ps.plan_cnt_b, &off_a = ps.plan_off_a,
+                         &off_b = ps.plan_off_b, &edges = ps.plan_edges, &flags = ps.plan_flags;
+        const size_t nmax = (size_t)std::max(F, Vn) + 1;
+        B2_TRY(face_slot.alloc(F)); B2_TRY(cnt_a.alloc(nmax)); B2_TRY(cnt_b.alloc(nmax)); B2_TRY(off_a.alloc(nmax)); B2_TRY(off_b.alloc(nmax));
+        B2_TRY(flags.alloc(1)); B2_TRY(flags.zero(s));
+        B2_CUDA(cudaMemsetAsync(face_slot.p, 0xFF, (size_t)F * sizeof(uint32_t), s));
+        B2_LAUNCH k_face_slot<<<(T + 255) / 256, 256, 0, s>>>(T, ps.slot_face.p, face_slot.p);
+        // seam edges, face major
+        B2_CUDA(cudaMemsetAsync(cnt_a.p, 0, nmax * sizeof(uint32_t), s));
+        B2_LAUNCH k_seam_edges<false><<<(F + 255) / 256, 256, 0, s>>>(F, c->adj_ptr.p, c->adj_idx.p, c->labels.p, c->faces.p, cnt_a.p, nullptr, nullptr);
+        B2_TRY(cub_exclusive_sum_u32(c, cnt_a.p, off_a.p, (size_t)F + 1));
+        B2_CUDA(cudaMemcpyAsync(&NE, off_a.p + F, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        B2_TRY(edges.alloc(2 * (size_t)(NE ? NE : 1)));
+        if (NE) B2_LAUNCH k_seam_edges<true><<<(F + 255) / 256, 256, 0, s>>>(F, c->adj_ptr.p, c->adj_idx.p, c->labels.p, c->faces.p, nullptr, off_a.p, edges.p);
+        B2_KERNEL_CHECK();
+        SeamPlanIn in{c->faces.p, c->vf_ptr.p, c->vf_idx.p, face_slot.p, ps.slot_patch.p, ps.slot_face.p, ps.tex.p};
+        // per edge: projections and samples (count -> scan -> fill)
+        B2_TRY(cnt_a.alloc(std::max(nmax, (size_t)NE + 1))); B2_TRY(cnt_b.alloc(std::max(nmax, (size_t)NE + 1)));
+        B2_TRY(off_a.alloc(std::max(nmax, (size_t)NE + 1))); B2_TRY(off_b.alloc(std::max(nmax, (size_t)NE + 1)));
+        B2_CUDA(cudaMemsetAsync(cnt_a.p + NE, 0, sizeof(uint32_t), s));
+        B2_CUDA(cudaMemsetAsync(cnt_b.p + NE, 0, sizeof(uint32_t), s));
+        if (NE) B2_LAUNCH k_plan_edges<false><<<(NE + 127) / 128, 128, 0, s>>>(NE, in, edges.p, cnt_a.p, cnt_b.p, nullptr, nullptr, 0u, nullptr, nullptr, nullptr, flags.p);
+        B2_TRY(cub_exclusive_sum_u32(c, cnt_a.p, off_a.p, (size_t)NE + 1));
+        B2_TRY(cub_exclusive_sum_u32(c, cnt_b.p, off_b.p, (size_t)NE + 1));
+        uint32_t lim = 0;
+        B2_CUDA(cudaMemcpyAsync(&NL, off_a.p + NE, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaMemcpyAsync(&S, off_b.p + NE, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaMemcpyAsync(&lim, flags.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        if (!lim) {
+            B2_TRY(d_edge_info.alloc(4 * (size_t)(NE ? NE : 1))); B2_TRY(d_proj.alloc(2 * (size_t)(NL ? NL : 1)));
+            B2_TRY(ps.edge_proj.alloc(4 * (size_t)(NL ? NL : 1))); B2_TRY(d_sample_edge.alloc(S ? S : 1));
+            if (NE) {
+                B2_LAUNCH k_plan_edges<true><<<(NE + 127) / 128, 128, 0, s>>>(NE, in, edges.p, nullptr, nullptr, off_a.p, off_b.p, NL, d_edge_info.p, d_proj.p,
+                                                                    ps.edge_proj.p, flags.p);
+                B2_LAUNCH k_plan_samples<<<(NE + 255) / 256, 256, 0, s>>>(NE, d_edge_info.p, d_sample_edge.p);
+            }
+            // multi-patch vertices
+            B2_TRY(cnt_a.alloc(std::max(nmax, (size_t)NE + 1)));
+            B2_CUDA(cudaMemsetAsync(cnt_a.p + Vn, 0, sizeof(uint32_t), s));
+            B2_CUDA(cudaMemsetAsync(cnt_b.p + Vn, 0, sizeof(uint32_t), s));
+            B2_LAUNCH k_plan_vertices<false><<<(Vn + 127) / 128, 128, 0, s>>>(Vn, in, cnt_a.p, cnt_b.p, nullptr, nullptr, 0u, nullptr, nullptr, nullptr, flags.p);
+            B2_TRY(cub_exclusive_sum_u32(c, cnt_a.p, off_a.p, (size_t)Vn + 1));
+            B2_TRY(cub_exclusive_sum_u32(c, cnt_b.p, off_b.p, (size_t)Vn + 1));
+            B2_CUDA(cudaMemcpyAsync(&NV, off_a.p + Vn, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            B2_CUDA(cudaMemcpyAsync(&NVP, off_b.p + Vn, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            B2_CUDA(cudaMemcpyAsync(&lim, flags.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            B2_CUDA(cudaStreamSynchronize(s));
+        }
+        if (!lim) {
+            B2_TRY(d_vert_info.alloc(2 * (size_t)(NV ? NV : 1))); B2_TRY(d_vproj.alloc(2 * (size_t)(NVP ? NVP : 1)));
+            B2_TRY(ps.vert_proj.alloc(2 * (size_t)(NVP ? NVP : 1)));
+            B2_LAUNCH k_plan_vertices<true><<<(Vn + 127) / 128, 128, 0, s>>>(Vn, in, nullptr, nullptr, off_a.p, off_b.p, NVP, d_vert_info.p, d_vproj.p,
+                                                                  ps.vert_proj.p, flags.p);
+            B2_KERNEL_CHECK();
+            planned = true;
+        }
+        // more than PLAN_MAXP patches around one edge or vertex: the host bookkeeping below has no such limit
+    }
+    if (!planned) {
     // ---- host bookkeeping: vertex projections, seam edges and their projections ----
     std::unique_ptr<ScopedTimer> t_host(new ScopedTimer(c, "ls.download+host_bookkeeping"));
     std::vector<float> tex(6 * (size_t)(T ? T : 1));
@@ -487,19 +718,14 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
     vertex_projections(c->Vn, mesh_faces.data(), pl, ps.faces.data(), tex.data(), seam_edges, vpi);
     SeamLines sl;
     plan_seam_lines(seam_edges, vpi, sl);
-    const uint32_t NE = sl.num_edges(), S = sl.num_samples(), NV = sl.num_verts();
-    const uint32_t NL = (uint32_t)sl.proj_patch.size(), NVP = (uint32_t)sl.vert_proj_patch.size();
+    NE = sl.num_edges(); S = sl.num_samples(); NV = sl.num_verts();
+    NL = (uint32_t)sl.proj_patch.size(); NVP = (uint32_t)sl.vert_proj_patch.size();
     std::vector<uint32_t> proj_edge(NL ? NL : 1), vproj_vert(NVP ? NVP : 1);
     for (uint32_t e = 0; e < NE; ++e)
         for (uint32_t k = sl.edge_info[4 * (size_t)e]; k < sl.edge_info[4 * (size_t)e] + sl.edge_info[4 * (size_t)e + 1]; ++k) proj_edge[k] = e;
     for (uint32_t v = 0; v < NV; ++v)
         for (uint32_t k = sl.vert_info[2 * (size_t)v]; k < sl.vert_info[2 * (size_t)v] + sl.vert_info[2 * (size_t)v + 1]; ++k) vproj_vert[k] = v;
-
     t_host.reset();
-    // ---- colours, stamping ----
-    std::unique_ptr<ScopedTimer> t_col(new ScopedTimer(c, "ls.upload+colors+stamp"));
-    DevBuf<uint32_t> &d_sample_edge = ps.sample_edge, &d_edge_info = ps.edge_info, &d_vert_info = ps.vert_info;
-    DevBuf<uint32_t> &d_proj = ps.line_info, &d_vproj = ps.pixw_info;   // [proj_patch | proj_edge], [vproj_patch | vproj_vert]
     std::vector<uint32_t> pack(2 * (size_t)(NL ? NL : 1)), vpack(2 * (size_t)(NVP ? NVP : 1));
     for (uint32_t k = 0; k < NL; ++k) { pack[k] = sl.proj_patch[k]; pack[(size_t)NL + k] = proj_edge[k]; }
     for (uint32_t k = 0; k < NVP; ++k) { vpack[k] = sl.vert_proj_patch[k]; vpack[(size_t)NVP + k] = vproj_vert[k]; }
@@ -510,6 +736,10 @@ int local_seam_run(b2tex_ctx *c, b2tex_local_seam_info *info)
     B2_TRY(d_vproj.upload(vpack.data(), 2 * (size_t)NVP, s));
     B2_TRY(ps.edge_proj.upload(sl.edge_proj.data(), 4 * (size_t)NL, s));
     B2_TRY(ps.vert_proj.upload(sl.vert_proj.data(), 2 * (size_t)NVP, s));
+    B2_CUDA(cudaStreamSynchronize(s));   // the staging vectors are locals of this block
+    }
+    // ---- colours, stamping ----
+    std::unique_ptr<ScopedTimer> t_col(new ScopedTimer(c, "ls.colors+stamp"));
     B2_TRY(ps.edge_color.alloc(3 * (size_t)S));
     B2_TRY(ps.vert_color.alloc(3 * (size_t)NV));
     B2_TRY(ps.orig.alloc(3 * P));

@@ -19,6 +19,7 @@ struct PatchState {
     DevBuf<float> orig;                   // images before the seam colours are stamped (Poisson source)
     DevBuf<float> edge_proj, edge_color, vert_color, vert_proj;
     DevBuf<uint32_t> edge_info, sample_edge, vert_info, line_info, pixw_info;
+    DevBuf<uint32_t> plan_face_slot, plan_cnt_a, plan_cnt_b, plan_off_a, plan_off_b, plan_edges, plan_flags;   // seam planning on the device
     DevBuf<uint8_t> layer;
     DevBuf<uint32_t> uflag, uidx, ulist;
     DevBuf<int32_t> unb;

@@ -220,7 +220,8 @@ def make_images(k, width, height, out=None):
     if out is None:
         out = np.empty((k, height, width, 3), dtype=np.uint8)
     tint = np.array([1.0, 0.9, 0.8], dtype=np.float32)
-    for v in range(k):
+
+    def one(v):   # every view from its own seed: the result does not depend on how the views are spread over threads
         rs = np.random.RandomState(1000 + v)
         gain = rs.uniform(0.8, 1.2)
         bias = rs.uniform(-20.0, 20.0)
@@ -229,6 +230,15 @@ def make_images(k, width, height, out=None):
         base = (np.float32(gain * 200.0) * Tv + np.float32(bias + 25.0))
         for c in range(3):
             out[v, :, :, c] = np.clip(np.rint(base * tint[c]), 1, 255).astype(np.uint8)
+
+    if k * width * height >= (1 << 26):   # large view sets (C3, C5): numpy releases the GIL in these kernels
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+            list(ex.map(one, range(k)))
+    else:
+        for v in range(k):
+            one(v)
     return out
 
 

@@ -469,11 +469,13 @@ def local_inputs(orc, scene_mod, get_scene):
     return _get
 
 
-@pytest.mark.parametrize("name", ["tiny", "occ", "messy"])
+@pytest.mark.parametrize("name", ["tiny", "occ", "messy", "C2s"])
 def test_device_seam_colours_stamping_and_blending_mask(emul, orc, local_inputs, name, monkeypatch):
     """csrc/localseam.cu up to the Poisson solve vs oracle/patches.local_seam_leveling with the solve switched off: the
     images with the mean seam / vertex colours stamped in ("last writer wins" by atomicMax on the write order) and the
-    blending masks after prepare_blending_mask (breadth-first layering, 20 px strip) are bit-identical."""
+    blending masks after prepare_blending_mask (breadth-first layering, 20 px strip) are bit-identical.  The harness also runs
+    the seam planning twice -- host bookkeeping (patches_host.h) and the device kernels (k_seam_edges / k_plan_edges /
+    k_plan_vertices) -- and fails unless every planning array is identical (error codes -7 .. -15)."""
     import patches as P
     s, adj, rings, labels, seam, pp, pvpi = local_inputs(name)
     pa = P.apply_adjust_values(s, pp, seam["row_ptr"], seam["row_label"], seam["x"])
