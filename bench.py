@@ -396,7 +396,8 @@ def main():
                "run": {"nnz": int(total_nnz), "mrf_iterations": mrf_it, "mrf_energy": res["mrf"].energy_final,
                        "mrf_energy_ref": verify["mrf_energy_ref"] if verify else None,
                        "cg_iterations": list(res["seam"].iterations), "cg_residual": [float(x) for x in res["seam"].residual],
-                       "scene_setup_s": round(gen_s, 1)},
+                       "scene_setup_s": round(gen_s, 1),
+                       "device_memory_in_use_gb": round((lambda fr, tot: (tot - fr) / 1e9)(*torch.cuda.mem_get_info()), 2)},
                "stage_ms": stage_ms, "kernels": kernels[:10], "roofline": roofline, "cpu_baseline": cpu,
                "verify": verify, "e2e": e2e, "extra_stages": extra, "gpu_launches": int(n_launch.item()), "clocks": clocks,
                "wall_ms_per_step": 1e3 * wall / args.steps}
