@@ -54,8 +54,19 @@ def tree_lower_bound(ap, ai, fp, view, cost):
         ok[ok] &= lv[idx[ok]] == lp[ok]
         msg[ok] = np.minimum(hv[idx[ok]], hmin + 1.0)
         h[p] = h[p] + msg
-        h[v] = None
-    return total
+    # top-down: the labeling that attains the bound (what a spanning-tree step of the solver would propose)
+    labels = np.zeros(F, np.uint32)
+    for v in order:
+        p = parent[v]
+        hv, lv = h[v], view[fp[v]:fp[v + 1]]
+        k = int(np.argmin(hv))
+        if p >= 0:
+            want = labels[p] - 1
+            j = int(np.searchsorted(lv, want))
+            if j < len(lv) and lv[j] == want and hv[j] <= hv.min() + 1.0:
+                k = j
+        labels[v] = int(lv[k]) + 1
+    return total, labels
 
 
 def main(names):
@@ -71,15 +82,18 @@ def main(names):
         m200 = O.view_selection(ap, ai, fp, view, cost, max_iterations=200, window=10 ** 6)
         n = np.diff(fp)
         lb_unary = float(sum(cost[fp[v]:fp[v + 1]].min() if n[v] else 1.0 for v in range(len(n))))
-        lb_tree = tree_lower_bound(ap, ai, fp, view, cost)
-        rows.append((name, s.num_faces, m["energy_initial"], m["iterations"], m["energy"], m200["energy"], lb_unary, lb_tree))
+        lb_tree, tree_labels = tree_lower_bound(ap, ai, fp, view, cost)
+        e_tree_labels = O.mrf_energy(ap, ai, fp, view, cost, tree_labels)   # full model, all edges
+        rows.append((name, s.num_faces, m["energy_initial"], m["iterations"], m["energy"], m200["energy"], lb_unary, lb_tree, e_tree_labels))
         print(rows[-1], f"({t1 - t0:.1f}s)", flush=True)
     out = ["# MRF solver quality (oracle = CUDA path bit for bit; `python tools/mrf_quality.py`)", "",
-           "| scene | faces | E arg-min unaries | stop rule: iterations | E at the stop rule | E after 200 iterations | LB unaries | LB spanning forest | (E_stop - LB_tree) / LB_tree | (E_stop - E_200) / E_200 |",
-           "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
+           "| scene | faces | E arg-min unaries | E of the spanning-forest optimum (all edges counted) | stop rule: iterations | E at the stop rule | E after 200 iterations | LB unaries | LB spanning forest | (E_stop - LB_tree) / LB_tree | (E_stop - E_200) / E_200 |",
+           "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
     for r in rows:
-        out.append(f"| {r[0]} | {r[1]} | {r[2]:.1f} | {r[3]} | {r[4]:.1f} | {r[5]:.1f} | {r[6]:.1f} | {r[7]:.1f} | {100 * (r[4] - r[7]) / r[7]:.2f} % | {100 * (r[4] - r[5]) / r[5]:.2f} % |")
-    out += ["", "LB spanning forest keeps F - 1 of the ~1.5 F edges, so the true optimum lies between it and E after 200 iterations."]
+        out.append(f"| {r[0]} | {r[1]} | {r[2]:.1f} | {r[8]:.1f} | {r[3]} | {r[4]:.1f} | {r[5]:.1f} | {r[6]:.1f} | {r[7]:.1f} | {100 * (r[4] - r[7]) / r[7]:.2f} % | {100 * (r[4] - r[5]) / r[5]:.2f} % |")
+    out += ["", "LB spanning forest keeps F - 1 of the ~1.5 F edges, so the true optimum lies between it and E after 200 iterations.",
+            "The second energy column is what mapMAP's spanning-tree step (`view_selection.cpp:105`, not built here) would hand the first",
+            "acyclic iteration instead of the arg-min labeling: the labeling that is optimal on a BFS spanning forest, scored on the full model."]
     open(os.path.join(ROOT, "profiles", "r02_mrf_quality.md"), "w").write("\n".join(out) + "\n")
 
 
