@@ -563,3 +563,43 @@ def test_local_seam_leveling_makes_patches_agree_on_seams(orc, scene_mod, oracle
         changed = np.abs(p.image - b).max(axis=2) > 1e-6
         assert not np.any(changed & (p.blending == 0))             # only masked pixels are re-solved
         assert np.isfinite(p.image).all()
+
+
+def test_spanning_forest_bound_brackets_the_solver(orc, scene_mod):
+    """tools/mrf_quality.py: the exact optimum of the model restricted to a spanning forest is a lower bound of every labeling's
+    energy (dropped Potts terms are >= 0), and the labeling that attains it is a valid labeling whose full energy lies above the
+    solver's result on this scene."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("mrf_quality", os.path.join(os.path.dirname(__file__), "..", "tools", "mrf_quality.py"))
+    mq = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mq)
+    s = scene_mod.config("tiny")
+    ap, ai = scene_mod.face_adjacency(s.faces)
+    dc = orc.data_costs(s)
+    fp, view, cost = dc["face_ptr"], dc["view"], dc["cost"]
+    m = orc.view_selection(ap, ai, fp, view, cost, threads=1)
+    lb, tree_labels = mq.tree_lower_bound(ap, ai, fp, view, cost)
+    e_tree = orc.mrf_energy(ap, ai, fp, view, cost, tree_labels)
+    assert lb <= m["energy"] + 1e-6 and lb <= e_tree + 1e-6
+    assert m["energy"] <= e_tree + 1e-6 <= m["energy_initial"] + 1e-6 or e_tree <= m["energy_initial"] + 1e-6
+    for f in range(s.num_faces):   # every label is one of the face's own views
+        if fp[f + 1] > fp[f]:
+            assert tree_labels[f] - 1 in view[fp[f]:fp[f + 1]]
+
+
+def test_image_synthesis_is_thread_order_independent(scene_mod):
+    """make_images spreads large view sets over threads; every view is seeded by its index, so the bytes do not depend on it."""
+    import zlib
+    a = scene_mod.make_images(9, 4096, 2048)       # above the threading threshold
+    ref = np.empty_like(a)
+    T = scene_mod.base_texture(4096, 2048)
+    tint = np.array([1.0, 0.9, 0.8], dtype=np.float32)
+    for v in range(9):
+        rs = np.random.RandomState(1000 + v)
+        gain, bias = rs.uniform(0.8, 1.2), rs.uniform(-20.0, 20.0)
+        dx, dy = int(rs.randint(0, 4096)), int(rs.randint(0, 2048))
+        base = np.float32(gain * 200.0) * np.roll(T, (dy, dx), axis=(0, 1)) + np.float32(bias + 25.0)
+        for c in range(3):
+            ref[v, :, :, c] = np.clip(np.rint(base * tint[c]), 1, 255).astype(np.uint8)
+    assert zlib.crc32(a.tobytes()) == zlib.crc32(ref.tobytes())
